@@ -1,0 +1,136 @@
+/*
+ * pulpo_b200.h -- C ABI of libpulpo_b200.so: the B200 (sm_100a) implementation of PULPo's
+ * dense-3D registration hot path (warp, scaling-and-squaring, Laplacian-pyramid field
+ * combination, local NCC + KL (+ L2) losses, MC moments).
+ *
+ * The reference (leonardsiegert/PULPo) is pure Python and has no FFI; its "operator API"
+ * for this path is the constructor/forward signatures of a handful of nn.Modules and loss
+ * functions.  Each entry point below names the reference interface it replaces
+ * (path:line in the upstream repo).  INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *   - all tensors: contiguous fp32, layout [B, C, D0, D1, D2], D2 innermost; field channel a
+ *     displaces along spatial axis a, in voxels (src/network_blocks.py:94-103)
+ *   - every pointer is a DEVICE pointer owned by the caller (outputs and workspaces too);
+ *     the library never allocates device memory, never synchronises, keeps no mutable
+ *     global state and enqueues only on `stream` (a cudaStream_t passed as void*)
+ *   - return value: PULPO_OK (0) or a negative pulpo_status; no C++ exception crosses
+ *   - `*_ws_bytes` helpers are pure host arithmetic
+ */
+#ifndef PULPO_B200_H
+#define PULPO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PULPO_B200_VERSION 100 /* 0.1.0 */
+
+typedef void *pulpo_stream_t; /* cudaStream_t */
+
+typedef enum pulpo_status {
+    PULPO_OK = 0,
+    PULPO_ERR_NULL_POINTER = -1,
+    PULPO_ERR_INVALID_SHAPE = -2,
+    PULPO_ERR_UNSUPPORTED = -3,
+    PULPO_ERR_WORKSPACE = -4,
+    PULPO_ERR_CUDA = -5
+} pulpo_status;
+
+/* How the sample position is rounded.  Integer corner indices are
+ * bit-exact against torch-CPU in mode 0 and against torch-CUDA in mode 1. */
+#define PULPO_COORD_CPU_EXACT 0 /* loc/(S-1) true division; ((n+1)*S-1)/2 rounded op by op */
+#define PULPO_COORD_CUDA_RCP 1  /* loc*(1/(S-1)); fma(n+1, S, -1)/2 */
+
+int pulpo_version(void);
+const char *pulpo_strerror(int status);
+
+/* ---- a2: SpatialTransformer.forward(df, moving_image)   src/network_blocks.py:101-121 ----
+ * out[b,c,v] = trilinear sample of img[b,c] at p(v) = clamp(((2*((v+df)/(S-1)-.5)+1)*S-1)/2).
+ * idx_dbg (nullable): int32 [B,3,D0,D1,D2], floor(p) per axis (the bit-exact contract). */
+int pulpo_warp3d_fwd(const float *img, const float *df, float *out, int32_t *idx_dbg,
+                     int B, int C, int D0, int D1, int D2, int coord_mode, pulpo_stream_t stream);
+
+/* grid_sampler_3d_backward + the autograd chain of network_blocks.py:103-117.
+ * gimg (nullable): ACCUMULATED into with vector/scalar red.global.add -> caller zeroes it.
+ * gdf (nullable): overwritten; zero where the border clamp is active. */
+int pulpo_warp3d_bwd(const float *gout, const float *img, const float *df, float *gimg, float *gdf,
+                     int B, int C, int D0, int D1, int D2, int coord_mode, pulpo_stream_t stream);
+
+/* ---- a3: VecInt.forward(vec)   src/network_blocks.py:173-177 ------------------------------
+ * vec,out: [B,3,D0,D1,D2].  ws holds the integration states as [*,B,S] float4 (xyz + pad):
+ * save_steps=1 keeps v_0..v_{nsteps-1} for the backward (nsteps states), save_steps=0 needs
+ * two ping-pong states.  One cooperative launch runs all steps. */
+size_t pulpo_vecint_ws_bytes(int nsteps, int save_steps, int B, int D0, int D1, int D2);
+int pulpo_vecint_fwd(const float *vec, float *out, void *ws, size_t ws_bytes, int nsteps,
+                     int save_steps, int B, int D0, int D1, int D2, int coord_mode,
+                     pulpo_stream_t stream);
+/* gvec = d loss/d vec.  `saved` = the ws of a save_steps=1 forward; scratch: 3 states. */
+size_t pulpo_vecint_bwd_scratch_bytes(int B, int D0, int D1, int D2);
+int pulpo_vecint_bwd(const float *gout, const void *saved, float *gvec, void *scratch,
+                     size_t scratch_bytes, int nsteps, int B, int D0, int D1, int D2,
+                     int coord_mode, pulpo_stream_t stream);
+
+/* ---- a4 + a5: ResizeTransform.forward (factor>1) fused with DFAdder.forward ---------------
+ * src/network_blocks.py:138-150, :152-158; used at src/components/pulpo.py:308,314 and
+ * src/models.py:356-367.   out = trilinear_up_f(scale * x) (+ addend),  x: [B,C,d0,d1,d2],
+ * out/addend: [B,C,f*d0,f*d1,f*d2].  factor: integer >= 2.  addend nullable. */
+int pulpo_resize_up_fwd(const float *x, const float *addend, float *out, int factor, float scale,
+                        int B, int C, int d0, int d1, int d2, pulpo_stream_t stream);
+/* exact adjoint w.r.t. x in gather form (no atomics); gout: [B,C,f*d0,f*d1,f*d2] */
+int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, float scale,
+                        int B, int C, int d0, int d1, int d2, pulpo_stream_t stream);
+
+/* ---- a10: F.interpolate(y, size=..., trilinear, align_corners=False)  src/losses.py:313 --- */
+int pulpo_interp_size_fwd(const float *x, float *out, int B, int C, int i0, int i1, int i2,
+                          int o0, int o1, int o2, pulpo_stream_t stream);
+
+/* ---- a8: avg_pool3d(2, 2, ceil_mode=True)  src/components/pulpo.py:171-179 ---------------- */
+int pulpo_avgpool2_fwd(const float *x, float *out, int B, int C, int D0, int D1, int D2,
+                       pulpo_stream_t stream);
+
+/* ---- a9: NCC_loss(y_pred, y_true, win_size, gamma)   src/losses.py:85-135 ------------------
+ * loss (device scalar) = -gamma/B * sum cc.  abc (nullable): [3][B,C,S] coefficient volumes
+ * the backward box-filters.  win odd, 3..15.  ws: per-CTA partial sums. */
+size_t pulpo_ncc_ws_bytes(int B, int C, int D0, int D1, int D2);
+int pulpo_ncc_fwd(const float *pred, const float *target, float *loss, float *abc, void *ws,
+                  size_t ws_bytes, int win, float gamma, int B, int C, int D0, int D1, int D2,
+                  pulpo_stream_t stream);
+/* gpred = gloss * (-gamma/B) * (I*Box(a) + Box(b) + 2*J*Box(c)); gloss: device scalar (nullable = 1) */
+int pulpo_ncc_bwd(const float *abc, const float *pred, const float *target, const float *gloss,
+                  float *gpred, int win, float gamma, int B, int C, int D0, int D1, int D2,
+                  pulpo_stream_t stream);
+
+/* ---- a11: KL_two_gauss_with_diag_cov(mu0, sigma0, mu1, sigma1, eps)  src/losses.py:47-76 ---
+ * mu1/sigma1 nullable = the N(0,1) prior of src/components/pulpo.py:337-339.  n = C*D0*D1*D2. */
+size_t pulpo_reduce_ws_bytes(void);
+int pulpo_kl_diag_fwd(const float *mu0, const float *sigma0, const float *mu1, const float *sigma1,
+                      float eps, float *out, void *ws, size_t ws_bytes, int B, long long n,
+                      pulpo_stream_t stream);
+int pulpo_kl_diag_bwd(const float *gloss, const float *mu0, const float *sigma0, const float *mu1,
+                      const float *sigma1, float eps, float *gmu0, float *gsigma0, int B,
+                      long long n, pulpo_stream_t stream);
+
+/* ---- f-1: L2_reg(deformation_field, lamb)   src/losses.py:208-222 (3-D branch) ------------- */
+int pulpo_l2reg_fwd(const float *f, float lamb, float *out, void *ws, size_t ws_bytes,
+                    int B, int C, int D0, int D1, int D2, pulpo_stream_t stream);
+int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, float *gf,
+                    int B, int C, int D0, int D1, int D2, pulpo_stream_t stream);
+
+/* ---- f-3: per-voxel MC moments   evaluate.py:243-251 (std over samples) -------------------
+ * Streaming Welford update of (mean, M2) with one new sample x (count = samples so far,
+ * including this one), Chan merge of two partial states, and the unbiased std. */
+int pulpo_moments_update(const float *x, float *mean, float *m2, int count, long long n,
+                         pulpo_stream_t stream);
+int pulpo_moments_merge(float *mean_a, float *m2_a, int count_a, const float *mean_b,
+                        const float *m2_b, int count_b, long long n, pulpo_stream_t stream);
+int pulpo_moments_std(const float *m2, float *std_out, int count, long long n,
+                      pulpo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PULPO_B200_H */

@@ -1,0 +1,68 @@
+"""ctypes binding of libpulpo_b200.so (the C ABI declared in include/pulpo_b200.h).
+
+There is NO fallback: if the CUDA library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpulpo_b200.so")
+
+CPU_EXACT = 0   # PULPO_COORD_CPU_EXACT
+CUDA_RCP = 1    # PULPO_COORD_CUDA_RCP
+
+_vp, _i, _f, _sz, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_longlong
+
+# name -> (restype, argtypes); mirrors include/pulpo_b200.h one to one
+SIGNATURES = {
+    "pulpo_version": (_i, []),
+    "pulpo_strerror": (ctypes.c_char_p, [_i]),
+    "pulpo_warp3d_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_warp3d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_vecint_ws_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "pulpo_vecint_fwd": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_vecint_bwd_scratch_bytes": (_sz, [_i, _i, _i, _i]),
+    "pulpo_vecint_bwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_resize_up_fwd": (_i, [_vp, _vp, _vp, _i, _f, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_resize_up_bwd": (_i, [_vp, _vp, _i, _f, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_interp_size_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_avgpool2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_ncc_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "pulpo_ncc_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _f, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_ncc_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_reduce_ws_bytes": (_sz, []),
+    "pulpo_kl_diag_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _sz, _i, _ll, _vp]),
+    "pulpo_kl_diag_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _ll, _vp]),
+    "pulpo_l2reg_fwd": (_i, [_vp, _f, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_l2reg_bwd": (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_moments_update": (_i, [_vp, _vp, _vp, _i, _ll, _vp]),
+    "pulpo_moments_merge": (_i, [_vp, _vp, _i, _vp, _vp, _i, _ll, _vp]),
+    "pulpo_moments_std": (_i, [_vp, _vp, _i, _ll, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the library once.  Raises RuntimeError (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libpulpo_b200.so not found at %s -- build it with `python -m pulpo_b200.build` "
+                "(nvcc, sm_100a). pulpo_b200 has no CPU or PyTorch fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)   # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib().pulpo_strerror(status).decode()
+        raise RuntimeError("libpulpo_b200 %s failed: %s (status %d)" % (what, msg, status))

@@ -1,0 +1,188 @@
+// common.cuh -- shared device helpers for libpulpo_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pulpo_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libpulpo_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace pulpo {
+
+typedef long long i64;
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
+
+#define PULPO_REQUIRE(cond, code) \
+    do {                          \
+        if (!(cond)) return (code); \
+    } while (0)
+
+static inline int launch_status()
+{
+    return cudaPeekAtLastError() == cudaSuccess ? PULPO_OK : PULPO_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sample position of SpatialTransformer (src/network_blocks.py:103-107 + ATen unnormalise for
+// align_corners=False).  Every op is rounded separately with _rn intrinsics so the compiler can
+// neither contract to FMA nor replace the division by a reciprocal multiply: floor(p) must match
+// torch bit for bit.  MODE 1 reproduces what torch-CUDA does instead.
+struct AxisConst {
+    float S;     // float(S)
+    float Sm1;   // float(S-1)
+    float rcp;   // 1.0f / float(S-1)   (MODE 1)
+    float gmul;  // S/(S-1) chain for the backward: applied as ((m*g)*2)/(S-1) with m = S/2
+};
+
+__host__ __device__ inline AxisConst make_axis(int S)
+{
+    AxisConst a;
+    a.S = (float)S;
+    a.Sm1 = (float)(S - 1);
+    a.rcp = 1.0f / (float)(S - 1);
+    a.gmul = (float)S / 2.0f;
+    return a;
+}
+
+template <int MODE>
+__device__ __forceinline__ float sample_pos(int v, float d, const AxisConst &a)
+{
+    float loc = __fadd_rn((float)v, d);
+    float q = (MODE == PULPO_COORD_CPU_EXACT) ? __fdiv_rn(loc, a.Sm1) : __fmul_rn(loc, a.rcp);
+    float n = __fmul_rn(2.0f, __fsub_rn(q, 0.5f));
+    float t = (MODE == PULPO_COORD_CPU_EXACT) ? __fsub_rn(__fmul_rn(__fadd_rn(n, 1.0f), a.S), 1.0f)
+                                              : __fmaf_rn(__fadd_rn(n, 1.0f), a.S, -1.0f);
+    return __fmul_rn(t, 0.5f);  // "/ 2" is exact either way
+}
+
+// border padding: min(S-1, max(p, 0)) with std::max/std::min NaN behaviour
+__device__ __forceinline__ float clip_pos(float p, float Sm1)
+{
+    float lo = (p < 0.0f) ? 0.0f : p;
+    return (lo < Sm1) ? lo : Sm1;
+}
+
+// one axis of the trilinear footprint
+struct Tap {
+    int i;      // floor(p)
+    float w0;   // (i+1) - p
+    float w1;   // p - i
+    bool in1;   // i+1 is inside the volume
+};
+
+template <int MODE>
+__device__ __forceinline__ Tap make_tap(int v, float d, const AxisConst &a, int S, float *unclamped = nullptr)
+{
+    float u = sample_pos<MODE>(v, d, a);
+    if (unclamped) *unclamped = u;
+    float p = clip_pos(u, a.Sm1);
+    Tap t;
+    float fl = floorf(p);
+    t.i = (int)fl;
+    t.w0 = __fsub_rn(fl + 1.0f, p);
+    t.w1 = __fsub_rn(p, fl);
+    t.in1 = (t.i + 1 < S);
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum in double (result valid in thread 0).  smem: >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double *smem)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    v = warp_sum(v);
+    if (lane == 0) smem[wid] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (wid == 0) {
+        r = (lane < (nthreads + 31) / 32) ? smem[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+// Deterministic two-stage scalar reduction: every CTA deposits one double partial in the
+// caller's workspace; the last CTA to arrive (ticket counter, self-resetting) sums the
+// partials in a fixed order and writes `scale * sum` to *out as fp32.
+struct ReduceWs {
+    unsigned int ticket;
+    unsigned int pad[3];
+    double partial[1];  // [max_ctas]
+};
+constexpr int kMaxReduceCtas = 4096;
+constexpr size_t kReduceWsBytes = 16 + sizeof(double) * kMaxReduceCtas;
+
+__device__ __forceinline__ void grid_reduce_finish(double block_total, ReduceWs *ws, float *out, double scale,
+                                                   double *smem)
+{
+    __shared__ bool is_last;
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const int nctas = gridDim.x * gridDim.y * gridDim.z;
+    if (threadIdx.x == 0) {
+        ws->partial[cta] = block_total;
+        __threadfence();
+        unsigned int t = atomicAdd(&ws->ticket, 1u);
+        is_last = (t == (unsigned int)(nctas - 1));
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nctas; i += blockDim.x) s += ((volatile double *)ws->partial)[i];
+        s = block_sum(s, smem);
+        if (threadIdx.x == 0) {
+            *out = (float)(s * scale);
+            ws->ticket = 0;  // ready for the next launch on this workspace
+        }
+    }
+}
+
+// streaming (read-once) 128-bit load that does not pollute L1
+__device__ __forceinline__ float4 ld_stream4(const float *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// sm_90+ vector reduction: one 16-byte red instead of four scalar atomics
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
+static inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
+
+static inline int grid_for(i64 work_items, int threads, int max_ctas_per_sm = 8)
+{
+    i64 g = (work_items + threads - 1) / threads;
+    i64 cap = (i64)kSMs * max_ctas_per_sm;
+    if (g > cap) g = cap;  // grid-stride loops: whole waves of 148 SMs
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace pulpo

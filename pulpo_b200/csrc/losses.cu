@@ -1,0 +1,250 @@
+// losses.cu -- streaming scalar losses and MC moments:
+//   * KL_two_gauss_with_diag_cov       src/losses.py:47-76   (call order :271-273)
+//   * L2_reg (3-D branch)              src/losses.py:208-222
+//   * per-voxel Welford/Chan moments   evaluate.py:243-251 (std over MC samples)
+// Pure HBM streaming: 128-bit loads where alignment allows, warp-shuffle -> CTA -> deterministic
+// two-stage grid reduction in double for the scalars.
+#include "common.cuh"
+
+namespace pulpo {
+
+__device__ __forceinline__ float kl_term(float m0, float s0, float m1, float s1, float eps)
+{
+    const float v0 = __fmul_rn(s0, s0), v1 = __fmul_rn(s1, s1);
+    const float dm = __fsub_rn(m1, m0);
+    const float num = __fadd_rn(v0, __fmul_rn(dm, dm));
+    const float den = __fadd_rn(v1, eps);
+    float t = __fdiv_rn(num, den);
+    t = __fadd_rn(t, logf(den));
+    t = __fsub_rn(t, logf(__fadd_rn(v0, eps)));
+    return __fsub_rn(t, 1.0f);
+}
+
+__global__ void __launch_bounds__(256)
+kl_fwd_kernel(const float *__restrict__ mu0, const float *__restrict__ sg0, const float *__restrict__ mu1,
+              const float *__restrict__ sg1, float eps, float *out, ReduceWs *ws, double scale, i64 total, int vec)
+{
+    __shared__ double red[32];
+    float acc = 0.0f;
+    const i64 tid = blockIdx.x * (i64)blockDim.x + threadIdx.x, nthr = (i64)gridDim.x * blockDim.x;
+    if (vec) {
+        for (i64 i = tid * 4; i < total; i += nthr * 4) {
+            float4 m = ld_stream4(mu0 + i), s = ld_stream4(sg0 + i);
+            float4 m1 = mu1 ? ld_stream4(mu1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 s1 = sg1 ? ld_stream4(sg1 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+            float t = kl_term(m.x, s.x, m1.x, s1.x, eps);
+            t += kl_term(m.y, s.y, m1.y, s1.y, eps);
+            t += kl_term(m.z, s.z, m1.z, s1.z, eps);
+            t += kl_term(m.w, s.w, m1.w, s1.w, eps);
+            acc += t;
+        }
+    } else {
+        for (i64 i = tid; i < total; i += nthr)
+            acc += kl_term(mu0[i], sg0[i], mu1 ? mu1[i] : 0.0f, sg1 ? sg1[i] : 1.0f, eps);
+    }
+    double bt = block_sum((double)acc, red);
+    grid_reduce_finish(bt, ws, out, scale, red);
+}
+
+__global__ void __launch_bounds__(256)
+kl_bwd_kernel(const float *__restrict__ gloss, const float *__restrict__ mu0, const float *__restrict__ sg0,
+              const float *__restrict__ mu1, const float *__restrict__ sg1, float eps, float *__restrict__ gmu,
+              float *__restrict__ gsg, float invB, i64 total)
+{
+    const float k = (gloss ? __ldg(gloss) : 1.0f) * invB;
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+        const float s = sg0[i];
+        const float s1 = sg1 ? sg1[i] : 1.0f;
+        const float m1 = mu1 ? mu1[i] : 0.0f;
+        const float den = s1 * s1 + eps;
+        gmu[i] = k * (mu0[i] - m1) / den;
+        gsg[i] = k * (s / den - s / (s * s + eps));
+    }
+}
+
+// L2_reg: forward differences on the [1:,1:,1:] crop
+__global__ void __launch_bounds__(256)
+l2reg_fwd_kernel(const float *__restrict__ f, float *out, ReduceWs *ws, double scale, int BC, int D0, int D1, int D2)
+{
+    __shared__ double red[32];
+    const i64 sy = D2, sz = (i64)D1 * D2, S = (i64)D0 * sz, total = (i64)BC * S;
+    float acc = 0.0f;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < total; g += (i64)gridDim.x * blockDim.x) {
+        int x = (int)(g % D2);
+        i64 r = g / D2;
+        int y = (int)(r % D1);
+        int z = (int)((r / D1) % D0);
+        if (x == 0 || y == 0 || z == 0) continue;
+        const float c = __ldg(f + g);
+        const float a = c - __ldg(f + g - sz), b = c - __ldg(f + g - sy), d = c - __ldg(f + g - 1);
+        acc += a * a + b * b + d * d;
+    }
+    double bt = block_sum((double)acc, red);
+    grid_reduce_finish(bt, ws, out, scale, red);
+}
+
+// gradient in gather form: voxel v collects its own three differences (if v is in the crop)
+// minus the difference of each forward neighbour that is in the crop
+__global__ void __launch_bounds__(256)
+l2reg_bwd_kernel(const float *__restrict__ gloss, const float *__restrict__ f, float *__restrict__ gf, float kk,
+                 int BC, int D0, int D1, int D2)
+{
+    const i64 sy = D2, sz = (i64)D1 * D2, S = (i64)D0 * sz, total = (i64)BC * S;
+    const float k = (gloss ? __ldg(gloss) : 1.0f) * kk;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < total; g += (i64)gridDim.x * blockDim.x) {
+        int x = (int)(g % D2);
+        i64 r = g / D2;
+        int y = (int)(r % D1);
+        int z = (int)((r / D1) % D0);
+        const float c = __ldg(f + g);
+        float acc = 0.0f;
+        if (x > 0 && y > 0 && z > 0)
+            acc += (c - __ldg(f + g - sz)) + (c - __ldg(f + g - sy)) + (c - __ldg(f + g - 1));
+        if (z + 1 < D0 && y > 0 && x > 0) acc -= __ldg(f + g + sz) - c;
+        if (y + 1 < D1 && z > 0 && x > 0) acc -= __ldg(f + g + sy) - c;
+        if (x + 1 < D2 && z > 0 && y > 0) acc -= __ldg(f + g + 1) - c;
+        gf[g] = k * acc;
+    }
+}
+
+// Welford: count = number of samples including x
+__global__ void __launch_bounds__(256)
+moments_update_kernel(const float *__restrict__ x, float *__restrict__ mean, float *__restrict__ m2, float inv_count,
+                      int first, i64 n)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        if (first) {
+            mean[i] = v;
+            m2[i] = 0.0f;
+        } else {
+            const float mu = mean[i];
+            const float d = v - mu;
+            const float mu2 = mu + d * inv_count;
+            mean[i] = mu2;
+            m2[i] += d * (v - mu2);
+        }
+    }
+}
+
+// Chan pairwise merge of (mean_a, m2_a, na) with (mean_b, m2_b, nb) into a
+__global__ void __launch_bounds__(256)
+moments_merge_kernel(float *__restrict__ mean_a, float *__restrict__ m2_a, const float *__restrict__ mean_b,
+                     const float *__restrict__ m2_b, float wb, float wab, i64 n)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const float d = mean_b[i] - mean_a[i];
+        mean_a[i] += d * wb;              // nb / (na + nb)
+        m2_a[i] += m2_b[i] + d * d * wab;  // na * nb / (na + nb)
+    }
+}
+
+__global__ void __launch_bounds__(256)
+moments_std_kernel(const float *__restrict__ m2, float *__restrict__ out, float inv_nm1, i64 n)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        out[i] = sqrtf(m2[i] * inv_nm1);
+}
+
+}  // namespace pulpo
+
+using namespace pulpo;
+
+extern "C" size_t pulpo_reduce_ws_bytes(void) { return kReduceWsBytes; }
+
+extern "C" int pulpo_kl_diag_fwd(const float *mu0, const float *sigma0, const float *mu1, const float *sigma1,
+                                 float eps, float *out, void *ws, size_t ws_bytes, int B, long long n,
+                                 pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(mu0 && sigma0 && out && ws, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && n > 0, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(ws_bytes >= kReduceWsBytes, PULPO_ERR_WORKSPACE);
+    const i64 total = (i64)B * n;
+    bool al = aligned16(mu0) && aligned16(sigma0) && (!mu1 || aligned16(mu1)) && (!sigma1 || aligned16(sigma1));
+    int grid = grid_for((total + 3) / 4, 256, 4);
+    kl_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mu0, sigma0, mu1, sigma1, eps, out, (ReduceWs *)ws,
+                                                        0.5 / (double)B, total, (al && (total & 3) == 0) ? 1 : 0);
+    return launch_status();
+}
+
+extern "C" int pulpo_kl_diag_bwd(const float *gloss, const float *mu0, const float *sigma0, const float *mu1,
+                                 const float *sigma1, float eps, float *gmu0, float *gsigma0, int B, long long n,
+                                 pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(mu0 && sigma0 && gmu0 && gsigma0, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && n > 0, PULPO_ERR_INVALID_SHAPE);
+    const i64 total = (i64)B * n;
+    kl_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(gloss, mu0, sigma0, mu1, sigma1, eps, gmu0,
+                                                                        gsigma0, 1.0f / (float)B, total);
+    return launch_status();
+}
+
+extern "C" int pulpo_l2reg_fwd(const float *f, float lamb, float *out, void *ws, size_t ws_bytes, int B, int C,
+                               int D0, int D1, int D2, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(f && out && ws, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(ws_bytes >= kReduceWsBytes, PULPO_ERR_WORKSPACE);
+    const i64 total = (i64)B * C * D0 * D1 * D2;
+    const double cnt = (double)B * C * (D0 - 1) * (double)(D1 - 1) * (D2 - 1);
+    const double scale = (double)lamb * D0 * D1 * D2 / cnt;
+    l2reg_fwd_kernel<<<grid_for(total, 256, 4), 256, 0, (cudaStream_t)stream>>>(f, out, (ReduceWs *)ws, scale, B * C,
+                                                                              D0, D1, D2);
+    return launch_status();
+}
+
+extern "C" int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, float *gf, int B, int C, int D0,
+                               int D1, int D2, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(f && gf, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2, PULPO_ERR_INVALID_SHAPE);
+    const i64 total = (i64)B * C * D0 * D1 * D2;
+    const double cnt = (double)B * C * (D0 - 1) * (double)(D1 - 1) * (D2 - 1);
+    const float kk = (float)(2.0 * (double)lamb * D0 * D1 * D2 / cnt);
+    l2reg_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(gloss, f, gf, kk, B * C, D0, D1, D2);
+    return launch_status();
+}
+
+extern "C" int pulpo_moments_update(const float *x, float *mean, float *m2, int count, long long n,
+                                    pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(x && mean && m2, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(count >= 1 && n > 0, PULPO_ERR_INVALID_SHAPE);
+    moments_update_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, mean, m2, 1.0f / (float)count,
+                                                                            count == 1, n);
+    return launch_status();
+}
+
+extern "C" int pulpo_moments_merge(float *mean_a, float *m2_a, int count_a, const float *mean_b, const float *m2_b,
+                                   int count_b, long long n, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(mean_a && m2_a && mean_b && m2_b, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(count_a >= 0 && count_b >= 0 && count_a + count_b > 0 && n > 0, PULPO_ERR_INVALID_SHAPE);
+    const float tot = (float)(count_a + count_b);
+    moments_merge_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        mean_a, m2_a, mean_b, m2_b, (float)count_b / tot, (float)count_a * (float)count_b / tot, n);
+    return launch_status();
+}
+
+extern "C" int pulpo_moments_std(const float *m2, float *std_out, int count, long long n, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(m2 && std_out, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(count >= 2 && n > 0, PULPO_ERR_INVALID_SHAPE);
+    moments_std_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(m2, std_out, 1.0f / (float)(count - 1), n);
+    return launch_status();
+}
+
+extern "C" int pulpo_version(void) { return PULPO_B200_VERSION; }
+
+extern "C" const char *pulpo_strerror(int status)
+{
+    switch (status) {
+        case PULPO_OK: return "ok";
+        case PULPO_ERR_NULL_POINTER: return "null pointer for a required argument";
+        case PULPO_ERR_INVALID_SHAPE: return "invalid shape (sizes must be positive; warp axes need S >= 2)";
+        case PULPO_ERR_UNSUPPORTED: return "unsupported argument (window/factor/coord_mode/alignment)";
+        case PULPO_ERR_WORKSPACE: return "workspace too small or misaligned";
+        case PULPO_ERR_CUDA: return "CUDA launch error";
+        default: return "unknown status";
+    }
+}

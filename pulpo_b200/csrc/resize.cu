@@ -1,0 +1,188 @@
+// resize.cu -- Laplacian-pyramid plumbing:
+//   * ResizeTransform(factor>1) fused with DFAdder      src/network_blocks.py:138-158
+//   * its exact adjoint in gather form (no atomics)     (autograd of the above)
+//   * F.interpolate(size=...) target pyramid            src/losses.py:313
+//   * avg_pool3d(2,2,ceil_mode=True) moving pyramid     src/components/pulpo.py:171-179
+// All follow ATen's upsample_trilinear3d (align_corners=False) index/weight rules
+// (SURVEY.md 9.4).  HBM-bound: one thread per output voxel, D2 innermost -> coalesced
+// stores; the 8 input taps of neighbouring outputs share cache lines.
+#include "common.cuh"
+
+namespace pulpo {
+
+struct LinTap {
+    int i0, i1;
+    float l0, l1;
+};
+
+// ATen: src = max(0, scale*(o+0.5)-0.5); i0 = min(floor(src), n-1); l1 = clamp(src-i0, 0, 1)
+__device__ __forceinline__ LinTap lin_tap(int o, int n_in, int n_out, float scale)
+{
+    LinTap t;
+    if (n_in == n_out) {
+        t.i0 = o; t.i1 = o; t.l0 = 1.0f; t.l1 = 0.0f;
+        return t;
+    }
+    float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)o, 0.5f)), 0.5f);
+    src = src < 0.0f ? 0.0f : src;
+    int i = (int)floorf(src);
+    i = i > n_in - 1 ? n_in - 1 : i;
+    float lam = __fsub_rn(src, (float)i);
+    lam = fminf(fmaxf(lam, 0.0f), 1.0f);
+    t.i0 = i;
+    t.i1 = i + (i < n_in - 1 ? 1 : 0);
+    t.l1 = lam;
+    t.l0 = __fsub_rn(1.0f, lam);
+    return t;
+}
+
+// out[bc, z, y, x] = trilinear(premul * in) (+ addend)
+__global__ void __launch_bounds__(256)
+trilinear_fwd_kernel(const float *__restrict__ in, const float *__restrict__ addend, float *__restrict__ out,
+                     float premul, int BC, int i0n, int i1n, int i2n, int o0n, int o1n, int o2n, float s0, float s1,
+                     float s2)
+{
+    const i64 Si = (i64)i0n * i1n * i2n, So = (i64)o0n * o1n * o2n;
+    const i64 total = (i64)BC * So;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < total; g += (i64)gridDim.x * blockDim.x) {
+        int x = (int)(g % o2n);
+        i64 r = g / o2n;
+        int y = (int)(r % o1n);
+        r /= o1n;
+        int z = (int)(r % o0n);
+        int bc = (int)(r / o0n);
+        LinTap tz = lin_tap(z, i0n, o0n, s0), ty = lin_tap(y, i1n, o1n, s1), tx = lin_tap(x, i2n, o2n, s2);
+        const float *p = in + (i64)bc * Si;
+        const float *r00 = p + ((i64)tz.i0 * i1n + ty.i0) * i2n, *r01 = p + ((i64)tz.i0 * i1n + ty.i1) * i2n;
+        const float *r10 = p + ((i64)tz.i1 * i1n + ty.i0) * i2n, *r11 = p + ((i64)tz.i1 * i1n + ty.i1) * i2n;
+        float a00 = premul * __ldg(r00 + tx.i0) * tx.l0 + premul * __ldg(r00 + tx.i1) * tx.l1;
+        float a01 = premul * __ldg(r01 + tx.i0) * tx.l0 + premul * __ldg(r01 + tx.i1) * tx.l1;
+        float a10 = premul * __ldg(r10 + tx.i0) * tx.l0 + premul * __ldg(r10 + tx.i1) * tx.l1;
+        float a11 = premul * __ldg(r11 + tx.i0) * tx.l0 + premul * __ldg(r11 + tx.i1) * tx.l1;
+        float v = (a00 * ty.l0 + a01 * ty.l1) * tz.l0 + (a10 * ty.l0 + a11 * ty.l1) * tz.l1;
+        if (addend) v += __ldg(addend + g);
+        out[g] = v;
+    }
+}
+
+// weight with which output o (along one axis) reads input i
+__device__ __forceinline__ float adj_w(int o, int i, int n_in, int n_out, float scale)
+{
+    LinTap t = lin_tap(o, n_in, n_out, scale);
+    return (t.i0 == i ? t.l0 : 0.0f) + (t.i1 == i ? t.l1 : 0.0f);
+}
+
+// gx[bc, i] = scale * sum_o w(o -> i) * gout[bc, o]; each input voxel gathers from the <= 2f+2
+// outputs per axis whose footprint touches it.
+__global__ void __launch_bounds__(128)
+upsample_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gx, int f, float scale, int BC, int d0,
+                    int d1, int d2)
+{
+    const int o0n = f * d0, o1n = f * d1, o2n = f * d2;
+    const float s = 1.0f / (float)f;
+    const i64 Si = (i64)d0 * d1 * d2, So = (i64)o0n * o1n * o2n;
+    const i64 total = (i64)BC * Si;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < total; g += (i64)gridDim.x * blockDim.x) {
+        int x = (int)(g % d2);
+        i64 r = g / d2;
+        int y = (int)(r % d1);
+        r /= d1;
+        int z = (int)(r % d0);
+        int bc = (int)(r / d0);
+        const float *go = gout + (i64)bc * So;
+        const int zl = max(0, f * z - f / 2 - 1), zh = min(o0n - 1, f * z + (3 * f) / 2);
+        const int yl = max(0, f * y - f / 2 - 1), yh = min(o1n - 1, f * y + (3 * f) / 2);
+        const int xl = max(0, f * x - f / 2 - 1), xh = min(o2n - 1, f * x + (3 * f) / 2);
+        float acc = 0.0f;
+        for (int oz = zl; oz <= zh; ++oz) {
+            float wz = adj_w(oz, z, d0, o0n, s);
+            if (wz == 0.0f) continue;
+            float accy = 0.0f;
+            for (int oy = yl; oy <= yh; ++oy) {
+                float wy = adj_w(oy, y, d1, o1n, s);
+                if (wy == 0.0f) continue;
+                const float *row = go + ((i64)oz * o1n + oy) * o2n;
+                float accx = 0.0f;
+                for (int ox = xl; ox <= xh; ++ox) accx += adj_w(ox, x, d2, o2n, s) * __ldg(row + ox);
+                accy += wy * accx;
+            }
+            acc += wz * accy;
+        }
+        gx[g] = scale * acc;
+    }
+}
+
+// avg_pool3d(kernel 2, stride 2, pad 0, ceil_mode=True): clipped windows, divide by clipped count
+__global__ void __launch_bounds__(256)
+avgpool2_kernel(const float *__restrict__ in, float *__restrict__ out, int BC, int D0, int D1, int D2)
+{
+    const int o0 = (D0 + 1) / 2, o1 = (D1 + 1) / 2, o2 = (D2 + 1) / 2;
+    const i64 Si = (i64)D0 * D1 * D2, So = (i64)o0 * o1 * o2, total = (i64)BC * So;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < total; g += (i64)gridDim.x * blockDim.x) {
+        int x = (int)(g % o2);
+        i64 r = g / o2;
+        int y = (int)(r % o1);
+        r /= o1;
+        int z = (int)(r % o0);
+        int bc = (int)(r / o0);
+        const int z1 = min(2 * z + 2, D0), y1 = min(2 * y + 2, D1), x1 = min(2 * x + 2, D2);
+        float s = 0.0f;
+        for (int a = 2 * z; a < z1; ++a)
+            for (int b = 2 * y; b < y1; ++b)
+                for (int c = 2 * x; c < x1; ++c) s += __ldg(in + (i64)bc * Si + ((i64)a * D1 + b) * D2 + c);
+        int cnt = (z1 - 2 * z) * (y1 - 2 * y) * (x1 - 2 * x);
+        out[g] = __fdiv_rn(s, (float)cnt);
+    }
+}
+
+}  // namespace pulpo
+
+using namespace pulpo;
+
+extern "C" int pulpo_resize_up_fwd(const float *x, const float *addend, float *out, int factor, float scale, int B,
+                                   int C, int d0, int d1, int d2, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(x && out, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && C > 0 && d0 > 0 && d1 > 0 && d2 > 0, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(factor >= 2 && factor <= 64, PULPO_ERR_UNSUPPORTED);
+    float s = (float)(1.0 / (double)factor);
+    i64 total = (i64)B * C * d0 * d1 * d2 * factor * factor * factor;
+    trilinear_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, addend, out, scale, B * C, d0, d1, d2, factor * d0, factor * d1, factor * d2, s, s, s);
+    return launch_status();
+}
+
+extern "C" int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, float scale, int B, int C, int d0,
+                                   int d1, int d2, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(gout && gx, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && C > 0 && d0 > 0 && d1 > 0 && d2 > 0, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(factor >= 2 && factor <= 64, PULPO_ERR_UNSUPPORTED);
+    i64 total = (i64)B * C * d0 * d1 * d2;
+    upsample_bwd_kernel<<<grid_for(total, 128, 16), 128, 0, (cudaStream_t)stream>>>(gout, gx, factor, scale, B * C,
+                                                                                  d0, d1, d2);
+    return launch_status();
+}
+
+extern "C" int pulpo_interp_size_fwd(const float *x, float *out, int B, int C, int i0, int i1, int i2, int o0,
+                                     int o1, int o2, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(x && out, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && C > 0 && i0 > 0 && i1 > 0 && i2 > 0 && o0 > 0 && o1 > 0 && o2 > 0,
+                  PULPO_ERR_INVALID_SHAPE);
+    i64 total = (i64)B * C * o0 * o1 * o2;
+    trilinear_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, nullptr, out, 1.0f, B * C, i0, i1, i2, o0, o1, o2, (float)i0 / (float)o0, (float)i1 / (float)o1,
+        (float)i2 / (float)o2);
+    return launch_status();
+}
+
+extern "C" int pulpo_avgpool2_fwd(const float *x, float *out, int B, int C, int D0, int D1, int D2,
+                                  pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(x && out, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && C > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
+    i64 total = (i64)B * C * ((D0 + 1) / 2) * ((D1 + 1) / 2) * ((D2 + 1) / 2);
+    avgpool2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B * C, D0, D1, D2);
+    return launch_status();
+}

@@ -1,0 +1,344 @@
+"""torch.autograd wrappers over the C ABI (include/pulpo_b200.h).
+
+Every function takes/returns CUDA fp32 tensors laid out [B,C,D0,D1,D2]; tensors are made
+contiguous here, all memory (outputs, saved states, workspaces) is allocated by torch and
+passed down as raw pointers, and kernels are enqueued on torch's current stream.  There is no
+CPU path: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import CPU_EXACT, CUDA_RCP, check  # noqa: F401
+
+_vp = ctypes.c_void_p
+
+
+def _ptr(t):
+    return None if t is None else _vp(t.data_ptr())
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _prep(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("pulpo_b200: %s must be a CUDA tensor (there is no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("pulpo_b200: %s must be float32, got %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _dims5(t, name):
+    if t.dim() != 5:
+        raise NotImplementedError("pulpo_b200: %s must be [B,C,D0,D1,D2] (only ndims == 3 is implemented)" % name)
+    return tuple(int(s) for s in t.shape)
+
+
+# reduction workspaces: tiny, zero-initialised once, self-resetting; one per (device, stream)
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+# ----------------------------------------------------------------------------- warp (a2)
+class _Warp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, df, img, coord_mode):
+        df, img = _prep(df, "df"), _prep(img, "moving_image")
+        B, C, D0, D1, D2 = _dims5(img, "moving_image")
+        if tuple(df.shape) != (B, 3, D0, D1, D2):
+            raise RuntimeError("pulpo_b200: df must be [B,3,*size] matching moving_image, got %s vs %s"
+                               % (tuple(df.shape), tuple(img.shape)))
+        out = torch.empty_like(img)
+        check(_lib.lib().pulpo_warp3d_fwd(_ptr(img), _ptr(df), _ptr(out), None, B, C, D0, D1, D2, coord_mode,
+                                          _stream()), "warp3d_fwd")
+        ctx.save_for_backward(df, img)
+        ctx.coord_mode = coord_mode
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        df, img = ctx.saved_tensors
+        gout = _prep(gout, "grad_output")
+        B, C, D0, D1, D2 = img.shape
+        need_df, need_img = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gdf = torch.empty_like(df) if need_df else None
+        gimg = torch.zeros_like(img) if need_img else None
+        if need_df or need_img:
+            check(_lib.lib().pulpo_warp3d_bwd(_ptr(gout), _ptr(img), _ptr(df), _ptr(gimg), _ptr(gdf), B, C, D0, D1,
+                                              D2, ctx.coord_mode, _stream()), "warp3d_bwd")
+        return gdf, gimg, None
+
+
+def warp(df, moving_image, coord_mode=CPU_EXACT):
+    """SpatialTransformer.forward (src/network_blocks.py:101-121)."""
+    return _Warp.apply(df, moving_image, coord_mode)
+
+
+def warp_indices(df, moving_image, coord_mode=CPU_EXACT):
+    """Warp + the int32 floor(p) corner indices [B,3,D0,D1,D2] (bit-exact parity contract)."""
+    df, img = _prep(df, "df"), _prep(moving_image, "moving_image")
+    B, C, D0, D1, D2 = _dims5(img, "moving_image")
+    out = torch.empty_like(img)
+    idx = torch.empty((B, 3, D0, D1, D2), dtype=torch.int32, device=img.device)
+    check(_lib.lib().pulpo_warp3d_fwd(_ptr(img), _ptr(df), _ptr(out), _ptr(idx), B, C, D0, D1, D2, coord_mode,
+                                      _stream()), "warp3d_fwd")
+    return out, idx
+
+
+# ----------------------------------------------------------------------------- VecInt (a3)
+class _VecInt(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vec, nsteps, coord_mode):
+        vec = _prep(vec, "vec")
+        B, C, D0, D1, D2 = _dims5(vec, "vec")
+        if C != 3:
+            raise RuntimeError("pulpo_b200: VecInt expects a 3-channel field, got C=%d" % C)
+        save = 1 if (ctx.needs_input_grad[0] and torch.is_grad_enabled()) else 0
+        L = _lib.lib()
+        nbytes = L.pulpo_vecint_ws_bytes(nsteps, save, B, D0, D1, D2)
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=vec.device)
+        out = torch.empty_like(vec)
+        check(L.pulpo_vecint_fwd(_ptr(vec), _ptr(out), _ptr(ws), nbytes, nsteps, save, B, D0, D1, D2, coord_mode,
+                                 _stream()), "vecint_fwd")
+        ctx.nsteps, ctx.coord_mode, ctx.dims = nsteps, coord_mode, (B, D0, D1, D2)
+        if save:
+            ctx.save_for_backward(ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (ws,) = ctx.saved_tensors
+        gout = _prep(gout, "grad_output")
+        B, D0, D1, D2 = ctx.dims
+        L = _lib.lib()
+        nbytes = L.pulpo_vecint_bwd_scratch_bytes(B, D0, D1, D2)
+        scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=gout.device)
+        gvec = torch.empty_like(gout)
+        check(L.pulpo_vecint_bwd(_ptr(gout), _ptr(ws), _ptr(gvec), _ptr(scratch), nbytes, ctx.nsteps, B, D0, D1, D2,
+                                 ctx.coord_mode, _stream()), "vecint_bwd")
+        return gvec, None, None
+
+
+def vecint(vec, nsteps=7, coord_mode=CPU_EXACT):
+    """VecInt.forward (src/network_blocks.py:173-177)."""
+    return _VecInt.apply(vec, nsteps, coord_mode)
+
+
+# ----------------------------------------------------------------------------- resize (a4, a5)
+class _ResizeUp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, addend, factor, scale):
+        x = _prep(x, "x")
+        B, C, d0, d1, d2 = _dims5(x, "x")
+        oshape = (B, C, factor * d0, factor * d1, factor * d2)
+        if addend is not None:
+            addend = _prep(addend, "addend")
+            if tuple(addend.shape) != oshape:
+                raise RuntimeError("pulpo_b200: cannot add fields of shape %s and %s" % (oshape, tuple(addend.shape)))
+        out = torch.empty(oshape, dtype=torch.float32, device=x.device)
+        check(_lib.lib().pulpo_resize_up_fwd(_ptr(x), _ptr(addend), _ptr(out), factor, float(scale), B, C, d0, d1,
+                                             d2, _stream()), "resize_up_fwd")
+        ctx.factor, ctx.scale, ctx.idims = factor, float(scale), (B, C, d0, d1, d2)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        gout = _prep(gout, "grad_output")
+        gx = None
+        if ctx.needs_input_grad[0]:
+            B, C, d0, d1, d2 = ctx.idims
+            gx = torch.empty(ctx.idims, dtype=torch.float32, device=gout.device)
+            check(_lib.lib().pulpo_resize_up_bwd(_ptr(gout), _ptr(gx), ctx.factor, ctx.scale, B, C, d0, d1, d2,
+                                                 _stream()), "resize_up_bwd")
+        return gx, (gout if ctx.needs_input_grad[1] else None), None, None
+
+
+def resize_up(x, factor, scale=None, addend=None):
+    """ResizeTransform.forward for integer factor>1 (value scale + trilinear up-sampling),
+    optionally fused with DFAdder (src/network_blocks.py:138-158)."""
+    return _ResizeUp.apply(x, addend, int(factor), float(factor if scale is None else scale))
+
+
+def interp_to_size(x, size):
+    """F.interpolate(x, size=size, mode='trilinear', align_corners=False) -- src/losses.py:313.
+    Used on the fixed image (no gradient)."""
+    x = _prep(x.detach(), "x")
+    B, C, i0, i1, i2 = _dims5(x, "x")
+    o0, o1, o2 = (int(s) for s in size)
+    if (o0, o1, o2) == (i0, i1, i2):
+        return x
+    out = torch.empty((B, C, o0, o1, o2), dtype=torch.float32, device=x.device)
+    check(_lib.lib().pulpo_interp_size_fwd(_ptr(x), _ptr(out), B, C, i0, i1, i2, o0, o1, o2, _stream()),
+          "interp_size_fwd")
+    return out
+
+
+def avgpool2(x):
+    """avg_pool3d(x, 2, 2, 0, ceil_mode=True) -- src/components/pulpo.py:174,177 (no gradient)."""
+    x = _prep(x.detach(), "x")
+    B, C, D0, D1, D2 = _dims5(x, "x")
+    out = torch.empty((B, C, (D0 + 1) // 2, (D1 + 1) // 2, (D2 + 1) // 2), dtype=torch.float32, device=x.device)
+    check(_lib.lib().pulpo_avgpool2_fwd(_ptr(x), _ptr(out), B, C, D0, D1, D2, _stream()), "avgpool2_fwd")
+    return out
+
+
+# ----------------------------------------------------------------------------- NCC (a9)
+class _NCC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, win, gamma):
+        pred, target = _prep(pred, "y_pred"), _prep(target, "y_true")
+        B, C, D0, D1, D2 = _dims5(pred, "y_pred")
+        if target.shape != pred.shape:
+            raise RuntimeError("pulpo_b200: NCC inputs differ in shape: %s vs %s" % (tuple(pred.shape), tuple(target.shape)))
+        L = _lib.lib()
+        need = ctx.needs_input_grad[0] and torch.is_grad_enabled()
+        abc = torch.empty((3,) + tuple(pred.shape), dtype=torch.float32, device=pred.device) if need else None
+        nbytes = L.pulpo_ncc_ws_bytes(B, C, D0, D1, D2)
+        ws = _workspace(nbytes, pred.device)
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        check(L.pulpo_ncc_fwd(_ptr(pred), _ptr(target), _ptr(loss), _ptr(abc), _ptr(ws), ws.numel(), int(win),
+                              float(gamma), B, C, D0, D1, D2, _stream()), "ncc_fwd")
+        ctx.win, ctx.gamma = int(win), float(gamma)
+        if need:
+            ctx.save_for_backward(abc, pred, target)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        abc, pred, target = ctx.saved_tensors
+        B, C, D0, D1, D2 = pred.shape
+        gloss = gloss.to(torch.float32).contiguous()
+        gpred = torch.empty_like(pred)
+        check(_lib.lib().pulpo_ncc_bwd(_ptr(abc), _ptr(pred), _ptr(target), _ptr(gloss), _ptr(gpred), ctx.win,
+                                       ctx.gamma, B, C, D0, D1, D2, _stream()), "ncc_bwd")
+        return gpred, None, None, None
+
+
+def ncc_loss(y_pred, y_true, win_size=9, gamma=0.05):
+    """NCC_loss (src/losses.py:85-135).  Differentiable w.r.t. y_pred only (the fixed image
+    never needs a gradient on this path)."""
+    if y_true.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("pulpo_b200: NCC gradient w.r.t. y_true is not implemented (never needed: "
+                                  "y_true is the fixed image)")
+    return _NCC.apply(y_pred, y_true, win_size, gamma)
+
+
+# ----------------------------------------------------------------------------- KL (a11)
+def _const_value(t):
+    """value of an expanded (all strides 0) constant tensor, else None"""
+    if t is None:
+        return None
+    if t.numel() > 0 and all(s == 0 for s in t.stride()):
+        return float(t.reshape(-1)[0])
+    return None
+
+
+class _KL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu0, sigma0, mu1, sigma1, eps):
+        mu0, sigma0 = _prep(mu0, "mu0"), _prep(sigma0, "sigma0")
+        mu1 = None if mu1 is None else _prep(mu1, "mu1")
+        sigma1 = None if sigma1 is None else _prep(sigma1, "sigma1")
+        B = int(mu0.shape[0])
+        n = mu0.numel() // B
+        L = _lib.lib()
+        ws = _workspace(L.pulpo_reduce_ws_bytes(), mu0.device)
+        out = torch.empty((), dtype=torch.float32, device=mu0.device)
+        check(L.pulpo_kl_diag_fwd(_ptr(mu0), _ptr(sigma0), _ptr(mu1), _ptr(sigma1), float(eps), _ptr(out), _ptr(ws),
+                                  ws.numel(), B, n, _stream()), "kl_diag_fwd")
+        ctx.eps, ctx.B, ctx.n = float(eps), B, n
+        ctx.have1 = (mu1 is not None, sigma1 is not None)
+        ctx.save_for_backward(mu0, sigma0, *[t for t in (mu1, sigma1) if t is not None])
+        return out
+
+    @staticmethod
+    def backward(ctx, gloss):
+        saved = list(ctx.saved_tensors)
+        mu0, sigma0 = saved[0], saved[1]
+        rest = saved[2:]
+        mu1 = rest.pop(0) if ctx.have1[0] else None
+        sigma1 = rest.pop(0) if ctx.have1[1] else None
+        gloss = gloss.to(torch.float32).contiguous()
+        gmu, gsg = torch.empty_like(mu0), torch.empty_like(sigma0)
+        check(_lib.lib().pulpo_kl_diag_bwd(_ptr(gloss), _ptr(mu0), _ptr(sigma0), _ptr(mu1), _ptr(sigma1), ctx.eps,
+                                           _ptr(gmu), _ptr(gsg), ctx.B, ctx.n, _stream()), "kl_diag_bwd")
+        return gmu, gsg, None, None, None
+
+
+def kl_diag(mu0, sigma0, mu1, sigma1, eps=1e-10):
+    """KL_two_gauss_with_diag_cov (src/losses.py:47-76): KL[p0 || p1], differentiable w.r.t. p0.
+    Expanded constant priors (mu1 == 0, sigma1 == 1 with stride 0) take the N(0,1) fast path."""
+    for t in (mu1, sigma1):
+        if t is not None and t.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("pulpo_b200: KL gradient w.r.t. the second distribution is not implemented "
+                                      "(the prior is constant on this path, src/components/pulpo.py:337-339)")
+    if _const_value(mu1) == 0.0:
+        mu1 = None
+    if _const_value(sigma1) == 1.0:
+        sigma1 = None
+    return _KL.apply(mu0, sigma0, mu1, sigma1, eps)
+
+
+# ----------------------------------------------------------------------------- L2 reg (f-1)
+class _L2Reg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, lamb):
+        f = _prep(f, "deformation_field")
+        B, C, D0, D1, D2 = _dims5(f, "deformation_field")
+        L = _lib.lib()
+        ws = _workspace(L.pulpo_reduce_ws_bytes(), f.device)
+        out = torch.empty((), dtype=torch.float32, device=f.device)
+        check(L.pulpo_l2reg_fwd(_ptr(f), float(lamb), _ptr(out), _ptr(ws), ws.numel(), B, C, D0, D1, D2, _stream()),
+              "l2reg_fwd")
+        ctx.lamb = float(lamb)
+        ctx.save_for_backward(f)
+        return out
+
+    @staticmethod
+    def backward(ctx, gloss):
+        (f,) = ctx.saved_tensors
+        B, C, D0, D1, D2 = f.shape
+        gloss = gloss.to(torch.float32).contiguous()
+        gf = torch.empty_like(f)
+        check(_lib.lib().pulpo_l2reg_bwd(_ptr(gloss), _ptr(f), ctx.lamb, _ptr(gf), B, C, D0, D1, D2, _stream()),
+              "l2reg_bwd")
+        return gf, None
+
+
+def l2_reg(deformation_field, lamb=0.0):
+    """L2_reg (src/losses.py:208-222), 3-D branch."""
+    return _L2Reg.apply(deformation_field, lamb)
+
+
+# ----------------------------------------------------------------------------- MC moments (f-3)
+def moments_update(x, mean, m2, count):
+    """Welford update of per-voxel (mean, M2) with sample x; count includes x."""
+    x = _prep(x, "x")
+    check(_lib.lib().pulpo_moments_update(_ptr(x), _ptr(mean), _ptr(m2), int(count), x.numel(), _stream()),
+          "moments_update")
+
+
+def moments_merge(mean_a, m2_a, count_a, mean_b, m2_b, count_b):
+    """Chan merge of two partial states into (mean_a, m2_a)."""
+    check(_lib.lib().pulpo_moments_merge(_ptr(mean_a), _ptr(m2_a), int(count_a), _ptr(mean_b), _ptr(m2_b),
+                                         int(count_b), mean_a.numel(), _stream()), "moments_merge")
+
+
+def moments_std(m2, count):
+    """Unbiased per-voxel std (torch.std(axis=0) of evaluate.py:243-251)."""
+    out = torch.empty_like(m2)
+    check(_lib.lib().pulpo_moments_std(_ptr(m2), _ptr(out), int(count), m2.numel(), _stream()), "moments_std")
+    return out

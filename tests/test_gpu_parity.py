@@ -1,0 +1,254 @@
+"""Parity of the CUDA path (through the C ABI) against the reference: committed golden
+fixtures (outputs of the real reference, tests/golden) and the plain-C oracle on seeded
+inputs.  Bit-exact for sampling indices; north_star tolerances for floating point."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import FIELD_ATOL, assert_close, assert_grad_close, assert_loss_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def PF():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from pulpo_b200 import functional
+    return functional
+
+
+def dev(a, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.requires_grad_(True) if grad else t
+
+
+# ----------------------------------------------------------------------------- warp (a2)
+@pytest.mark.parametrize("case", ["warp_c1", "warp_c3", "warp_c5_big", "warp_adversarial"])
+def test_warp_golden(PF, case):
+    from oracle import cport
+    g = load_golden(case)
+    df, img = dev(g["df"], True), dev(g["img"], True)
+    out = PF.warp(df, img)
+    # forward arithmetic follows the CPU grid sampler op for op -> identical bits expected
+    assert np.array_equal(out.detach().cpu().numpy(), g["out"]), \
+        "warp fwd not bit-identical: max-abs %.3e" % np.abs(out.detach().cpu().numpy() - g["out"]).max()
+    assert_close(out.detach().cpu().numpy(), g["out"], FIELD_ATOL, case + " out")
+    out.backward(dev(g["gout"]))
+    assert_grad_close(df.grad.cpu().numpy(), g["gdf"], case + " gdf")
+    assert_grad_close(img.grad.cpu().numpy(), g["gimg"], case + " gimg")
+    # integer sampling indices: bit-exact against the oracle (itself bit-identical to torch-CPU outputs)
+    _, idx = PF.warp_indices(dev(g["df"]), dev(g["img"]))
+    _, idx_ref = cport.warp3d_fwd(g["df"], g["img"], want_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), idx_ref), "%d index mismatches" % (idx.cpu().numpy() != idx_ref).sum()
+
+
+def test_warp_indices_seeded_vs_oracle(PF):
+    from oracle import cport
+    from pulpo_b200 import synthetic as syn
+    shape = (40, 48, 56)
+    for seed, amp in [(0, 3.0), (1, 40.0), (2, 0.01)]:
+        df = syn.make_field(shape, seed, max_abs=amp)
+        img = syn.make_field(shape, 50 + seed, max_abs=1.0, channels=2)
+        out, idx = PF.warp_indices(df.cuda(), img.cuda())
+        out_ref, idx_ref = cport.warp3d_fwd(df.numpy(), img.numpy(), want_idx=True)
+        assert np.array_equal(idx.cpu().numpy(), idx_ref)
+        assert np.array_equal(out.cpu().numpy(), out_ref)
+        out4 = PF.warp(df.cuda(), img.cuda())   # vectorised kernel variant
+        assert np.array_equal(out4.cpu().numpy(), out_ref)
+
+
+def test_warp_cuda_rcp_mode_matches_oracle_mode1(PF):
+    from oracle import cport
+    from pulpo_b200 import synthetic as syn
+    shape = (20, 24, 28)
+    df = syn.make_field(shape, 3, max_abs=5.0)
+    img = syn.make_field(shape, 4, max_abs=1.0, channels=1)
+    _, idx = PF.warp_indices(df.cuda(), img.cuda(), coord_mode=PF.CUDA_RCP)
+    _, idx_ref = cport.warp3d_fwd(df.numpy(), img.numpy(), mode=cport.CUDA_RCP, want_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), idx_ref)
+
+
+# ----------------------------------------------------------------------------- VecInt (a3)
+@pytest.mark.parametrize("case", ["vecint_small", "vecint_large_disp"])
+def test_vecint_golden(PF, case):
+    g = load_golden(case)
+    vec = dev(g["vec"], True)
+    out = PF.vecint(vec, 7)
+    assert np.array_equal(out.detach().cpu().numpy(), g["out"]), \
+        "vecint fwd not bit-identical: max-abs %.3e" % np.abs(out.detach().cpu().numpy() - g["out"]).max()
+    out.backward(dev(g["gout"]))
+    assert_grad_close(vec.grad.cpu().numpy(), g["gvec"], case + " gvec")
+    with torch.no_grad():   # ping-pong (no saved states) variant
+        out2 = PF.vecint(dev(g["vec"]), 7)
+    assert np.array_equal(out2.cpu().numpy(), g["out"])
+
+
+def test_vecint_zero_steps_and_zero_field(PF):
+    v = torch.randn(1, 3, 6, 8, 10, device="cuda")
+    assert torch.equal(PF.vecint(v, 0), v)
+    z = torch.zeros(1, 3, 6, 8, 12, device="cuda")
+    out = PF.vecint(z, 7)
+    # zero velocity is NOT the identity in the reference (p = v*S/(S-1) - 0.5), but v=0 stays 0
+    assert torch.equal(out, z)
+
+
+# ----------------------------------------------------------------------------- resize / combine (a4, a5)
+def test_combine_up2_golden(PF):
+    g = load_golden("combine_up2")
+    lo, ind = dev(g["lower"], True), dev(g["indiv"], True)
+    out = PF.resize_up(lo, 2, 2.0, addend=ind)
+    assert_close(out.detach().cpu().numpy(), g["out"], FIELD_ATOL, "combine out")
+    out.backward(dev(g["gout"]))
+    assert_grad_close(lo.grad.cpu().numpy(), g["glower"], "combine glower")
+    assert_grad_close(ind.grad.cpu().numpy(), g["gindiv"], "combine gindiv")
+
+
+@pytest.mark.parametrize("f", [2, 4, 8])
+def test_resize_up_golden(PF, f):
+    from pulpo_b200.network_blocks import ResizeTransform
+    g = load_golden("resize_up%d" % f)
+    x = dev(g["x"], True)
+    out = ResizeTransform(1 / f, 3)(x)
+    assert_close(out.detach().cpu().numpy(), g["out"], FIELD_ATOL, "resize out")
+    out.backward(dev(g["gout"]))
+    assert_grad_close(x.grad.cpu().numpy(), g["gx"], "resize gx")
+
+
+def test_resize_factor_one_is_noop(PF):
+    from pulpo_b200.network_blocks import ResizeTransform
+    x = torch.randn(1, 3, 4, 5, 6, device="cuda")
+    assert ResizeTransform(1.0, 3)(x) is x
+
+
+# ----------------------------------------------------------------------------- pyramids (a8, a10)
+def test_target_pyramid_golden(PF):
+    g = load_golden("target_pyramid")
+    y = dev(g["y"])
+    for i in range(5):
+        out = PF.interp_to_size(y, tuple(int(s) for s in g["size%d" % i]))
+        assert_close(out.cpu().numpy(), g["out%d" % i], 1e-6, "target pyramid %d" % i)
+
+
+def test_avgpool2_golden(PF):
+    g = load_golden("avgpool2")
+    assert_close(PF.avgpool2(dev(g["x_even"])).cpu().numpy(), g["out_even"], 1e-6, "avgpool even")
+    assert_close(PF.avgpool2(dev(g["x_odd"])).cpu().numpy(), g["out_odd"], 1e-6, "avgpool odd (ceil_mode)")
+
+
+# ----------------------------------------------------------------------------- NCC (a9)
+@pytest.mark.parametrize("win", [9, 7, 5, 3])
+def test_ncc_golden(PF, win):
+    g = load_golden("ncc")
+    pred, target = dev(g["pred"], True), dev(g["target"])
+    loss = PF.ncc_loss(pred, target, win, 0.05)
+    assert_loss_close(loss.item(), g["loss_w%d" % win], "ncc loss w=%d" % win)
+    loss.backward()
+    assert_grad_close(pred.grad.cpu().numpy(), g["gpred_w%d" % win], "ncc grad w=%d" % win)
+
+
+def test_ncc_vs_oracle_midsize_ragged(PF):
+    from oracle import cport
+    from pulpo_b200 import synthetic as syn
+    # sizes that are not multiples of the CTA tile (32 x 16) and span several z-chunks
+    x, y = syn.make_pair((70, 45, 83), 5, batch=1)
+    for win in (9, 3):
+        p = x.cuda().requires_grad_(True)
+        loss = PF.ncc_loss(p, y.cuda(), win, 0.05)
+        loss.backward()
+        ref, gref = cport.ncc(x.numpy(), y.numpy(), win, 0.05, want_grad=True)
+        assert_loss_close(loss.item(), ref, "ncc ragged w=%d" % win)
+        assert_grad_close(p.grad.cpu().numpy(), gref, "ncc ragged grad w=%d" % win)
+
+
+# ----------------------------------------------------------------------------- KL (a11) / L2 (f-1)
+def test_kl_golden(PF):
+    g = load_golden("kl_diag")
+    for tag, m1, s1 in [("std", np.zeros_like(g["mu0"]), np.ones_like(g["sigma0"])), ("gen", g["mu1"], g["sigma1"])]:
+        mu, sg = dev(g["mu0"], True), dev(g["sigma0"], True)
+        kl = PF.kl_diag(mu, sg, dev(m1), dev(s1))
+        assert_loss_close(kl.item(), g["kl_" + tag], "kl " + tag)
+        kl.backward()
+        assert_grad_close(mu.grad.cpu().numpy(), g["gmu0_" + tag], "kl gmu " + tag)
+        assert_grad_close(sg.grad.cpu().numpy(), g["gsigma0_" + tag], "kl gsigma " + tag)
+    # N(0,1) fast path through the expanded-constant prior
+    from pulpo_b200.components.pulpo import PULPoPrior
+    mu, sg = dev(g["mu0"]), dev(g["sigma0"])
+    pm, ps = PULPoPrior()({0: mu}, {0: sg})
+    assert_loss_close(PF.kl_diag(mu, sg, pm[0], ps[0]).item(), g["kl_std"], "kl fast path")
+
+
+def test_l2reg_golden(PF):
+    g = load_golden("l2reg")
+    f = dev(g["f"], True)
+    loss = PF.l2_reg(f, 0.025)
+    assert_loss_close(loss.item(), g["loss"], "l2reg")
+    loss.backward()
+    assert_grad_close(f.grad.cpu().numpy(), g["gf"], "l2reg grad")
+
+
+# ----------------------------------------------------------------------------- decoder chain + losses (a6, a7, a10, a12)
+def test_hot_path_golden(PF):
+    from pulpo_b200.models import RegistrationHotPath
+    g = load_golden("hot_path_3lvl")
+    total, latent = int(g["total_levels"]), int(g["latent_levels"])
+    hp = RegistrationHotPath(list(g["x"].shape[2:]), total, latent, beta=0.1, gamma=0.05, lamb=0.025).cuda()
+    dfs = {l: dev(g["df%d" % l], True) for l in range(latent)}
+    mus = {l: dev(g["mu%d" % l], True) for l in range(latent)}
+    sgs = {l: dev(g["sigma%d" % l], True) for l in range(latent)}
+    loss, parts, outs = hp(dev(g["x"]), dev(g["y"]), dfs, mus, sgs)
+    for l in range(latent):
+        assert_close(outs["combined"][l].detach().cpu().numpy(), g["combined%d" % l], FIELD_ATOL, "combined %d" % l)
+        assert_close(outs["final"][l].detach().cpu().numpy(), g["final%d" % l], FIELD_ATOL, "final %d" % l)
+        assert_close(outs["moved"][l].detach().cpu().numpy(), g["moved%d" % l], FIELD_ATOL, "moved %d" % l)
+        assert_loss_close(parts["kl_levels"][l].item() * 0.1, g["kl_level%d" % l], "kl level %d" % l)
+        assert_loss_close(parts["recon_levels"][l].item(), g["recon_level%d" % l], "recon level %d" % l)
+        assert_loss_close(parts["reg_levels"][l].item(), g["reg_level%d" % l], "reg level %d" % l)
+    assert_loss_close(parts["kl"].item(), g["kl"], "kl")
+    assert_loss_close(parts["recon"].item(), g["recon"], "recon")
+    assert_loss_close(parts["reg"].item(), g["reg"], "reg")
+    assert_loss_close(loss.item(), g["total"], "total")
+    loss.backward()
+    for l in range(latent):
+        assert_grad_close(dfs[l].grad.cpu().numpy(), g["gdf%d" % l], "gdf %d" % l)
+        assert_grad_close(mus[l].grad.cpu().numpy(), g["gmu%d" % l], "gmu %d" % l)
+        assert_grad_close(sgs[l].grad.cpu().numpy(), g["gsigma%d" % l], "gsigma %d" % l)
+
+
+def test_combine_dfs_golden(PF):
+    from pulpo_b200.models import combine_dfs
+    g = load_golden("combine_dfs")
+    dfs = {l: dev(g["df%d" % l]) for l in range(2)}
+    with torch.no_grad():
+        comb, fin = combine_dfs(dfs, [int(s) for s in g["input_size"]])
+    for l in range(2):
+        assert_close(comb[l].cpu().numpy(), g["combined%d" % l], FIELD_ATOL, "combined %d" % l)
+        assert_close(fin[l].cpu().numpy(), g["final%d" % l], FIELD_ATOL, "final %d" % l)
+
+
+def test_hot_path_vs_torch_oracle_config1(PF):
+    """config 1 of BASELINE.json (64^3, 3 latent / 4 total levels) against the torch-CPU restatement."""
+    from oracle import torch_ref as T
+    from pulpo_b200 import synthetic as syn
+    from pulpo_b200.models import RegistrationHotPath
+    size, total, latent = [64, 64, 64], 4, 3
+    x, y, dfs, mus, sgs = syn.make_hot_path_inputs(size, total, latent, seed=0)
+    d_ref = {l: dfs[l].clone().requires_grad_(True) for l in dfs}
+    m_ref = {l: mus[l].clone().requires_grad_(True) for l in dfs}
+    s_ref = {l: sgs[l].clone().requires_grad_(True) for l in dfs}
+    ref_total, ref_parts, ref_out = T.hot_path_losses(x, y, d_ref, m_ref, s_ref, total)
+    ref_total.backward()
+    hp = RegistrationHotPath(size, total, latent).cuda()
+    d = {l: dfs[l].cuda().requires_grad_(True) for l in dfs}
+    m = {l: mus[l].cuda().requires_grad_(True) for l in dfs}
+    s = {l: sgs[l].cuda().requires_grad_(True) for l in dfs}
+    loss, parts, outs = hp(x.cuda(), y.cuda(), d, m, s)
+    loss.backward()
+    for k in ("kl", "recon", "reg"):
+        assert_loss_close(parts[k].item(), ref_parts[k].item(), k)
+    assert_loss_close(loss.item(), ref_total.item(), "total")
+    for l in range(latent):
+        assert_close(outs["moved"][l].detach().cpu().numpy(), ref_out["moved"][l].detach().numpy(), FIELD_ATOL, "moved")
+        assert_close(outs["final"][l].detach().cpu().numpy(), ref_out["final"][l].detach().numpy(), FIELD_ATOL, "final")
+        assert_grad_close(d[l].grad.cpu().numpy(), d_ref[l].grad.numpy(), "gdf %d" % l)
+        assert_grad_close(m[l].grad.cpu().numpy(), m_ref[l].grad.numpy(), "gmu %d" % l)
+        assert_grad_close(s[l].grad.cpu().numpy(), s_ref[l].grad.numpy(), "gsigma %d" % l)
