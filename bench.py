@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- PULPo registration hot path on B200 (BASELINE.json metric:
+"warp+NCC fwd/bwd Gvoxels/s at 1/2/4/8 B200; % of HBM roofline").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # reference PyTorch CPU path (oracle port)
+
+A "step" = one pass of the hot path (per level: combine -> 7-step integration -> output resize
+-> warp; hierarchical NCC + beta*KL + L2 losses; backward to the velocity fields / mu / sigma)
+over one synthetic OASIS-shaped (160x192x224) pair per GPU -- configs[1] of BASELINE.json.
+Multi-GPU: one process per GPU (torchrun), pairs sharded across ranks with no data-path
+collective (weak scaling); the three loss scalars are all-reduced over NCCL each step.
+
+value   = voxels of all ranks / max-over-ranks device time, inputs resident in HBM, the whole
+          step replayed as one CUDA graph.
+e2e     = same metric through the public module API with pinned HOST inputs: H2D copies of
+          x, y, velocity fields, mu, sigma and the D2H read of the loss are inside the timed region.
+roofline= dominant kernel: algorithmic bytes / its CUDA-event time, vs MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (input_size, total_levels, latent_levels)
+    "oasis_160x192x224_5tot_4lat": ([160, 192, 224], 5, 4),
+    "cube64_4tot_3lat": ([64, 64, 64], 4, 3),
+}
+ALGO_BYTES_PER_VOXEL = 220.9   # SURVEY.md 8d, config 2, fwd+bwd incl. L2_reg
+METRIC = "hot-path fwd+bwd throughput (warp + integration + pyramid + NCC/KL/L2)"
+UNIT = "Gvoxel/s"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            p = [t.strip() for t in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        busy = [v for v in sm if v > 0.5 * (max(sm) if sm else 1)]
+        med = busy[len(busy) // 2] if busy else (sm[len(sm) // 2] if sm else None)
+        return {"sm_mhz": med, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def _cpu_hot_path_step(T, torch, inputs, total_levels):
+    x, y, dfs, mus, sgs = inputs
+    d = {l: dfs[l].clone().requires_grad_(True) for l in dfs}
+    m = {l: mus[l].clone().requires_grad_(True) for l in dfs}
+    s = {l: sgs[l].clone().requires_grad_(True) for l in dfs}
+    t0 = time.perf_counter()
+    loss, _, _ = T.hot_path_losses(x, y, d, m, s, total_levels)
+    loss.backward()
+    return time.perf_counter() - t0, float(loss.detach())
+
+
+def cpu_baseline(budget_s, steps=1, warmup=0, want_workload=None):
+    """Reference PyTorch CPU path (oracle/torch_ref.py: the same ATen ops the reference calls)
+    on the host cores, on a bounded sample of the workload: the largest shape whose
+    (steps+warmup) passes fit the budget, calibrated on a 32^3 pass."""
+    import torch
+    from oracle import torch_ref as T
+    from pulpo_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cal = syn.make_hot_path_inputs([32, 32, 32], 4, 3, seed=0)
+    _cpu_hot_path_step(T, torch, cal, 4)
+    t_cal, _ = _cpu_hot_path_step(T, torch, cal, 4)
+    per_voxel = t_cal / 32 ** 3
+    candidates = [("oasis_160x192x224_5tot_4lat", [160, 192, 224], 5, 4), ("half_80x96x112_4tot_3lat", [80, 96, 112], 4, 3),
+                  ("cube64_4tot_3lat", [64, 64, 64], 4, 3), ("cube32_4tot_3lat", [32, 32, 32], 4, 3)]
+    if want_workload:
+        candidates = [c for c in candidates if c[0] == want_workload] + candidates
+    chosen = candidates[-1]
+    for c in candidates:
+        n = c[1][0] * c[1][1] * c[1][2]
+        if per_voxel * n * 1.3 * (steps + warmup) <= budget_s:
+            chosen = c
+            break
+    name, size, total, latent = chosen
+    inputs = syn.make_hot_path_inputs(size, total, latent, seed=0)
+    for _ in range(warmup):
+        _cpu_hot_path_step(T, torch, inputs, total)
+    times = [_cpu_hot_path_step(T, torch, inputs, total)[0] for _ in range(steps)]
+    nvox = size[0] * size[1] * size[2]
+    tot = sum(times)
+    return {"value": nvox * steps / tot / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d step(s) of %s (B=1) fwd+bwd via oracle/torch_ref.py (torch %s CPU, %d threads), %.2f s/step"
+                      % (steps, name, torch.__version__, cores, tot / steps)}, tot / steps, name
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, ms, name = cpu_baseline(budget_s=150.0, steps=args.steps, warmup=args.warmup,
+                                want_workload=args.workload)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "sample_workload": name, "batch_per_gpu": 1,
+                       "note": "reference PyTorch CPU path on host cores; rank 0 only"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pulpo_b200 import _lib, synthetic as syn
+    from pulpo_b200.models import RegistrationHotPath
+    from pulpo_b200.roofline import algo_bytes, measured_peaks
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- pulpo_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()   # fail loudly if the CUDA library is missing
+
+    size, total, latent = WORKLOADS[args.workload]
+    nvox = size[0] * size[1] * size[2]
+    B = args.batch
+    x_h, y_h, d_h, m_h, s_h = syn.make_hot_path_inputs(size, total, latent, seed=rank, batch=B)
+    host = [x_h, y_h] + [d_h[l] for l in range(latent)] + [m_h[l] for l in range(latent)] + [s_h[l] for l in range(latent)]
+    host = [t.pin_memory() for t in host]
+    h2d_bytes = sum(t.numel() * 4 for t in host)
+    hp = RegistrationHotPath(size, total, latent).to(dev)
+
+    def to_dev(non_blocking=True):
+        ts = [t.to(dev, non_blocking=non_blocking) for t in host]
+        x, y = ts[0], ts[1]
+        d = {l: ts[2 + l].requires_grad_(True) for l in range(latent)}
+        m = {l: ts[2 + latent + l].requires_grad_(True) for l in range(latent)}
+        s = {l: ts[2 + 2 * latent + l].requires_grad_(True) for l in range(latent)}
+        return x, y, d, m, s
+
+    x, y, d, m, s = to_dev(False)
+    leaves = list(d.values()) + list(m.values()) + list(s.values())
+    scal = torch.zeros(3, device=dev)
+
+    def step():
+        for t in leaves:
+            t.grad = None
+        loss, parts, _ = hp(x, y, d, m, s)
+        loss.backward()
+        if world > 1:   # the only exchange this path has: loss scalars (gradients of the convs live upstream)
+            scal.copy_(torch.stack([parts["kl"], parts["recon"], parts["reg"]]).detach())
+            dist.all_reduce(scal)
+        return loss
+
+    # ---- warm-up (eager), then capture the step as ONE CUDA graph
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    launch_mode = "cuda_graph"
+    graph = None
+    if not args.no_graph and world == 1:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = step()
+            for _ in range(2):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write("bench.py: CUDA graph capture failed (%r); timing eager launches\n" % (e,))
+            graph, launch_mode = None, "eager"
+    else:
+        launch_mode = "eager"
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+
+    # count our kernel launches per step (C-ABI calls; each enqueues exactly one kernel)
+    _lib.profiler.enabled, _lib.profiler.timing = True, False
+    _lib.profiler.reset()
+    step()
+    launches_per_step = _lib.profiler.launches
+    _lib.profiler.enabled = False
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: EXACTLY K steps, CUDA events, max over ranks
+    clocks = ClockSampler(local)
+    for _ in range(args.warmup):
+        run_step()
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run_step()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * B * nvox / (ms_step * 1e-3) / 1e9
+
+    # ---- e2e: public module API, pinned host inputs, H2D + D2H inside the timed region
+    def e2e_step():
+        xx, yy, dd, mm, ss = to_dev(True)
+        loss, _, _ = hp(xx, yy, dd, mm, ss)
+        loss.backward()
+        return float(loss.item())     # D2H read of the step's result
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    e2e_steps = max(2, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = world * B * nvox / (ms_e2e / e2e_steps * 1e-3) / 1e9
+
+    # ---- per-kernel breakdown with CUDA events around every C-ABI call (eager, same stream)
+    peak, peak_src = measured_peaks(ROOT)
+    _lib.profiler.enabled, _lib.profiler.timing = True, True
+    _lib.profiler.reset()
+    prof_steps = max(2, min(args.steps, 5))
+    for _ in range(prof_steps):
+        step()
+    torch.cuda.synchronize()
+    _lib.profiler.enabled = _lib.profiler.timing = False
+    agg, shapes = {}, {}
+    for name, cargs, s_ev, e_ev in _lib.profiler.records:
+        t_ms, nb = s_ev.elapsed_time(e_ev), algo_bytes(name, cargs)
+        a = agg.setdefault(name, {"ms": 0.0, "bytes": 0, "calls": 0})
+        a["ms"] += t_ms; a["bytes"] += nb; a["calls"] += 1
+        g = shapes.setdefault((name, nb), {"ms": 0.0, "n": 0})   # one entry per distinct launch shape
+        g["ms"] += t_ms; g["n"] += 1
+    breakdown = {k: {"ms_per_step": v["ms"] / prof_steps, "calls_per_step": v["calls"] / prof_steps,
+                     "algo_MB_per_step": v["bytes"] / prof_steps / 1e6,
+                     "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None}
+                 for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+    (dname, dbytes), dg = max(shapes.items(), key=lambda kv: kv[1]["ms"])
+    d_ms = dg["ms"] / dg["n"]
+    achieved = dbytes / (d_ms * 1e-3) / 1e9
+    roofline = {"kernel": dname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": dbytes, "us_per_launch": d_ms * 1e3, "launches_timed": dg["n"],
+                "share_of_step": dg["ms"] / sum(v["ms"] for v in agg.values()),
+                "note": "launch shape with the largest share of the step; algorithmic bytes (SURVEY.md 8d) / mean CUDA-event duration"}
+
+    if rank == 0:
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cb, _, _ = cpu_baseline(budget_s=25.0, steps=1, warmup=0, want_workload=args.workload)
+            except Exception as e:  # pragma: no cover
+                cb = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "pairs_per_gpu": B, "voxels_per_pair": nvox,
+                       "levels": "%d total / %d latent, level_res, 7 integration steps" % (total, latent),
+                       "launch": launch_mode, "parallelism": "pairs sharded over %d GPU(s), no data-path collective" % world,
+                       "l2": "per-step working set ~1.5 GB >> 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "clocks": clk,
+            "roofline": roofline,
+            "path_roofline": {"algo_bytes_per_voxel": ALGO_BYTES_PER_VOXEL,
+                              "achieved": value / world * ALGO_BYTES_PER_VOXEL, "peak": peak, "unit": "GB/s",
+                              "frac": value / world * ALGO_BYTES_PER_VOXEL / peak, "peak_source": peak_src},
+            "kernels": breakdown,
+        }
+        if cb is not None:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="oasis_160x192x224_5tot_4lat", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=1, help="pairs per GPU")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -94,7 +94,7 @@ int pulpo_avgpool2_fwd(const float *x, float *out, int B, int C, int D0, int D1,
 
 /* ---- a9: NCC_loss(y_pred, y_true, win_size, gamma)   src/losses.py:85-135 ------------------
  * loss (device scalar) = -gamma/B * sum cc.  abc (nullable): [3][B,C,S] coefficient volumes
- * the backward box-filters.  win odd, 3..15.  ws: per-CTA partial sums. */
+ * the backward box-filters.  win odd, 3..11.  ws: per-CTA partial sums. */
 size_t pulpo_ncc_ws_bytes(int B, int C, int D0, int D1, int D2);
 int pulpo_ncc_fwd(const float *pred, const float *target, float *loss, float *abc, void *ws,
                   size_t ws_bytes, int win, float gamma, int B, int C, int D0, int D1, int D2,

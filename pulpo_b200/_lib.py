@@ -45,6 +45,47 @@ SIGNATURES = {
 _lib = None
 
 
+class KernelProfiler:
+    """Optional per-call instrumentation used by bench.py: counts C-ABI launches and, when
+    ``timing`` is on, brackets every call with CUDA events on the current stream."""
+
+    def __init__(self):
+        self.enabled = False
+        self.timing = False
+        self.records = []      # (name, args, start_event, end_event)
+        self.launches = 0
+
+    def reset(self):
+        self.records, self.launches = [], 0
+
+
+profiler = KernelProfiler()
+_LAUNCHING = None  # names of entry points that enqueue a kernel
+
+
+class _Proxy:
+    def __init__(self, handle):
+        self._h = handle
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        if not profiler.enabled or name.endswith("_bytes") or name in ("pulpo_version", "pulpo_strerror"):
+            return fn
+
+        def wrapped(*args):
+            profiler.launches += 1
+            if not profiler.timing:
+                return fn(*args)
+            import torch
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*args)
+            e.record()
+            profiler.records.append((name, args, s, e))
+            return r
+        return wrapped
+
+
 def lib():
     """Load the library once.  Raises RuntimeError (loudly) when it has not been built."""
     global _lib
@@ -58,7 +99,7 @@ def lib():
             fn = getattr(handle, name)   # AttributeError if the .so is stale
             fn.restype = res
             fn.argtypes = args
-        _lib = handle
+        _lib = _Proxy(handle)
     return _lib
 
 

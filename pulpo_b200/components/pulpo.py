@@ -91,6 +91,7 @@ class PULPoPrior(nn.Module):
             m, s = posterior_mus[l], posterior_sigmas[l]
             prior_mus[l] = torch.zeros((), dtype=torch.float32, device=m.device).expand(m.shape)
             prior_sigmas[l] = torch.ones((), dtype=torch.float32, device=s.device).expand(s.shape)
+            prior_mus[l]._pulpo_const, prior_sigmas[l]._pulpo_const = 0.0, 1.0   # host-side tag
         return prior_mus, prior_sigmas
 
 

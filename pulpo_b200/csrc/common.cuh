@@ -34,8 +34,8 @@ static inline int launch_status()
 struct AxisConst {
     float S;     // float(S)
     float Sm1;   // float(S-1)
-    float rcp;   // 1.0f / float(S-1)   (MODE 1)
-    float gmul;  // S/(S-1) chain for the backward: applied as ((m*g)*2)/(S-1) with m = S/2
+    float rcp;   // RN(1 / float(S-1))
+    float gmul;  // S/2: d p / d n of the unnormalise (backward)
 };
 
 __host__ __device__ inline AxisConst make_axis(int S)
@@ -48,11 +48,28 @@ __host__ __device__ inline AxisConst make_axis(int S)
     return a;
 }
 
-template <int MODE>
-__device__ __forceinline__ float sample_pos(int v, float d, const AxisConst &a)
+// Correctly rounded x / c for the per-axis constant c = S-1 without the generic division
+// sequence: y = RN(1/c) is precomputed, two FMA residual corrections make q1 faithful and the
+// last FMA rounds correctly (Markstein's theorem; it only fails for a divisor whose significand
+// is all ones, i.e. S-1 = 2^24-1).  Non-finite x is passed through.  Tiny |x| may lose
+// denormal bits, which the following "- 0.5" absorbs.
+__device__ __forceinline__ float div_by_axis(float x, const AxisConst &a)
 {
-    float loc = __fadd_rn((float)v, d);
-    float q = (MODE == PULPO_COORD_CPU_EXACT) ? __fdiv_rn(loc, a.Sm1) : __fmul_rn(loc, a.rcp);
+    float q0 = __fmul_rn(x, a.rcp);
+    float r0 = __fmaf_rn(-a.Sm1, q0, x);
+    float q1 = __fmaf_rn(r0, a.rcp, q0);
+    float r1 = __fmaf_rn(-a.Sm1, q1, x);
+    float q = __fmaf_rn(r1, a.rcp, q1);
+    // non-finite or absurdly large x: x itself has the right sign/NaN-ness and clamps identically
+    return (fabsf(x) <= 1e30f) ? q : x;
+}
+
+// vf = float(voxel index along this axis)
+template <int MODE>
+__device__ __forceinline__ float sample_pos(float vf, float d, const AxisConst &a)
+{
+    float loc = __fadd_rn(vf, d);
+    float q = (MODE == PULPO_COORD_CPU_EXACT) ? div_by_axis(loc, a) : __fmul_rn(loc, a.rcp);
     float n = __fmul_rn(2.0f, __fsub_rn(q, 0.5f));
     float t = (MODE == PULPO_COORD_CPU_EXACT) ? __fsub_rn(__fmul_rn(__fadd_rn(n, 1.0f), a.S), 1.0f)
                                               : __fmaf_rn(__fadd_rn(n, 1.0f), a.S, -1.0f);
@@ -68,25 +85,61 @@ __device__ __forceinline__ float clip_pos(float p, float Sm1)
 
 // one axis of the trilinear footprint
 struct Tap {
-    int i;      // floor(p)
-    float w0;   // (i+1) - p
-    float w1;   // p - i
-    bool in1;   // i+1 is inside the volume
+    int i;      // index of the low corner actually read (floor(p), or S-2 when floor(p) == S-1)
+    float w0;   // weight of corner i
+    float w1;   // weight of corner i+1
+    int hi;     // 1 when the footprint was shifted down at the upper border (floor(p) == i + 1)
 };
 
 template <int MODE>
-__device__ __forceinline__ Tap make_tap(int v, float d, const AxisConst &a, int S, float *unclamped = nullptr)
+__device__ __forceinline__ Tap make_tap(float vf, float d, const AxisConst &a, int S, float *unclamped = nullptr)
 {
-    float u = sample_pos<MODE>(v, d, a);
+    float u = sample_pos<MODE>(vf, d, a);
     if (unclamped) *unclamped = u;
     float p = clip_pos(u, a.Sm1);
-    Tap t;
-    float fl = floorf(p);
-    t.i = (int)fl;
-    t.w0 = __fsub_rn(fl + 1.0f, p);
-    t.w1 = __fsub_rn(p, fl);
-    t.in1 = (t.i + 1 < S);
-    return t;
+    // floor of 0 <= p < 2^22 without the conversion unit: adding 2^23 in round-toward-zero
+    // truncates the fraction; the integer sits in the low mantissa bits
+    float t = __fadd_rz(p, 8388608.0f);
+    float fl = __fsub_rn(t, 8388608.0f);
+    int i = __float_as_int(t) - 0x4B000000;
+    float w0 = __fsub_rn(__fadd_rn(fl, 1.0f), p);   // (i+1) - p
+    float w1 = __fsub_rn(p, fl);                    // p - i
+    // p == S-1 exactly: corner i+1 is outside the volume and has weight 0.  Read corners
+    // (S-2, S-1) with weights (0, 1) instead, so that every footprint is 2x2x2 in-bounds and the
+    // +1 neighbours are fixed immediates; 0*x + 1*y == y keeps the result bit-identical.
+    Tap tp;
+    tp.hi = (i >= S - 1) ? 1 : 0;
+    tp.i = i - tp.hi;
+    tp.w0 = tp.hi ? w1 : w0;
+    tp.w1 = tp.hi ? w0 : w1;
+    return tp;
+}
+
+// 32-bit division by a launch constant (q = umulhi(n, mul) >> shr, valid for n < 2^31)
+struct FastDiv {
+    unsigned int d, mul, shr;
+};
+
+static inline FastDiv make_fastdiv(unsigned int d)
+{
+    FastDiv f;
+    f.d = d;
+    if (d == 1) {
+        f.mul = 0; f.shr = 0;
+        return f;
+    }
+    unsigned int lg = 0;
+    while ((1ull << lg) < d) ++lg;
+    unsigned int p = 31 + lg;
+    f.mul = (unsigned int)(((1ull << p) + d - 1) / d);
+    f.shr = p - 32;
+    return f;
+}
+
+__device__ __forceinline__ void fast_divmod(unsigned int n, const FastDiv &f, unsigned int &q, unsigned int &r)
+{
+    q = (f.d == 1) ? n : (__umulhi(n, f.mul) >> f.shr);
+    r = n - q * f.d;
 }
 
 // ---------------------------------------------------------------------------------------------

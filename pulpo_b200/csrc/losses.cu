@@ -107,6 +107,93 @@ l2reg_bwd_kernel(const float *__restrict__ gloss, const float *__restrict__ f, f
     }
 }
 
+// 128-bit variants (D2 % 4 == 0): one thread owns 4 consecutive voxels of a row, FastDiv decode
+struct RowGeom {
+    int BC, D0, D1, D2, XG;
+    unsigned int groups;
+    FastDiv dXG, dD1, dD0;
+};
+
+static bool make_rowgeom(RowGeom &g, int BC, int D0, int D1, int D2)
+{
+    if (D2 % 4 || (i64)BC * D0 * D1 * D2 >= (1ll << 31)) return false;
+    g.BC = BC; g.D0 = D0; g.D1 = D1; g.D2 = D2; g.XG = D2 / 4;
+    g.groups = (unsigned int)((i64)BC * D0 * D1 * g.XG);
+    g.dXG = make_fastdiv(g.XG); g.dD1 = make_fastdiv(D1); g.dD0 = make_fastdiv(D0);
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+l2reg_fwd_v4_kernel(const float *__restrict__ f, float *out, ReduceWs *ws, double scale, const RowGeom g)
+{
+    __shared__ double red[32];
+    const int sy = g.D2, sz = g.D1 * g.D2;
+    float acc = 0.0f;
+    for (unsigned int gid = blockIdx.x * 256u + threadIdx.x; gid < g.groups; gid += gridDim.x * 256u) {
+        unsigned int row, xg, zb, y, bc, z;
+        fast_divmod(gid, g.dXG, row, xg);
+        fast_divmod(row, g.dD1, zb, y);
+        fast_divmod(zb, g.dD0, bc, z);
+        if (y == 0 || z == 0) continue;
+        const float *p = f + (i64)gid * 4;
+        const float4 c = ld_stream4(p), pz = ld_stream4(p - sz), py = ld_stream4(p - sy);
+        const float px = xg ? __ldg(p - 1) : c.x;   // x == 0 is outside the crop
+        float t;
+        if (xg) { t = c.x - pz.x; acc += t * t; t = c.x - py.x; acc += t * t; t = c.x - px; acc += t * t; }
+        t = c.y - pz.y; acc += t * t; t = c.y - py.y; acc += t * t; t = c.y - c.x; acc += t * t;
+        t = c.z - pz.z; acc += t * t; t = c.z - py.z; acc += t * t; t = c.z - c.y; acc += t * t;
+        t = c.w - pz.w; acc += t * t; t = c.w - py.w; acc += t * t; t = c.w - c.z; acc += t * t;
+    }
+    double bt = block_sum((double)acc, red);
+    grid_reduce_finish(bt, ws, out, scale, red);
+}
+
+// ACC: gf += ...  (lets the caller fold this gradient into an existing one without an extra pass)
+template <bool ACC>
+__global__ void __launch_bounds__(256)
+l2reg_bwd_v4_kernel(const float *__restrict__ gloss, const float *__restrict__ f, float *__restrict__ gf, float kk,
+                    const RowGeom g)
+{
+    const unsigned int gid = blockIdx.x * 256u + threadIdx.x;
+    if (gid >= g.groups) return;
+    const int sy = g.D2, sz = g.D1 * g.D2;
+    const float k = (gloss ? __ldg(gloss) : 1.0f) * kk;
+    unsigned int row, xg, zb, y, bc, z;
+    fast_divmod(gid, g.dXG, row, xg);
+    fast_divmod(row, g.dD1, zb, y);
+    fast_divmod(zb, g.dD0, bc, z);
+    const float *p = f + (i64)gid * 4;
+    const float4 c4 = ld_stream4(p);
+    const float c[6] = {xg ? __ldg(p - 1) : 0.0f, c4.x, c4.y, c4.z, c4.w, (int)xg + 1 < g.XG ? __ldg(p + 4) : 0.0f};
+    const bool zin = z > 0, yin = y > 0, zn = (int)z + 1 < g.D0, yn = (int)y + 1 < g.D1;
+    float4 pz = make_float4(0.f, 0.f, 0.f, 0.f), py = pz, nz = pz, ny = pz;
+    if (zin) pz = ld_stream4(p - sz);
+    if (yin) py = ld_stream4(p - sy);
+    if (zn) nz = ld_stream4(p + sz);
+    if (yn) ny = ld_stream4(p + sy);
+    const float pzv[4] = {pz.x, pz.y, pz.z, pz.w}, pyv[4] = {py.x, py.y, py.z, py.w};
+    const float nzv[4] = {nz.x, nz.y, nz.z, nz.w}, nyv[4] = {ny.x, ny.y, ny.z, ny.w};
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = 4 * (int)xg + j;
+        const bool xin = x > 0, xn = x + 1 < g.D2;
+        const float cc = c[j + 1];
+        float a = 0.0f;
+        if (xin && yin && zin) a += (cc - pzv[j]) + (cc - pyv[j]) + (cc - c[j]);
+        if (zn && yin && xin) a -= nzv[j] - cc;
+        if (yn && zin && xin) a -= nyv[j] - cc;
+        if (xn && zin && yin) a -= c[j + 2] - cc;
+        r[j] = k * a;
+    }
+    float4 *o = reinterpret_cast<float4 *>(gf + (i64)gid * 4);
+    if (ACC) {
+        const float4 old = *o;
+        r[0] += old.x; r[1] += old.y; r[2] += old.z; r[3] += old.w;
+    }
+    *o = make_float4(r[0], r[1], r[2], r[3]);
+}
+
 // Welford: count = number of samples including x
 __global__ void __launch_bounds__(256)
 moments_update_kernel(const float *__restrict__ x, float *__restrict__ mean, float *__restrict__ m2, float inv_count,
@@ -188,8 +275,12 @@ extern "C" int pulpo_l2reg_fwd(const float *f, float lamb, float *out, void *ws,
     const i64 total = (i64)B * C * D0 * D1 * D2;
     const double cnt = (double)B * C * (D0 - 1) * (double)(D1 - 1) * (D2 - 1);
     const double scale = (double)lamb * D0 * D1 * D2 / cnt;
-    l2reg_fwd_kernel<<<grid_for(total, 256, 4), 256, 0, (cudaStream_t)stream>>>(f, out, (ReduceWs *)ws, scale, B * C,
-                                                                              D0, D1, D2);
+    RowGeom g;
+    if (make_rowgeom(g, B * C, D0, D1, D2) && aligned16(f))
+        l2reg_fwd_v4_kernel<<<grid_for(g.groups, 256, 4), 256, 0, (cudaStream_t)stream>>>(f, out, (ReduceWs *)ws, scale, g);
+    else
+        l2reg_fwd_kernel<<<grid_for(total, 256, 4), 256, 0, (cudaStream_t)stream>>>(f, out, (ReduceWs *)ws, scale,
+                                                                                  B * C, D0, D1, D2);
     return launch_status();
 }
 
@@ -201,7 +292,11 @@ extern "C" int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, f
     const i64 total = (i64)B * C * D0 * D1 * D2;
     const double cnt = (double)B * C * (D0 - 1) * (double)(D1 - 1) * (D2 - 1);
     const float kk = (float)(2.0 * (double)lamb * D0 * D1 * D2 / cnt);
-    l2reg_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(gloss, f, gf, kk, B * C, D0, D1, D2);
+    RowGeom g;
+    if (make_rowgeom(g, B * C, D0, D1, D2) && aligned16(f) && aligned16(gf))
+        l2reg_bwd_v4_kernel<false><<<(g.groups + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gloss, f, gf, kk, g);
+    else
+        l2reg_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(gloss, f, gf, kk, B * C, D0, D1, D2);
     return launch_status();
 }
 

@@ -4,15 +4,20 @@
 // The reference computes five win^3 box sums (I, J, I^2, J^2, IJ) as dense conv3d calls
 // (729 taps each at win=9).  Here they are separable direct sums inside one streaming kernel:
 // a CTA owns a (TY x TX) tile in (D1, D2) and marches along D0.
-//   phase 1  x-sums: a thread reads XS+2R consecutive values per input from global (zero padded
-//            at the volume border exactly like conv3d's padding), forms the products in
-//            registers and writes XS x-summed values per quantity to shared memory;
-//   phase 2  y-sums from shared memory (two output rows per thread), then the z window as a
-//            register ring of the last W plane sums -- no subtraction, so no running-sum drift
-//            and exact zeros stay exact zeros (the conditioning issue of SURVEY.md 9.5).
-// The loss is reduced warp-shuffle -> CTA -> deterministic two-stage grid sum in double.
-// Forward optionally emits the three coefficient volumes (a, b, c) whose box filter is the
-// gradient; backward runs the same box kernel on them.
+//   phase 1  x-sums: a thread reads 12 consecutive values per input with three 128-bit loads
+//            (zero padded at the volume border exactly like conv3d's padding), forms the
+//            products in registers and writes 4 x-summed values per quantity to shared memory
+//            (15 adds per quantity for 4 outputs by sharing the common core of the windows);
+//   phase 2  y-sums from shared memory (two output rows per thread, shared core), then the z
+//            window as a register ring of the last W plane sums -- no subtraction, so no
+//            running-sum drift and exact zeros stay exact zeros (the conditioning issue of
+//            SURVEY.md 9.5).
+// The kernel is bound by instruction issue, not HBM (8 B/voxel leaves ~45 issue slots per voxel
+// per SM), so the five quantities travel as two packed float2 (I,J), (I^2,J^2) plus one scalar IJ
+// and are summed with Blackwell's packed-fp32 FADD2/FMUL2 (__fadd2_rn/__fmul2_rn): 3 adds per
+// tap instead of 5.  The loss is reduced warp-shuffle -> CTA -> deterministic two-stage grid sum
+// in double.  Forward optionally emits the coefficient volumes (a, b, c) whose box filter is the
+// gradient; backward runs the same box kernel on them (packed (a,b) + scalar c).
 // Algorithmic bytes: fwd 8 B/voxel (+12 when saving a,b,c), bwd 12 B/voxel (+12 reading a,b,c).
 #include "common.cuh"
 
@@ -32,40 +37,85 @@ struct NccParams {
     ReduceWs *ws;
     double loss_scale;             // -gamma / B
     float k;                       // bwd: -gamma / B
-    float Wf;                      // win^3
+    float Wf, rcpW;                // win^3 and RN(1/win^3)
     int BC, D0, D1, D2, zchunk, nzchunks;
 };
 
-template <int W, bool FWD>
-__global__ void __launch_bounds__(NCC_THREADS)
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float add2(float a, float b) { return __fadd_rn(a, b); }
+
+// sums of W consecutive values for 4 consecutive outputs: o[j] = sum a[j .. j+W-1]
+template <int W, typename T>
+__device__ __forceinline__ void xsum4(const T (&a)[W + 3], T (&o)[4])
+{
+    if (W >= 5) {
+        T core = a[3];
+#pragma unroll
+        for (int t = 4; t < W; ++t) core = add2(core, a[t]);
+        const T p12 = add2(a[1], a[2]), pw = add2(a[W], a[W + 1]);
+        o[0] = add2(core, add2(a[0], p12));
+        o[1] = add2(core, add2(p12, a[W]));
+        o[2] = add2(core, add2(a[2], pw));
+        o[3] = add2(core, add2(pw, a[W + 2]));
+    } else {  // W == 3
+        const T p12 = add2(a[1], a[2]), p34 = add2(a[3], a[4]);
+        o[0] = add2(a[0], p12);
+        o[1] = add2(p12, a[3]);
+        o[2] = add2(a[2], p34);
+        o[3] = add2(p34, a[5]);
+    }
+}
+
+// correctly rounded x / W with the precomputed reciprocal (see div_by_axis)
+__device__ __forceinline__ float div_by_W(float x, float Wf, float rcpW)
+{
+    float q0 = __fmul_rn(x, rcpW);
+    float r0 = __fmaf_rn(-Wf, q0, x);
+    float q1 = __fmaf_rn(r0, rcpW, q0);
+    float r1 = __fmaf_rn(-Wf, q1, x);
+    return __fmaf_rn(r1, rcpW, q1);
+}
+
+template <int W, bool FWD, bool VECLOAD>
+__global__ void __launch_bounds__(NCC_THREADS, 2)
 ncc_box_kernel(const NccParams p)
 {
     constexpr int R = W / 2;
-    constexpr int NQ = FWD ? 5 : 3;
     constexpr int NIN = FWD ? 2 : 3;
     constexpr int ROWS = NCC_TY + 2 * R;
     constexpr int SEGS = NCC_TX / NCC_XS;
-    __shared__ __align__(16) float X[NQ][ROWS][NCC_TX];
+    constexpr int NV = NCC_XS + 2 * R;  // inputs per item
+    constexpr int PAD = ((R + 3) / 4) * 4;  // aligned halo: loads cover [xq-PAD, xq+4+PAD)
+    constexpr int NL = 2 * PAD + 4;
+    // packed quantities: A = (I, J) | (a, b);  B = (I^2, J^2) [fwd only];  C = IJ | c
+    __shared__ __align__(16) float2 XA[ROWS][NCC_TX];
+    __shared__ __align__(16) float2 XB[FWD ? ROWS : 1][NCC_TX];
+    __shared__ __align__(16) float XC[ROWS][NCC_TX];
     __shared__ double red[32];
 
     const int D0 = p.D0, D1 = p.D1, D2 = p.D2;
-    const i64 sy = D2, sz = (i64)D1 * D2, S = (i64)D0 * sz;
+    const int sy = D2, sz = D1 * D2;
+    const i64 S = (i64)D0 * sz;
     const int x0 = blockIdx.x * NCC_TX, y0 = blockIdx.y * NCC_TY;
     const int bc = blockIdx.z / p.nzchunks, zc = blockIdx.z % p.nzchunks;
     const int z_start = zc * p.zchunk, z_end = min(D0, z_start + p.zchunk);
-    const float *in[3] = {p.in0 + (i64)bc * S, p.in1 + (i64)bc * S, FWD ? nullptr : p.in2 + (i64)bc * S};
+    const float *in0 = p.in0 + (i64)bc * S, *in1 = p.in1 + (i64)bc * S;
+    const float *in2 = FWD ? nullptr : p.in2 + (i64)bc * S;
 
-    // phase-2 ownership: column x, output rows 2*yp and 2*yp+1
+    // phase-2 ownership: column tx, output rows 2*yp and 2*yp+1
     const int tx = threadIdx.x % NCC_TX, yp = threadIdx.x / NCC_TX;
     const int gx = x0 + tx, gy = y0 + 2 * yp;
-    float ring[W][NQ][2];
+    float2 rA[W][2], rB[FWD ? W : 1][2];
+    float rC[W][2];
 #pragma unroll
-    for (int s = 0; s < W; ++s)
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) ring[s][q][0] = ring[s][q][1] = 0.0f;
+    for (int s = 0; s < W; ++s) {
+        rA[s][0] = rA[s][1] = make_float2(0.f, 0.f);
+        if (FWD) rB[s % (FWD ? W : 1)][0] = rB[s % (FWD ? W : 1)][1] = make_float2(0.f, 0.f);
+        rC[s][0] = rC[s][1] = 0.0f;
+    }
 
     float cc_acc = 0.0f;
-    const float gl = (!FWD && p.gloss) ? __ldg(p.gloss) : 1.0f;
+    const float gk = FWD ? 0.0f : ((p.gloss ? __ldg(p.gloss) : 1.0f) * p.k);
     const int nplanes = (z_end - z_start) + 2 * R;
 
     for (int zp0 = 0; zp0 < nplanes; zp0 += W) {
@@ -79,54 +129,92 @@ ncc_box_kernel(const NccParams p)
             for (int item = threadIdx.x; item < ROWS * SEGS; item += NCC_THREADS) {
                 const int r = item / SEGS, sg = item % SEGS;
                 const int yy = y0 - R + r;
-                float acc[NQ][NCC_XS];
+                float2 oA[4], oB[4];
+                float oC[4];
 #pragma unroll
-                for (int q = 0; q < NQ; ++q)
-#pragma unroll
-                    for (int j = 0; j < NCC_XS; ++j) acc[q][j] = 0.0f;
-                if (plane_ok && yy >= 0 && yy < D1) {
-                    const i64 rowoff = (i64)zin * sz + (i64)yy * sy;
-                    const int xb = x0 + sg * NCC_XS - R;
-                    float v[NIN][NCC_XS + 2 * R];
-#pragma unroll
-                    for (int n = 0; n < NIN; ++n)
-#pragma unroll
-                        for (int j = 0; j < NCC_XS + 2 * R; ++j) {
-                            const int xx = xb + j;
-                            v[n][j] = (xx >= 0 && xx < D2) ? __ldg(in[n] + rowoff + xx) : 0.0f;
-                        }
-#pragma unroll
-                    for (int j = 0; j < NCC_XS; ++j)
-#pragma unroll
-                        for (int t = 0; t < W; ++t) {
-                            if (FWD) {
-                                const float a = v[0][j + t], b = v[1][j + t];
-                                acc[0][j] += a;
-                                acc[1][j] += b;
-                                acc[2][j] = __fadd_rn(acc[2][j], __fmul_rn(a, a));
-                                acc[3][j] = __fadd_rn(acc[3][j], __fmul_rn(b, b));
-                                acc[4 % NQ][j] = __fadd_rn(acc[4 % NQ][j], __fmul_rn(a, b));
-                            } else {
-                                acc[0][j] += v[0][j + t];
-                                acc[1][j] += v[1][j + t];
-                                acc[2][j] += v[2 % NIN][j + t];
-                            }
-                        }
+                for (int j = 0; j < 4; ++j) {
+                    oA[j] = oB[j] = make_float2(0.f, 0.f);
+                    oC[j] = 0.0f;
                 }
+                if (plane_ok && yy >= 0 && yy < D1) {
+                    const int rowoff = zin * sz + yy * sy;
+                    float v0[NL], v1[NL], v2[NL];
+                    if (VECLOAD) {
+                        // aligned 128-bit loads cover [xq-PAD, xq+4+PAD); a float4 is wholly in or out
+                        const int xq = x0 + sg * NCC_XS;
 #pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    *reinterpret_cast<float4 *>(&X[q][r][sg * NCC_XS]) =
-                        make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+                        for (int q4 = 0; q4 < NL / 4; ++q4) {
+                            const int xx = xq - PAD + 4 * q4;
+                            const bool ok = (xx >= 0 && xx < D2);
+                            float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0, t2 = t0;
+                            if (ok) {
+                                t0 = __ldg(reinterpret_cast<const float4 *>(in0 + rowoff + xx));
+                                t1 = __ldg(reinterpret_cast<const float4 *>(in1 + rowoff + xx));
+                                if (!FWD) t2 = __ldg(reinterpret_cast<const float4 *>(in2 + rowoff + xx));
+                            }
+                            v0[4 * q4] = t0.x; v0[4 * q4 + 1] = t0.y; v0[4 * q4 + 2] = t0.z; v0[4 * q4 + 3] = t0.w;
+                            v1[4 * q4] = t1.x; v1[4 * q4 + 1] = t1.y; v1[4 * q4 + 2] = t1.z; v1[4 * q4 + 3] = t1.w;
+                            v2[4 * q4] = t2.x; v2[4 * q4 + 1] = t2.y; v2[4 * q4 + 2] = t2.z; v2[4 * q4 + 3] = t2.w;
+                        }
+                    } else {
+                        const int xb = x0 + sg * NCC_XS - PAD;
+#pragma unroll
+                        for (int j = 0; j < NL; ++j) {
+                            const int xx = xb + j;
+                            const bool ok = (xx >= 0 && xx < D2) && (j >= PAD - R) && (j < PAD - R + NV);
+                            v0[j] = ok ? __ldg(in0 + rowoff + xx) : 0.0f;
+                            v1[j] = ok ? __ldg(in1 + rowoff + xx) : 0.0f;
+                            v2[j] = (ok && !FWD) ? __ldg(in2 + rowoff + xx) : 0.0f;
+                        }
+                    }
+                    float2 a[NV], b[NV];
+                    float c[NV];
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        const int jj = j + PAD - R;   // window of output 0 starts at x - R
+                        a[j] = make_float2(v0[jj], v1[jj]);
+                        if (FWD) {
+                            b[j] = __fmul2_rn(a[j], a[j]);
+                            c[j] = __fmul_rn(v0[jj], v1[jj]);
+                        } else {
+                            c[j] = v2[jj];
+                        }
+                    }
+                    xsum4<W>(a, oA);
+                    if (FWD) xsum4<W>(b, oB);
+                    xsum4<W>(c, oC);
+                }
+                float4 *da = reinterpret_cast<float4 *>(&XA[r][sg * NCC_XS]);
+                da[0] = make_float4(oA[0].x, oA[0].y, oA[1].x, oA[1].y);
+                da[1] = make_float4(oA[2].x, oA[2].y, oA[3].x, oA[3].y);
+                if (FWD) {
+                    float4 *db = reinterpret_cast<float4 *>(&XB[r][sg * NCC_XS]);
+                    db[0] = make_float4(oB[0].x, oB[0].y, oB[1].x, oB[1].y);
+                    db[1] = make_float4(oB[2].x, oB[2].y, oB[3].x, oB[3].y);
+                }
+                *reinterpret_cast<float4 *>(&XC[r][sg * NCC_XS]) = make_float4(oC[0], oC[1], oC[2], oC[3]);
             }
             __syncthreads();
-            // ---------------- phase 2: y-sums (two rows) + z ring
+            // ---------------- phase 2: y-sums (two rows sharing the window core) + z ring
+            {
+                float2 coreA = XA[2 * yp + 1][tx];
+                float coreC = XC[2 * yp + 1][tx];
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                float core = 0.0f;
+                for (int t = 2; t < W; ++t) {
+                    coreA = add2(coreA, XA[2 * yp + t][tx]);
+                    coreC = add2(coreC, XC[2 * yp + t][tx]);
+                }
+                rA[s][0] = add2(XA[2 * yp][tx], coreA);
+                rA[s][1] = add2(coreA, XA[2 * yp + W][tx]);
+                rC[s][0] = add2(XC[2 * yp][tx], coreC);
+                rC[s][1] = add2(coreC, XC[2 * yp + W][tx]);
+                if (FWD) {
+                    float2 coreB = XB[2 * yp + 1][tx];
 #pragma unroll
-                for (int t = 1; t < W; ++t) core += X[q][2 * yp + t][tx];
-                ring[s][q][0] = X[q][2 * yp][tx] + core;
-                ring[s][q][1] = core + X[q][2 * yp + W][tx];
+                    for (int t = 2; t < W; ++t) coreB = add2(coreB, XB[2 * yp + t][tx]);
+                    rB[FWD ? s : 0][0] = add2(XB[2 * yp][tx], coreB);
+                    rB[FWD ? s : 0][1] = add2(coreB, XB[2 * yp + W][tx]);
+                }
             }
             __syncthreads();
             const int zout = zin - R;
@@ -134,19 +222,19 @@ ncc_box_kernel(const NccParams p)
 #pragma unroll
                 for (int o = 0; o < 2; ++o) {
                     if (gy + o >= D1) continue;
-                    float sum[NQ];
+                    float2 sA = rA[0][o], sB = FWD ? rB[0][o] : make_float2(0.f, 0.f);
+                    float sC = rC[0][o];
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        float t = 0.0f;
-#pragma unroll
-                        for (int u = 0; u < W; ++u) t += ring[u][q][o];
-                        sum[q] = t;
+                    for (int u = 1; u < W; ++u) {
+                        sA = add2(sA, rA[u][o]);
+                        if (FWD) sB = add2(sB, rB[u % (FWD ? W : 1)][o]);
+                        sC = add2(sC, rC[u][o]);
                     }
-                    const i64 off = (i64)bc * S + (i64)zout * sz + (i64)(gy + o) * sy + gx;
+                    const i64 off = (i64)bc * S + (i64)zout * sz + (gy + o) * sy + gx;
                     if (FWD) {
-                        const float sI = sum[0], sJ = sum[1], sII = sum[2], sJJ = sum[3], sIJ = sum[4 % NQ];
+                        const float sI = sA.x, sJ = sA.y, sII = sB.x, sJJ = sB.y, sIJ = sC;
                         const float Wf = p.Wf;
-                        const float uI = __fdiv_rn(sI, Wf), uJ = __fdiv_rn(sJ, Wf);
+                        const float uI = div_by_W(sI, Wf, p.rcpW), uJ = div_by_W(sJ, Wf, p.rcpW);
                         // same expanded (cancellation-prone) formulas as the reference, op by op
                         float cross = __fsub_rn(sIJ, __fmul_rn(uJ, sI));
                         cross = __fsub_rn(cross, __fmul_rn(uI, sJ));
@@ -157,17 +245,18 @@ ncc_box_kernel(const NccParams p)
                         Jv = __fadd_rn(Jv, __fmul_rn(__fmul_rn(uJ, uJ), Wf));
                         const float Dn = __fadd_rn(__fmul_rn(Iv, Jv), 1e-8f);
                         const float c2 = __fmul_rn(cross, cross);
-                        cc_acc += __fdiv_rn(c2, Dn);
+                        const float rD = __fdividef(1.0f, Dn);
+                        cc_acc += c2 * rD;
                         if (p.o0) {
-                            const float a = __fdiv_rn(2.0f * cross, Dn);
-                            const float c = -(c2 * Iv) / (Dn * Dn);
+                            const float a = 2.0f * cross * rD;
+                            const float c = -(c2 * Iv) * (rD * rD);
                             p.o0[off] = a;
-                            p.o1[off] = -(a * sI) / Wf - (2.0f * c * sJ) / Wf;
+                            p.o1[off] = -(a * sI + 2.0f * c * sJ) * p.rcpW;
                             p.o2[off] = c;
                         }
                     } else {
                         const float Iv = __ldg(p.I + off), Jv = __ldg(p.J + off);
-                        p.o0[off] = (gl * p.k) * (Iv * sum[0] + sum[1] + 2.0f * Jv * sum[2 % NQ]);
+                        p.o0[off] = gk * (Iv * sA.x + sA.y + 2.0f * Jv * sC);
                     }
                 }
             }
@@ -200,18 +289,26 @@ static NccGrid ncc_grid(int BC, int D0, int D1, int D2, int win)
     return g;
 }
 
-template <bool FWD>
-static int ncc_launch(const NccParams &p, const NccGrid &g, int win, cudaStream_t st)
+template <bool FWD, bool VEC>
+static int ncc_launch_w(const NccParams &p, const NccGrid &g, int win, cudaStream_t st)
 {
     switch (win) {
-        case 3: ncc_box_kernel<3, FWD><<<g.grid, NCC_THREADS, 0, st>>>(p); break;
-        case 5: ncc_box_kernel<5, FWD><<<g.grid, NCC_THREADS, 0, st>>>(p); break;
-        case 7: ncc_box_kernel<7, FWD><<<g.grid, NCC_THREADS, 0, st>>>(p); break;
-        case 9: ncc_box_kernel<9, FWD><<<g.grid, NCC_THREADS, 0, st>>>(p); break;
-        case 11: ncc_box_kernel<11, FWD><<<g.grid, NCC_THREADS, 0, st>>>(p); break;
+        case 3: ncc_box_kernel<3, FWD, VEC><<<g.grid, NCC_THREADS, 0, st>>>(p); break;
+        case 5: ncc_box_kernel<5, FWD, VEC><<<g.grid, NCC_THREADS, 0, st>>>(p); break;
+        case 7: ncc_box_kernel<7, FWD, VEC><<<g.grid, NCC_THREADS, 0, st>>>(p); break;
+        case 9: ncc_box_kernel<9, FWD, VEC><<<g.grid, NCC_THREADS, 0, st>>>(p); break;
+        case 11: ncc_box_kernel<11, FWD, VEC><<<g.grid, NCC_THREADS, 0, st>>>(p); break;
         default: return PULPO_ERR_UNSUPPORTED;
     }
     return launch_status();
+}
+
+template <bool FWD>
+static int ncc_launch(const NccParams &p, const NccGrid &g, int win, cudaStream_t st)
+{
+    bool vec = (p.D2 % 4 == 0) && aligned16(p.in0) && aligned16(p.in1) && (FWD || aligned16(p.in2)) &&
+               (i64)p.D0 * p.D1 * p.D2 < (1ll << 31);
+    return vec ? ncc_launch_w<FWD, true>(p, g, win, st) : ncc_launch_w<FWD, false>(p, g, win, st);
 }
 
 }  // namespace pulpo
@@ -232,6 +329,7 @@ extern "C" int pulpo_ncc_fwd(const float *pred, const float *target, float *loss
 {
     PULPO_REQUIRE(pred && target && loss && ws, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE((i64)D0 * D1 * D2 < (1ll << 31), PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(win >= 3 && win <= 11 && (win & 1), PULPO_ERR_UNSUPPORTED);
     NccGrid g = ncc_grid(B * C, D0, D1, D2, win);
     PULPO_REQUIRE(g.grid.y <= 65535 && g.grid.z <= 65535, PULPO_ERR_INVALID_SHAPE);
@@ -243,6 +341,7 @@ extern "C" int pulpo_ncc_fwd(const float *pred, const float *target, float *loss
     p.loss = loss; p.ws = (ReduceWs *)ws;
     p.loss_scale = -(double)gamma / (double)B;
     p.Wf = (float)(win * win * win);
+    p.rcpW = 1.0f / p.Wf;
     p.BC = B * C; p.D0 = D0; p.D1 = D1; p.D2 = D2; p.zchunk = g.zchunk; p.nzchunks = g.nzchunks;
     return ncc_launch<true>(p, g, win, (cudaStream_t)stream);
 }
@@ -253,6 +352,7 @@ extern "C" int pulpo_ncc_bwd(const float *abc, const float *pred, const float *t
 {
     PULPO_REQUIRE(abc && pred && target && gpred, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE((i64)D0 * D1 * D2 < (1ll << 31), PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(win >= 3 && win <= 11 && (win & 1), PULPO_ERR_UNSUPPORTED);
     NccGrid g = ncc_grid(B * C, D0, D1, D2, win);
     PULPO_REQUIRE(g.grid.y <= 65535 && g.grid.z <= 65535, PULPO_ERR_INVALID_SHAPE);
@@ -262,6 +362,7 @@ extern "C" int pulpo_ncc_bwd(const float *abc, const float *pred, const float *t
     p.I = target; p.J = pred; p.o0 = gpred; p.gloss = gloss;
     p.k = -gamma / (float)B;
     p.Wf = (float)(win * win * win);
+    p.rcpW = 1.0f / p.Wf;
     p.BC = B * C; p.D0 = D0; p.D1 = D1; p.D2 = D2; p.zchunk = g.zchunk; p.nzchunks = g.nzchunks;
     return ncc_launch<false>(p, g, win, (cudaStream_t)stream);
 }

@@ -4,96 +4,137 @@
 // HBM-bound streaming gather.  One thread owns VEC consecutive voxels along D2: the three
 // displacement channels are read with 128-bit loads, the 8 corner gathers go through L1/L2
 // (neighbouring voxels share cache lines), the output is written with 128-bit stores.
+// At 20 B/voxel (C=1) the HBM roofline leaves ~110 issue slots per voxel per SM, so the kernel is
+// written for instruction count: no 64-bit div/mod (FastDiv decode), 32-bit offsets, exact
+// constant division in 5 FMAs, floor via an RZ add (no conversion unit), clamped corner offsets
+// instead of predicated loads.
 // Algorithmic bytes: fwd 12 + 8C per voxel; bwd 4C (gout) + 12 (df) + 4C (img) + 12 (gdf) [+ 4C gimg].
 #include "common.cuh"
 
 namespace pulpo {
 
-struct VoxTaps {
-    Tap z, y, x;
-    i64 base;
+struct WarpGeom {
+    int B, C, D0, D1, D2, XG;
+    unsigned int groups;
+    FastDiv dXG, dD1, dD0;
+    AxisConst a0, a1, a2;
 };
+
+static int make_geom(WarpGeom &g, int B, int C, int D0, int D1, int D2, int vec)
+{
+    i64 S = (i64)D0 * D1 * D2;
+    if (S >= (1ll << 31) || (i64)B * S / vec >= (1ll << 31) || D0 > (1 << 22) || D1 > (1 << 22) || D2 > (1 << 22))
+        return PULPO_ERR_INVALID_SHAPE;
+    g.B = B; g.C = C; g.D0 = D0; g.D1 = D1; g.D2 = D2; g.XG = D2 / vec;
+    g.groups = (unsigned int)((i64)B * D0 * D1 * g.XG);
+    g.dXG = make_fastdiv(g.XG); g.dD1 = make_fastdiv(D1); g.dD0 = make_fastdiv(D0);
+    g.a0 = make_axis(D0); g.a1 = make_axis(D1); g.a2 = make_axis(D2);
+    return PULPO_OK;
+}
+
+struct Foot {        // trilinear footprint of one voxel: 2x2x2 corners, always inside the volume
+    int base;        // offset of the low corner inside one [D0,D1,D2] volume
+    int hz, hy, hx;  // upper-border shifts (only needed to report floor(p))
+    float wx0, wx1, wy0, wy1, wz0, wz1;
+};
+
+template <int MODE>
+__device__ __forceinline__ Foot make_foot(float zf, float yf, float xf, float dz, float dy, float dx,
+                                          const WarpGeom &g, float *uz = nullptr, float *uy = nullptr,
+                                          float *ux = nullptr)
+{
+    Tap tz = make_tap<MODE>(zf, dz, g.a0, g.D0, uz);
+    Tap ty = make_tap<MODE>(yf, dy, g.a1, g.D1, uy);
+    Tap tx = make_tap<MODE>(xf, dx, g.a2, g.D2, ux);
+    Foot f;
+    f.base = (tz.i * g.D1 + ty.i) * g.D2 + tx.i;
+    f.hz = tz.hi; f.hy = ty.hi; f.hx = tx.hi;
+    f.wx0 = tx.w0; f.wx1 = tx.w1; f.wy0 = ty.w0; f.wy1 = ty.w1; f.wz0 = tz.w0; f.wz1 = tz.w1;
+    return f;
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float *p, float (&v)[VEC])
+{
+    if (VEC == 4) {
+        float4 t = ld_stream4(p);
+        v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+    } else {
+        v[0] = __ldg(p);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec(float *p, const float (&v)[VEC])
+{
+    if (VEC == 4)
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+    else
+        p[0] = v[0];
+}
 
 template <int MODE, int VEC>
 __global__ void __launch_bounds__(256)
 warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, float *__restrict__ out,
-                  int32_t *__restrict__ idx, int B, int C, int D0, int D1, int D2, AxisConst a0,
-                  AxisConst a1, AxisConst a2)
+                  int32_t *__restrict__ idx, const WarpGeom g)
 {
-    const int XG = D2 / VEC;
-    const i64 S = (i64)D0 * D1 * D2;
-    const i64 sy = D2, sz = (i64)D1 * D2;
-    const i64 groups = (i64)B * D0 * D1 * XG;
-    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < groups; g += (i64)gridDim.x * blockDim.x) {
-        int xg = (int)(g % XG);
-        i64 r = g / XG;
-        int y = (int)(r % D1);
-        r /= D1;
-        int z = (int)(r % D0);
-        int b = (int)(r / D0);
-        const int x0 = xg * VEC;
-        const i64 v0 = ((i64)z * D1 + y) * D2 + x0;
-        const float *f = df + (i64)b * 3 * S + v0;
+    const unsigned int gid = blockIdx.x * 256u + threadIdx.x;
+    if (gid >= g.groups) return;
+    unsigned int row, xg, zb, y, b, z;
+    fast_divmod(gid, g.dXG, row, xg);
+    fast_divmod(row, g.dD1, zb, y);
+    fast_divmod(zb, g.dD0, b, z);
+    const int S = g.D0 * g.D1 * g.D2;
+    const int x0 = xg * VEC;
+    const int v0 = (z * g.D1 + y) * g.D2 + x0;
+    const float *f = df + (i64)b * 3 * S + v0;
 
-        float dz[VEC], dy[VEC], dx[VEC];
-        if (VEC == 4) {
-            float4 t0 = ld_stream4(f), t1 = ld_stream4(f + S), t2 = ld_stream4(f + 2 * S);
-            dz[0] = t0.x; dz[1 % VEC] = t0.y; dz[2 % VEC] = t0.z; dz[3 % VEC] = t0.w;
-            dy[0] = t1.x; dy[1 % VEC] = t1.y; dy[2 % VEC] = t1.z; dy[3 % VEC] = t1.w;
-            dx[0] = t2.x; dx[1 % VEC] = t2.y; dx[2 % VEC] = t2.z; dx[3 % VEC] = t2.w;
-        } else {
-            dz[0] = __ldg(f); dy[0] = __ldg(f + S); dx[0] = __ldg(f + 2 * S);
-        }
+    float dz[VEC], dy[VEC], dx[VEC];
+    load_vec<VEC>(f, dz);
+    load_vec<VEC>(f + S, dy);
+    load_vec<VEC>(f + 2 * S, dx);
+    const float zf = (float)(int)z, yf = (float)(int)y, xf0 = (float)x0;
 
-        VoxTaps tp[VEC];
+    Foot ft[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) ft[j] = make_foot<MODE>(zf, yf, xf0 + (float)j, dz[j], dy[j], dx[j], g);
+    if (idx) {
+        int32_t *o = idx + (i64)b * 3 * S + v0;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            tp[j].z = make_tap<MODE>(z, dz[j], a0, D0);
-            tp[j].y = make_tap<MODE>(y, dy[j], a1, D1);
-            tp[j].x = make_tap<MODE>(x0 + j, dx[j], a2, D2);
-            tp[j].base = ((i64)tp[j].z.i * D1 + tp[j].y.i) * D2 + tp[j].x.i;
+            // recover floor(p) = (iz, iy, ix) from the (possibly border-shifted) base offset
+            int rem = ft[j].base;
+            int iz = rem / (g.D1 * g.D2);
+            rem -= iz * g.D1 * g.D2;
+            int iy = rem / g.D2;
+            o[j] = iz + ft[j].hz; o[S + j] = iy + ft[j].hy; o[2 * S + j] = rem - iy * g.D2 + ft[j].hx;
         }
-        if (idx) {
-            int32_t *o = idx + (i64)b * 3 * S + v0;
+    }
+    const int sy = g.D2, sz = g.D1 * g.D2;
+    for (int c = 0; c < g.C; ++c) {
+        const float *im = img + ((i64)b * g.C + c) * S;
+        float res[VEC];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                o[j] = tp[j].z.i; o[S + j] = tp[j].y.i; o[2 * S + j] = tp[j].x.i;
-            }
+        for (int j = 0; j < VEC; ++j) {
+            const Foot &k = ft[j];
+            const float *p = im + k.base;
+            const float *py = p + sy, *pz = p + sz, *pzy = pz + sy;
+            const float c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(py), c011 = __ldg(py + 1);
+            const float c100 = __ldg(pz), c101 = __ldg(pz + 1), c110 = __ldg(pzy), c111 = __ldg(pzy + 1);
+            // same corner order and op order as the CPU grid sampler: bit-identical to torch-CPU
+            const float w00 = __fmul_rn(k.wx0, k.wy0), w01 = __fmul_rn(k.wx1, k.wy0);
+            const float w10 = __fmul_rn(k.wx0, k.wy1), w11 = __fmul_rn(k.wx1, k.wy1);
+            float acc = __fmul_rn(c000, __fmul_rn(w00, k.wz0));
+            acc = __fadd_rn(acc, __fmul_rn(c001, __fmul_rn(w01, k.wz0)));
+            acc = __fadd_rn(acc, __fmul_rn(c010, __fmul_rn(w10, k.wz0)));
+            acc = __fadd_rn(acc, __fmul_rn(c011, __fmul_rn(w11, k.wz0)));
+            acc = __fadd_rn(acc, __fmul_rn(c100, __fmul_rn(w00, k.wz1)));
+            acc = __fadd_rn(acc, __fmul_rn(c101, __fmul_rn(w01, k.wz1)));
+            acc = __fadd_rn(acc, __fmul_rn(c110, __fmul_rn(w10, k.wz1)));
+            acc = __fadd_rn(acc, __fmul_rn(c111, __fmul_rn(w11, k.wz1)));
+            res[j] = acc;
         }
-        for (int c = 0; c < C; ++c) {
-            const float *im = img + ((i64)b * C + c) * S;
-            float res[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const Tap &tz = tp[j].z, &ty = tp[j].y, &tx = tp[j].x;
-                const float *p = im + tp[j].base;
-                // same corner order and op order as the CPU grid sampler: bit-exact vs torch-CPU
-                float c000 = __ldg(p);
-                float c001 = tx.in1 ? __ldg(p + 1) : 0.0f;
-                float c010 = ty.in1 ? __ldg(p + sy) : 0.0f;
-                float c011 = (ty.in1 && tx.in1) ? __ldg(p + sy + 1) : 0.0f;
-                float c100 = tz.in1 ? __ldg(p + sz) : 0.0f;
-                float c101 = (tz.in1 && tx.in1) ? __ldg(p + sz + 1) : 0.0f;
-                float c110 = (tz.in1 && ty.in1) ? __ldg(p + sz + sy) : 0.0f;
-                float c111 = (tz.in1 && ty.in1 && tx.in1) ? __ldg(p + sz + sy + 1) : 0.0f;
-                float w00 = __fmul_rn(tx.w0, ty.w0), w01 = __fmul_rn(tx.w1, ty.w0);
-                float w10 = __fmul_rn(tx.w0, ty.w1), w11 = __fmul_rn(tx.w1, ty.w1);
-                float acc = __fmul_rn(c000, __fmul_rn(w00, tz.w0));
-                acc = __fadd_rn(acc, __fmul_rn(c001, __fmul_rn(w01, tz.w0)));
-                acc = __fadd_rn(acc, __fmul_rn(c010, __fmul_rn(w10, tz.w0)));
-                acc = __fadd_rn(acc, __fmul_rn(c011, __fmul_rn(w11, tz.w0)));
-                acc = __fadd_rn(acc, __fmul_rn(c100, __fmul_rn(w00, tz.w1)));
-                acc = __fadd_rn(acc, __fmul_rn(c101, __fmul_rn(w01, tz.w1)));
-                acc = __fadd_rn(acc, __fmul_rn(c110, __fmul_rn(w10, tz.w1)));
-                acc = __fadd_rn(acc, __fmul_rn(c111, __fmul_rn(w11, tz.w1)));
-                res[j] = acc;
-            }
-            float *o = out + ((i64)b * C + c) * S + v0;
-            if (VEC == 4)
-                *reinterpret_cast<float4 *>(o) = make_float4(res[0], res[1 % VEC], res[2 % VEC], res[3 % VEC]);
-            else
-                o[0] = res[0];
-        }
+        store_vec<VEC>(out + ((i64)b * g.C + c) * S + v0, res);
     }
 }
 
@@ -101,116 +142,89 @@ warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, f
 template <int MODE, int VEC, bool SCATTER>
 __global__ void __launch_bounds__(256)
 warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ df,
-                  float *__restrict__ gimg, float *__restrict__ gdf, int B, int C, int D0, int D1, int D2,
-                  AxisConst a0, AxisConst a1, AxisConst a2)
+                  float *__restrict__ gimg, float *__restrict__ gdf, const WarpGeom g)
 {
-    const int XG = D2 / VEC;
-    const i64 S = (i64)D0 * D1 * D2;
-    const i64 sy = D2, sz = (i64)D1 * D2;
-    const i64 groups = (i64)B * D0 * D1 * XG;
-    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < groups; g += (i64)gridDim.x * blockDim.x) {
-        int xg = (int)(g % XG);
-        i64 r = g / XG;
-        int y = (int)(r % D1);
-        r /= D1;
-        int z = (int)(r % D0);
-        int b = (int)(r / D0);
-        const int x0 = xg * VEC;
-        const i64 v0 = ((i64)z * D1 + y) * D2 + x0;
-        const float *f = df + (i64)b * 3 * S + v0;
+    const unsigned int gid = blockIdx.x * 256u + threadIdx.x;
+    if (gid >= g.groups) return;
+    unsigned int row, xg, zb, y, b, z;
+    fast_divmod(gid, g.dXG, row, xg);
+    fast_divmod(row, g.dD1, zb, y);
+    fast_divmod(zb, g.dD0, b, z);
+    const int S = g.D0 * g.D1 * g.D2;
+    const int x0 = xg * VEC;
+    const int v0 = (z * g.D1 + y) * g.D2 + x0;
+    const float *f = df + (i64)b * 3 * S + v0;
 
-        float dz[VEC], dy[VEC], dx[VEC];
-        if (VEC == 4) {
-            float4 t0 = ld_stream4(f), t1 = ld_stream4(f + S), t2 = ld_stream4(f + 2 * S);
-            dz[0] = t0.x; dz[1 % VEC] = t0.y; dz[2 % VEC] = t0.z; dz[3 % VEC] = t0.w;
-            dy[0] = t1.x; dy[1 % VEC] = t1.y; dy[2 % VEC] = t1.z; dy[3 % VEC] = t1.w;
-            dx[0] = t2.x; dx[1 % VEC] = t2.y; dx[2 % VEC] = t2.z; dx[3 % VEC] = t2.w;
-        } else {
-            dz[0] = __ldg(f); dy[0] = __ldg(f + S); dx[0] = __ldg(f + 2 * S);
-        }
+    float dz[VEC], dy[VEC], dx[VEC];
+    load_vec<VEC>(f, dz);
+    load_vec<VEC>(f + S, dy);
+    load_vec<VEC>(f + 2 * S, dx);
+    const float zf = (float)(int)z, yf = (float)(int)y, xf0 = (float)x0;
 
-        VoxTaps tp[VEC];
-        float mz[VEC], my[VEC], mx[VEC], gz[VEC], gy[VEC], gx[VEC];
+    const int sy = g.D2, sz = g.D1 * g.D2;
+    Foot ft[VEC];
+    float mz[VEC], my[VEC], mx[VEC], gz[VEC], gy[VEC], gx[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        float uz, uy, ux;
+        ft[j] = make_foot<MODE>(zf, yf, xf0 + (float)j, dz[j], dy[j], dx[j], g, &uz, &uy, &ux);
+        // zero gradient wherever the border clamp is active (p <= 0 or p >= S-1)
+        mz[j] = (uz <= 0.0f || uz >= g.a0.Sm1) ? 0.0f : g.a0.gmul;
+        my[j] = (uy <= 0.0f || uy >= g.a1.Sm1) ? 0.0f : g.a1.gmul;
+        mx[j] = (ux <= 0.0f || ux >= g.a2.Sm1) ? 0.0f : g.a2.gmul;
+        gz[j] = gy[j] = gx[j] = 0.0f;
+    }
+    for (int c = 0; c < g.C; ++c) {
+        const i64 off = ((i64)b * g.C + c) * S;
+        const float *im = img + off;
+        float go[VEC];
+        load_vec<VEC>(gout + off + v0, go);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            float uz, uy, ux;
-            tp[j].z = make_tap<MODE>(z, dz[j], a0, D0, &uz);
-            tp[j].y = make_tap<MODE>(y, dy[j], a1, D1, &uy);
-            tp[j].x = make_tap<MODE>(x0 + j, dx[j], a2, D2, &ux);
-            tp[j].base = ((i64)tp[j].z.i * D1 + tp[j].y.i) * D2 + tp[j].x.i;
-            // zero gradient wherever the border clamp is active (p <= 0 or p >= S-1)
-            mz[j] = (uz <= 0.0f || uz >= a0.Sm1) ? 0.0f : a0.gmul;
-            my[j] = (uy <= 0.0f || uy >= a1.Sm1) ? 0.0f : a1.gmul;
-            mx[j] = (ux <= 0.0f || ux >= a2.Sm1) ? 0.0f : a2.gmul;
-            gz[j] = gy[j] = gx[j] = 0.0f;
-        }
-        for (int c = 0; c < C; ++c) {
-            const i64 off = ((i64)b * C + c) * S;
-            const float *im = img + off;
-            float go[VEC];
-            if (VEC == 4) {
-                float4 t = ld_stream4(gout + off + v0);
-                go[0] = t.x; go[1 % VEC] = t.y; go[2 % VEC] = t.z; go[3 % VEC] = t.w;
-            } else {
-                go[0] = __ldg(gout + off + v0);
+            const Foot &k = ft[j];
+            const float *p = im + k.base;
+            const float *py = p + sy, *pz = p + sz, *pzy = pz + sy;
+            const float c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(py), c011 = __ldg(py + 1);
+            const float c100 = __ldg(pz), c101 = __ldg(pz + 1), c110 = __ldg(pzy), c111 = __ldg(pzy + 1);
+            // d/dx: difference along x, interpolated along y and z; likewise for y and z
+            const float sx = ((c001 - c000) * k.wy0 + (c011 - c010) * k.wy1) * k.wz0 +
+                             ((c101 - c100) * k.wy0 + (c111 - c110) * k.wy1) * k.wz1;
+            const float sy_ = ((c010 - c000) * k.wx0 + (c011 - c001) * k.wx1) * k.wz0 +
+                             ((c110 - c100) * k.wx0 + (c111 - c101) * k.wx1) * k.wz1;
+            const float sz_ = ((c100 - c000) * k.wx0 + (c101 - c001) * k.wx1) * k.wy0 +
+                             ((c110 - c010) * k.wx0 + (c111 - c011) * k.wx1) * k.wy1;
+            gx[j] += sx * go[j];
+            gy[j] += sy_ * go[j];
+            gz[j] += sz_ * go[j];
+            if (SCATTER) {
+                float *q = gimg + off + k.base;
+                const float w00 = k.wx0 * k.wy0, w01 = k.wx1 * k.wy0, w10 = k.wx0 * k.wy1, w11 = k.wx1 * k.wy1;
+                const float g0 = go[j] * k.wz0, g1 = go[j] * k.wz1;
+                atomicAdd(q, w00 * g0);
+                atomicAdd(q + 1, w01 * g0);
+                atomicAdd(q + sy, w10 * g0);
+                atomicAdd(q + sy + 1, w11 * g0);
+                atomicAdd(q + sz, w00 * g1);
+                atomicAdd(q + sz + 1, w01 * g1);
+                atomicAdd(q + sz + sy, w10 * g1);
+                atomicAdd(q + sz + sy + 1, w11 * g1);
             }
+        }
+    }
+    if (gdf) {
+        float *o = gdf + (i64)b * 3 * S + v0;
+        float rz[VEC], ry[VEC], rx[VEC];
+        // autograd chain of 2*(loc/(S-1)-0.5) after the sampler's S/2:  (m*g*2)/(S-1)
+        const float kz = 2.0f * g.a0.rcp, ky = 2.0f * g.a1.rcp, kx = 2.0f * g.a2.rcp;
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const Tap &tz = tp[j].z, &ty = tp[j].y, &tx = tp[j].x;
-                const float *p = im + tp[j].base;
-                float c000 = __ldg(p);
-                float c001 = tx.in1 ? __ldg(p + 1) : 0.0f;
-                float c010 = ty.in1 ? __ldg(p + sy) : 0.0f;
-                float c011 = (ty.in1 && tx.in1) ? __ldg(p + sy + 1) : 0.0f;
-                float c100 = tz.in1 ? __ldg(p + sz) : 0.0f;
-                float c101 = (tz.in1 && tx.in1) ? __ldg(p + sz + 1) : 0.0f;
-                float c110 = (tz.in1 && ty.in1) ? __ldg(p + sz + sy) : 0.0f;
-                float c111 = (tz.in1 && ty.in1 && tx.in1) ? __ldg(p + sz + sy + 1) : 0.0f;
-                // d/dx: difference along x, interpolated along y and z; likewise for y, z
-                float ex0 = c001 - c000, ex1 = c011 - c010, ex2 = c101 - c100, ex3 = c111 - c110;
-                float sx = (ex0 * ty.w0 + ex1 * ty.w1) * tz.w0 + (ex2 * ty.w0 + ex3 * ty.w1) * tz.w1;
-                float ey0 = c010 - c000, ey1 = c011 - c001, ey2 = c110 - c100, ey3 = c111 - c101;
-                float sy_ = (ey0 * tx.w0 + ey1 * tx.w1) * tz.w0 + (ey2 * tx.w0 + ey3 * tx.w1) * tz.w1;
-                float ez0 = c100 - c000, ez1 = c101 - c001, ez2 = c110 - c010, ez3 = c111 - c011;
-                float sz_ = (ez0 * tx.w0 + ez1 * tx.w1) * ty.w0 + (ez2 * tx.w0 + ez3 * tx.w1) * ty.w1;
-                gx[j] += sx * go[j];
-                gy[j] += sy_ * go[j];
-                gz[j] += sz_ * go[j];
-                if (SCATTER) {
-                    float *q = gimg + off + tp[j].base;
-                    float w00 = tx.w0 * ty.w0, w01 = tx.w1 * ty.w0, w10 = tx.w0 * ty.w1, w11 = tx.w1 * ty.w1;
-                    float g0 = go[j] * tz.w0, g1 = go[j] * tz.w1;
-                    atomicAdd(q, w00 * g0);
-                    if (tx.in1) atomicAdd(q + 1, w01 * g0);
-                    if (ty.in1) atomicAdd(q + sy, w10 * g0);
-                    if (ty.in1 && tx.in1) atomicAdd(q + sy + 1, w11 * g0);
-                    if (tz.in1) {
-                        atomicAdd(q + sz, w00 * g1);
-                        if (tx.in1) atomicAdd(q + sz + 1, w01 * g1);
-                        if (ty.in1) atomicAdd(q + sz + sy, w10 * g1);
-                        if (ty.in1 && tx.in1) atomicAdd(q + sz + sy + 1, w11 * g1);
-                    }
-                }
-            }
+        for (int j = 0; j < VEC; ++j) {
+            rz[j] = (mz[j] * gz[j]) * kz;
+            ry[j] = (my[j] * gy[j]) * ky;
+            rx[j] = (mx[j] * gx[j]) * kx;
         }
-        if (gdf) {
-            float *o = gdf + (i64)b * 3 * S + v0;
-            float rz[VEC], ry[VEC], rx[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                // autograd chain of 2*(loc/(S-1)-0.5): (g*2)/(S-1), after the sampler's S/2
-                rz[j] = __fdiv_rn((mz[j] * gz[j]) * 2.0f, a0.Sm1);
-                ry[j] = __fdiv_rn((my[j] * gy[j]) * 2.0f, a1.Sm1);
-                rx[j] = __fdiv_rn((mx[j] * gx[j]) * 2.0f, a2.Sm1);
-            }
-            if (VEC == 4) {
-                *reinterpret_cast<float4 *>(o) = make_float4(rz[0], rz[1 % VEC], rz[2 % VEC], rz[3 % VEC]);
-                *reinterpret_cast<float4 *>(o + S) = make_float4(ry[0], ry[1 % VEC], ry[2 % VEC], ry[3 % VEC]);
-                *reinterpret_cast<float4 *>(o + 2 * S) = make_float4(rx[0], rx[1 % VEC], rx[2 % VEC], rx[3 % VEC]);
-            } else {
-                o[0] = rz[0]; o[S] = ry[0]; o[2 * S] = rx[0];
-            }
-        }
+        store_vec<VEC>(o, rz);
+        store_vec<VEC>(o + S, ry);
+        store_vec<VEC>(o + 2 * S, rx);
     }
 }
 
@@ -218,9 +232,10 @@ template <int MODE, int VEC>
 static int launch_fwd(const float *img, const float *df, float *out, int32_t *idx, int B, int C, int D0, int D1,
                       int D2, cudaStream_t st)
 {
-    i64 groups = (i64)B * D0 * D1 * (D2 / VEC);
-    warp3d_fwd_kernel<MODE, VEC><<<grid_for(groups, 256), 256, 0, st>>>(img, df, out, idx, B, C, D0, D1, D2,
-                                                                      make_axis(D0), make_axis(D1), make_axis(D2));
+    WarpGeom g;
+    int rc = make_geom(g, B, C, D0, D1, D2, VEC);
+    if (rc != PULPO_OK) return rc;
+    warp3d_fwd_kernel<MODE, VEC><<<(g.groups + 255) / 256, 256, 0, st>>>(img, df, out, idx, g);
     return launch_status();
 }
 
@@ -228,14 +243,14 @@ template <int MODE, int VEC>
 static int launch_bwd(const float *gout, const float *img, const float *df, float *gimg, float *gdf, int B, int C,
                       int D0, int D1, int D2, cudaStream_t st)
 {
-    i64 groups = (i64)B * D0 * D1 * (D2 / VEC);
-    int grid = grid_for(groups, 256);
+    WarpGeom g;
+    int rc = make_geom(g, B, C, D0, D1, D2, VEC);
+    if (rc != PULPO_OK) return rc;
+    const unsigned int grid = (g.groups + 255) / 256;
     if (gimg)
-        warp3d_bwd_kernel<MODE, VEC, true><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, B, C, D0, D1, D2,
-                                                                 make_axis(D0), make_axis(D1), make_axis(D2));
+        warp3d_bwd_kernel<MODE, VEC, true><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, g);
     else
-        warp3d_bwd_kernel<MODE, VEC, false><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, B, C, D0, D1, D2,
-                                                                  make_axis(D0), make_axis(D1), make_axis(D2));
+        warp3d_bwd_kernel<MODE, VEC, false><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, g);
     return launch_status();
 }
 

@@ -106,7 +106,7 @@ class _VecInt(torch.autograd.Function):
         B, C, D0, D1, D2 = _dims5(vec, "vec")
         if C != 3:
             raise RuntimeError("pulpo_b200: VecInt expects a 3-channel field, got C=%d" % C)
-        save = 1 if (ctx.needs_input_grad[0] and torch.is_grad_enabled()) else 0
+        save = 1 if ctx.needs_input_grad[0] else 0
         L = _lib.lib()
         nbytes = L.pulpo_vecint_ws_bytes(nsteps, save, B, D0, D1, D2)
         ws = torch.empty(nbytes // 4, dtype=torch.float32, device=vec.device)
@@ -204,7 +204,7 @@ class _NCC(torch.autograd.Function):
         if target.shape != pred.shape:
             raise RuntimeError("pulpo_b200: NCC inputs differ in shape: %s vs %s" % (tuple(pred.shape), tuple(target.shape)))
         L = _lib.lib()
-        need = ctx.needs_input_grad[0] and torch.is_grad_enabled()
+        need = bool(ctx.needs_input_grad[0])
         abc = torch.empty((3,) + tuple(pred.shape), dtype=torch.float32, device=pred.device) if need else None
         nbytes = L.pulpo_ncc_ws_bytes(B, C, D0, D1, D2)
         ws = _workspace(nbytes, pred.device)
@@ -238,11 +238,13 @@ def ncc_loss(y_pred, y_true, win_size=9, gamma=0.05):
 
 # ----------------------------------------------------------------------------- KL (a11)
 def _const_value(t):
-    """value of an expanded (all strides 0) constant tensor, else None"""
+    """Value of a tensor tagged as an expanded constant (see components.pulpo.PULPoPrior), else
+    None.  Only the Python-side tag is read: no device access, so this is CUDA-graph safe."""
     if t is None:
         return None
-    if t.numel() > 0 and all(s == 0 for s in t.stride()):
-        return float(t.reshape(-1)[0])
+    tag = getattr(t, "_pulpo_const", None)
+    if tag is not None and t.numel() > 0 and all(s == 0 for s in t.stride()):
+        return float(tag)
     return None
 
 
