@@ -191,7 +191,21 @@ def run_ours(args):
     leaves = list(d.values()) + list(m.values()) + list(s.values())
     scal = torch.zeros(3, device=dev)
 
+    plan = None
+    if args.engine == "plan":
+        from pulpo_b200.plan import HotPathPlan
+        plan = HotPathPlan(size, total, latent, batch=B, device=dev)
+        dd = {l: d[l].detach() for l in d}
+        mm = {l: m[l].detach() for l in m}
+        ss = {l: s[l].detach() for l in s}
+
     def step():
+        if plan is not None:     # pre-planned multi-stream launch sequence (same kernels, no autograd)
+            loss = plan.run(x, y, dd, mm, ss)
+            if world > 1:
+                scal.copy_(plan.losses.sum(dim=1))
+                dist.all_reduce(scal)
+            return loss
         for t in leaves:
             t.grad = None
         loss, parts, _ = hp(x, y, d, m, s)
@@ -332,7 +346,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "pairs_per_gpu": B, "voxels_per_pair": nvox,
                        "levels": "%d total / %d latent, level_res, 7 integration steps" % (total, latent),
-                       "launch": launch_mode, "parallelism": "pairs sharded over %d GPU(s), no data-path collective" % world,
+                       "launch": launch_mode, "engine": args.engine, "parallelism": "pairs sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "per-step working set ~1.5 GB >> 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
@@ -360,6 +374,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="oasis_160x192x224_5tot_4lat", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=1, help="pairs per GPU")
+    ap.add_argument("--engine", default="plan", choices=["plan", "autograd"],
+                    help="plan: pre-planned multi-stream C-ABI sequence; autograd: the drop-in nn.Modules")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -80,8 +80,9 @@ int pulpo_vecint_bwd(const float *gout, const void *saved, float *gvec, void *sc
  * out/addend: [B,C,f*d0,f*d1,f*d2].  factor: integer >= 2.  addend nullable. */
 int pulpo_resize_up_fwd(const float *x, const float *addend, float *out, int factor, float scale,
                         int B, int C, int d0, int d1, int d2, pulpo_stream_t stream);
-/* exact adjoint w.r.t. x in gather form (no atomics); gout: [B,C,f*d0,f*d1,f*d2] */
-int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, float scale,
+/* exact adjoint w.r.t. x in gather form (no atomics); gout: [B,C,f*d0,f*d1,f*d2].
+ * accumulate != 0: gx += ... (folds the Laplacian-pyramid gradient sum into this pass). */
+int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, float scale, int accumulate,
                         int B, int C, int d0, int d1, int d2, pulpo_stream_t stream);
 
 /* ---- a10: F.interpolate(y, size=..., trilinear, align_corners=False)  src/losses.py:313 --- */
@@ -107,17 +108,20 @@ int pulpo_ncc_bwd(const float *abc, const float *pred, const float *target, cons
 /* ---- a11: KL_two_gauss_with_diag_cov(mu0, sigma0, mu1, sigma1, eps)  src/losses.py:47-76 ---
  * mu1/sigma1 nullable = the N(0,1) prior of src/components/pulpo.py:337-339.  n = C*D0*D1*D2. */
 size_t pulpo_reduce_ws_bytes(void);
+/* out = weight * KL (weight carries the level weight and beta of src/losses.py:268-274,
+ * src/models.py:157); gloss: device scalar, nullable = 1. */
 int pulpo_kl_diag_fwd(const float *mu0, const float *sigma0, const float *mu1, const float *sigma1,
-                      float eps, float *out, void *ws, size_t ws_bytes, int B, long long n,
-                      pulpo_stream_t stream);
-int pulpo_kl_diag_bwd(const float *gloss, const float *mu0, const float *sigma0, const float *mu1,
-                      const float *sigma1, float eps, float *gmu0, float *gsigma0, int B,
+                      float eps, float weight, float *out, void *ws, size_t ws_bytes, int B,
                       long long n, pulpo_stream_t stream);
+int pulpo_kl_diag_bwd(const float *gloss, const float *mu0, const float *sigma0, const float *mu1,
+                      const float *sigma1, float eps, float weight, float *gmu0, float *gsigma0,
+                      int B, long long n, pulpo_stream_t stream);
 
 /* ---- f-1: L2_reg(deformation_field, lamb)   src/losses.py:208-222 (3-D branch) ------------- */
 int pulpo_l2reg_fwd(const float *f, float lamb, float *out, void *ws, size_t ws_bytes,
                     int B, int C, int D0, int D1, int D2, pulpo_stream_t stream);
-int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, float *gf,
+/* accumulate != 0: gf += ... (lets the caller fold this gradient into the warp's gdf) */
+int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, float *gf, int accumulate,
                     int B, int C, int D0, int D1, int D2, pulpo_stream_t stream);
 
 /* ---- f-3: per-voxel MC moments   evaluate.py:243-251 (std over samples) -------------------

@@ -26,17 +26,17 @@ SIGNATURES = {
     "pulpo_vecint_bwd_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "pulpo_vecint_bwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_resize_up_fwd": (_i, [_vp, _vp, _vp, _i, _f, _i, _i, _i, _i, _i, _vp]),
-    "pulpo_resize_up_bwd": (_i, [_vp, _vp, _i, _f, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_resize_up_bwd": (_i, [_vp, _vp, _i, _f, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_interp_size_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_avgpool2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "pulpo_ncc_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "pulpo_ncc_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _f, _i, _i, _i, _i, _i, _vp]),
     "pulpo_ncc_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _i, _i, _i, _i, _vp]),
     "pulpo_reduce_ws_bytes": (_sz, []),
-    "pulpo_kl_diag_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _sz, _i, _ll, _vp]),
-    "pulpo_kl_diag_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _ll, _vp]),
+    "pulpo_kl_diag_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _sz, _i, _ll, _vp]),
+    "pulpo_kl_diag_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _ll, _vp]),
     "pulpo_l2reg_fwd": (_i, [_vp, _f, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
-    "pulpo_l2reg_bwd": (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_l2reg_bwd": (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_moments_update": (_i, [_vp, _vp, _vp, _i, _ll, _vp]),
     "pulpo_moments_merge": (_i, [_vp, _vp, _i, _vp, _vp, _i, _ll, _vp]),
     "pulpo_moments_std": (_i, [_vp, _vp, _i, _ll, _vp]),

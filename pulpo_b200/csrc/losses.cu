@@ -87,7 +87,7 @@ l2reg_fwd_kernel(const float *__restrict__ f, float *out, ReduceWs *ws, double s
 // minus the difference of each forward neighbour that is in the crop
 __global__ void __launch_bounds__(256)
 l2reg_bwd_kernel(const float *__restrict__ gloss, const float *__restrict__ f, float *__restrict__ gf, float kk,
-                 int BC, int D0, int D1, int D2)
+                 int BC, int D0, int D1, int D2, int accumulate)
 {
     const i64 sy = D2, sz = (i64)D1 * D2, S = (i64)D0 * sz, total = (i64)BC * S;
     const float k = (gloss ? __ldg(gloss) : 1.0f) * kk;
@@ -103,7 +103,7 @@ l2reg_bwd_kernel(const float *__restrict__ gloss, const float *__restrict__ f, f
         if (z + 1 < D0 && y > 0 && x > 0) acc -= __ldg(f + g + sz) - c;
         if (y + 1 < D1 && z > 0 && x > 0) acc -= __ldg(f + g + sy) - c;
         if (x + 1 < D2 && z > 0 && y > 0) acc -= __ldg(f + g + 1) - c;
-        gf[g] = k * acc;
+        gf[g] = accumulate ? gf[g] + k * acc : k * acc;
     }
 }
 
@@ -240,7 +240,7 @@ using namespace pulpo;
 extern "C" size_t pulpo_reduce_ws_bytes(void) { return kReduceWsBytes; }
 
 extern "C" int pulpo_kl_diag_fwd(const float *mu0, const float *sigma0, const float *mu1, const float *sigma1,
-                                 float eps, float *out, void *ws, size_t ws_bytes, int B, long long n,
+                                 float eps, float weight, float *out, void *ws, size_t ws_bytes, int B, long long n,
                                  pulpo_stream_t stream)
 {
     PULPO_REQUIRE(mu0 && sigma0 && out && ws, PULPO_ERR_NULL_POINTER);
@@ -250,19 +250,19 @@ extern "C" int pulpo_kl_diag_fwd(const float *mu0, const float *sigma0, const fl
     bool al = aligned16(mu0) && aligned16(sigma0) && (!mu1 || aligned16(mu1)) && (!sigma1 || aligned16(sigma1));
     int grid = grid_for((total + 3) / 4, 256, 4);
     kl_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mu0, sigma0, mu1, sigma1, eps, out, (ReduceWs *)ws,
-                                                        0.5 / (double)B, total, (al && (total & 3) == 0) ? 1 : 0);
+                                                        0.5 * (double)weight / (double)B, total, (al && (total & 3) == 0) ? 1 : 0);
     return launch_status();
 }
 
 extern "C" int pulpo_kl_diag_bwd(const float *gloss, const float *mu0, const float *sigma0, const float *mu1,
-                                 const float *sigma1, float eps, float *gmu0, float *gsigma0, int B, long long n,
-                                 pulpo_stream_t stream)
+                                 const float *sigma1, float eps, float weight, float *gmu0, float *gsigma0, int B,
+                                 long long n, pulpo_stream_t stream)
 {
     PULPO_REQUIRE(mu0 && sigma0 && gmu0 && gsigma0, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && n > 0, PULPO_ERR_INVALID_SHAPE);
     const i64 total = (i64)B * n;
     kl_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(gloss, mu0, sigma0, mu1, sigma1, eps, gmu0,
-                                                                        gsigma0, 1.0f / (float)B, total);
+                                                                        gsigma0, weight / (float)B, total);
     return launch_status();
 }
 
@@ -284,8 +284,8 @@ extern "C" int pulpo_l2reg_fwd(const float *f, float lamb, float *out, void *ws,
     return launch_status();
 }
 
-extern "C" int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, float *gf, int B, int C, int D0,
-                               int D1, int D2, pulpo_stream_t stream)
+extern "C" int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, float *gf, int accumulate, int B,
+                               int C, int D0, int D1, int D2, pulpo_stream_t stream)
 {
     PULPO_REQUIRE(f && gf, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2, PULPO_ERR_INVALID_SHAPE);
@@ -294,9 +294,12 @@ extern "C" int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, f
     const float kk = (float)(2.0 * (double)lamb * D0 * D1 * D2 / cnt);
     RowGeom g;
     if (make_rowgeom(g, B * C, D0, D1, D2) && aligned16(f) && aligned16(gf))
-        l2reg_bwd_v4_kernel<false><<<(g.groups + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gloss, f, gf, kk, g);
+        if (accumulate)
+            l2reg_bwd_v4_kernel<true><<<(g.groups + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gloss, f, gf, kk, g);
+        else
+            l2reg_bwd_v4_kernel<false><<<(g.groups + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gloss, f, gf, kk, g);
     else
-        l2reg_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(gloss, f, gf, kk, B * C, D0, D1, D2);
+        l2reg_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(gloss, f, gf, kk, B * C, D0, D1, D2, accumulate);
     return launch_status();
 }
 

@@ -76,7 +76,7 @@ __device__ __forceinline__ float adj_w(int o, int i, int n_in, int n_out, float 
 // outputs per axis whose footprint touches it.
 __global__ void __launch_bounds__(128)
 upsample_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gx, int f, float scale, int BC, int d0,
-                    int d1, int d2)
+                    int d1, int d2, int accumulate)
 {
     const int o0n = f * d0, o1n = f * d1, o2n = f * d2;
     const float s = 1.0f / (float)f;
@@ -108,7 +108,7 @@ upsample_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gx, int 
             }
             acc += wz * accy;
         }
-        gx[g] = scale * acc;
+        gx[g] = accumulate ? gx[g] + scale * acc : scale * acc;
     }
 }
 
@@ -205,6 +205,7 @@ __device__ __forceinline__ void adj4(int j, int n, float (&w)[4])
     w[3] = j < n - 1 ? 0.25f : 0.0f;
 }
 
+template <bool ACC>
 __global__ void __launch_bounds__(128)
 up2_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gx, float scale, const Up2BGeom g)
 {
@@ -243,7 +244,12 @@ up2_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gx, float sca
         for (int t = 0; t < 4; ++t) acc[t] += wz[a] * accy[t];
     }
     float *o = gx + (((i64)bc * d0 + z) * d1 + y) * d2 + 4 * m;
-    *reinterpret_cast<float4 *>(o) = make_float4(scale * acc[0], scale * acc[1], scale * acc[2], scale * acc[3]);
+    float4 res = make_float4(scale * acc[0], scale * acc[1], scale * acc[2], scale * acc[3]);
+    if (ACC) {
+        const float4 old = *reinterpret_cast<float4 *>(o);
+        res.x += old.x; res.y += old.y; res.z += old.z; res.w += old.w;
+    }
+    *reinterpret_cast<float4 *>(o) = res;
 }
 
 // avg_pool3d(kernel 2, stride 2, pad 0, ceil_mode=True): clipped windows, divide by clipped count
@@ -299,8 +305,8 @@ extern "C" int pulpo_resize_up_fwd(const float *x, const float *addend, float *o
     return launch_status();
 }
 
-extern "C" int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, float scale, int B, int C, int d0,
-                                   int d1, int d2, pulpo_stream_t stream)
+extern "C" int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, float scale, int accumulate, int B,
+                                   int C, int d0, int d1, int d2, pulpo_stream_t stream)
 {
     PULPO_REQUIRE(gout && gx, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && d0 > 0 && d1 > 0 && d2 > 0, PULPO_ERR_INVALID_SHAPE);
@@ -310,12 +316,15 @@ extern "C" int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, flo
         g.BC = B * C; g.d0 = d0; g.d1 = d1; g.d2 = d2; g.XQ = d2 / 4;
         g.threads = (unsigned int)((i64)B * C * d0 * d1 * g.XQ);
         g.dXQ = make_fastdiv(g.XQ); g.dd1 = make_fastdiv(d1); g.dd0 = make_fastdiv(d0);
-        up2_bwd_kernel<<<(g.threads + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gout, gx, scale, g);
+        if (accumulate)
+            up2_bwd_kernel<true><<<(g.threads + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gout, gx, scale, g);
+        else
+            up2_bwd_kernel<false><<<(g.threads + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gout, gx, scale, g);
         return launch_status();
     }
     i64 total = (i64)B * C * d0 * d1 * d2;
     upsample_bwd_kernel<<<grid_for(total, 128, 16), 128, 0, (cudaStream_t)stream>>>(gout, gx, factor, scale, B * C,
-                                                                                  d0, d1, d2);
+                                                                                  d0, d1, d2, accumulate);
     return launch_status();
 }
 

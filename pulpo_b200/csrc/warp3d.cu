@@ -162,27 +162,25 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
     const float zf = (float)(int)z, yf = (float)(int)y, xf0 = (float)x0;
 
     const int sy = g.D2, sz = g.D1 * g.D2;
-    Foot ft[VEC];
-    float mz[VEC], my[VEC], mx[VEC], gz[VEC], gy[VEC], gx[VEC];
+    float rz[VEC], ry[VEC], rx[VEC];
+    // autograd chain of 2*(loc/(S-1)-0.5) after the sampler's S/2:  (m*g*2)/(S-1)
+    const float kz = 2.0f * g.a0.rcp, ky = 2.0f * g.a1.rcp, kx = 2.0f * g.a2.rcp;
+    float go1[VEC];
+    if (g.C == 1) load_vec<VEC>(gout + (i64)b * S + v0, go1);   // the common case: one 128-bit load
+    // voxel-outer loop keeps only one footprint live (register pressure -> occupancy)
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         float uz, uy, ux;
-        ft[j] = make_foot<MODE>(zf, yf, xf0 + (float)j, dz[j], dy[j], dx[j], g, &uz, &uy, &ux);
+        const Foot k = make_foot<MODE>(zf, yf, xf0 + (float)j, dz[j], dy[j], dx[j], g, &uz, &uy, &ux);
         // zero gradient wherever the border clamp is active (p <= 0 or p >= S-1)
-        mz[j] = (uz <= 0.0f || uz >= g.a0.Sm1) ? 0.0f : g.a0.gmul;
-        my[j] = (uy <= 0.0f || uy >= g.a1.Sm1) ? 0.0f : g.a1.gmul;
-        mx[j] = (ux <= 0.0f || ux >= g.a2.Sm1) ? 0.0f : g.a2.gmul;
-        gz[j] = gy[j] = gx[j] = 0.0f;
-    }
-    for (int c = 0; c < g.C; ++c) {
-        const i64 off = ((i64)b * g.C + c) * S;
-        const float *im = img + off;
-        float go[VEC];
-        load_vec<VEC>(gout + off + v0, go);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const Foot &k = ft[j];
-            const float *p = im + k.base;
+        const float mz = (uz <= 0.0f || uz >= g.a0.Sm1) ? 0.0f : g.a0.gmul;
+        const float my = (uy <= 0.0f || uy >= g.a1.Sm1) ? 0.0f : g.a1.gmul;
+        const float mx = (ux <= 0.0f || ux >= g.a2.Sm1) ? 0.0f : g.a2.gmul;
+        float gz = 0.0f, gy = 0.0f, gx = 0.0f;
+        for (int c = 0; c < g.C; ++c) {
+            const i64 off = ((i64)b * g.C + c) * S;
+            const float go = (g.C == 1) ? go1[j] : __ldg(gout + off + v0 + j);
+            const float *p = img + off + k.base;
             const float *py = p + sy, *pz = p + sz, *pzy = pz + sy;
             const float c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(py), c011 = __ldg(py + 1);
             const float c100 = __ldg(pz), c101 = __ldg(pz + 1), c110 = __ldg(pzy), c111 = __ldg(pzy + 1);
@@ -190,16 +188,16 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
             const float sx = ((c001 - c000) * k.wy0 + (c011 - c010) * k.wy1) * k.wz0 +
                              ((c101 - c100) * k.wy0 + (c111 - c110) * k.wy1) * k.wz1;
             const float sy_ = ((c010 - c000) * k.wx0 + (c011 - c001) * k.wx1) * k.wz0 +
-                             ((c110 - c100) * k.wx0 + (c111 - c101) * k.wx1) * k.wz1;
+                              ((c110 - c100) * k.wx0 + (c111 - c101) * k.wx1) * k.wz1;
             const float sz_ = ((c100 - c000) * k.wx0 + (c101 - c001) * k.wx1) * k.wy0 +
-                             ((c110 - c010) * k.wx0 + (c111 - c011) * k.wx1) * k.wy1;
-            gx[j] += sx * go[j];
-            gy[j] += sy_ * go[j];
-            gz[j] += sz_ * go[j];
+                              ((c110 - c010) * k.wx0 + (c111 - c011) * k.wx1) * k.wy1;
+            gx += sx * go;
+            gy += sy_ * go;
+            gz += sz_ * go;
             if (SCATTER) {
                 float *q = gimg + off + k.base;
                 const float w00 = k.wx0 * k.wy0, w01 = k.wx1 * k.wy0, w10 = k.wx0 * k.wy1, w11 = k.wx1 * k.wy1;
-                const float g0 = go[j] * k.wz0, g1 = go[j] * k.wz1;
+                const float g0 = go * k.wz0, g1 = go * k.wz1;
                 atomicAdd(q, w00 * g0);
                 atomicAdd(q + 1, w01 * g0);
                 atomicAdd(q + sy, w10 * g0);
@@ -210,18 +208,12 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
                 atomicAdd(q + sz + sy + 1, w11 * g1);
             }
         }
+        rz[j] = (mz * gz) * kz;
+        ry[j] = (my * gy) * ky;
+        rx[j] = (mx * gx) * kx;
     }
     if (gdf) {
         float *o = gdf + (i64)b * 3 * S + v0;
-        float rz[VEC], ry[VEC], rx[VEC];
-        // autograd chain of 2*(loc/(S-1)-0.5) after the sampler's S/2:  (m*g*2)/(S-1)
-        const float kz = 2.0f * g.a0.rcp, ky = 2.0f * g.a1.rcp, kx = 2.0f * g.a2.rcp;
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            rz[j] = (mz[j] * gz[j]) * kz;
-            ry[j] = (my[j] * gy[j]) * ky;
-            rx[j] = (mx[j] * gx[j]) * kx;
-        }
         store_vec<VEC>(o, rz);
         store_vec<VEC>(o + S, ry);
         store_vec<VEC>(o + 2 * S, rx);

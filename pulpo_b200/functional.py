@@ -161,7 +161,7 @@ class _ResizeUp(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             B, C, d0, d1, d2 = ctx.idims
             gx = torch.empty(ctx.idims, dtype=torch.float32, device=gout.device)
-            check(_lib.lib().pulpo_resize_up_bwd(_ptr(gout), _ptr(gx), ctx.factor, ctx.scale, B, C, d0, d1, d2,
+            check(_lib.lib().pulpo_resize_up_bwd(_ptr(gout), _ptr(gx), ctx.factor, ctx.scale, 0, B, C, d0, d1, d2,
                                                  _stream()), "resize_up_bwd")
         return gx, (gout if ctx.needs_input_grad[1] else None), None, None
 
@@ -259,7 +259,7 @@ class _KL(torch.autograd.Function):
         L = _lib.lib()
         ws = _workspace(L.pulpo_reduce_ws_bytes(), mu0.device)
         out = torch.empty((), dtype=torch.float32, device=mu0.device)
-        check(L.pulpo_kl_diag_fwd(_ptr(mu0), _ptr(sigma0), _ptr(mu1), _ptr(sigma1), float(eps), _ptr(out), _ptr(ws),
+        check(L.pulpo_kl_diag_fwd(_ptr(mu0), _ptr(sigma0), _ptr(mu1), _ptr(sigma1), float(eps), 1.0, _ptr(out), _ptr(ws),
                                   ws.numel(), B, n, _stream()), "kl_diag_fwd")
         ctx.eps, ctx.B, ctx.n = float(eps), B, n
         ctx.have1 = (mu1 is not None, sigma1 is not None)
@@ -276,7 +276,7 @@ class _KL(torch.autograd.Function):
         gloss = gloss.to(torch.float32).contiguous()
         gmu, gsg = torch.empty_like(mu0), torch.empty_like(sigma0)
         check(_lib.lib().pulpo_kl_diag_bwd(_ptr(gloss), _ptr(mu0), _ptr(sigma0), _ptr(mu1), _ptr(sigma1), ctx.eps,
-                                           _ptr(gmu), _ptr(gsg), ctx.B, ctx.n, _stream()), "kl_diag_bwd")
+                                           1.0, _ptr(gmu), _ptr(gsg), ctx.B, ctx.n, _stream()), "kl_diag_bwd")
         return gmu, gsg, None, None, None
 
 
@@ -315,7 +315,7 @@ class _L2Reg(torch.autograd.Function):
         B, C, D0, D1, D2 = f.shape
         gloss = gloss.to(torch.float32).contiguous()
         gf = torch.empty_like(f)
-        check(_lib.lib().pulpo_l2reg_bwd(_ptr(gloss), _ptr(f), ctx.lamb, _ptr(gf), B, C, D0, D1, D2, _stream()),
+        check(_lib.lib().pulpo_l2reg_bwd(_ptr(gloss), _ptr(f), ctx.lamb, _ptr(gf), 0, B, C, D0, D1, D2, _stream()),
               "l2reg_bwd")
         return gf, None
 

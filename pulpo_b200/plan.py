@@ -1,0 +1,217 @@
+"""HotPathPlan -- the whole registration hot path (forward + backward) as one pre-planned,
+multi-stream, CUDA-graph-capturable sequence of C-ABI launches.
+
+Same arithmetic and the same kernels as the autograd drop-in modules (``RegistrationHotPath``),
+but orchestrated B200-first:
+  * every buffer (outputs, saved integration states, NCC coefficient volumes, gradients,
+    reduction workspaces) is allocated once, so a step is pure kernel launches and can be
+    replayed as a CUDA graph;
+  * the latent levels are independent once the coarse-to-fine field combination is done, so
+    each level runs on its own stream: the three small levels (<= 107 k voxels, pure launch /
+    grid-sync latency) hide behind the full-resolution level instead of serialising with it;
+  * the loss weights (level weight, beta, gamma, lambda; reference src/models.py:104-123,157)
+    are folded into the kernels' scale arguments, so the backward of every loss term starts
+    right after its forward -- no scalar graph, no autograd bookkeeping kernels;
+  * gradient sums that autograd would do in extra passes are folded into producers:
+    L2-reg's gradient accumulates into the warp's field gradient, the Laplacian-pyramid
+    up-sampling adjoint accumulates into the coarser level's gradient.
+
+Reference call structure reproduced: SVFDecoder.forward (src/components/pulpo.py:301-319) per
+level, Autoencoder's moving pyramid (:168-179), HierarchicalReconstructionLoss / KLLoss /
+Regularization (src/losses.py:225-355) with PULPo's weights (src/models.py:104-123).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import CPU_EXACT, check
+from .models import loss_config
+from .synthetic import level_sizes
+
+_vp = ctypes.c_void_p
+
+
+def _p(t, byte_offset=0):
+    return None if t is None else _vp(t.data_ptr() + byte_offset)
+
+
+class HotPathPlan:
+    def __init__(self, input_size, total_levels, latent_levels, batch=1, beta=0.1, gamma=0.05, lamb=0.025,
+                 with_reg=True, nsteps=7, coord_mode=CPU_EXACT, device=None, multi_stream=True):
+        self.L = L = latent_levels
+        self.B = B = batch
+        self.lk = lk = total_levels - latent_levels
+        self.nsteps, self.mode, self.with_reg = nsteps, coord_mode, with_reg
+        self.dev = dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.lib = _lib.lib()
+        self.full = tuple(int(s) for s in input_size)
+        sizes = level_sizes(self.full, total_levels)
+        self.insz = {l: tuple(sizes[lk + l]) for l in range(L)}
+        self.outsz = {l: (self.full if l == 0 else self.insz[l]) for l in range(L)}
+        for l in range(L):
+            if l == 0 and self.insz[0] != self.full and tuple(2 * s for s in self.insz[0]) != self.full:
+                raise NotImplementedError("HotPathPlan: level-0 output resize must be x1 or x2 (got %s -> %s)"
+                                          % (self.insz[0], self.full))
+            if l + 1 < L and tuple(2 * s for s in self.insz[l + 1]) != self.insz[l]:
+                raise ValueError("level sizes must halve exactly (reference DFAdder would shape-mismatch)")
+        win, kl_w, rec_w, reg_w = loss_config(L, lk)
+        self.win = win
+        self.kl_weight = {l: float(beta * kl_w[l]) for l in range(L)}
+        self.gamma_eff = {l: float(gamma * rec_w[l]) for l in range(L)}
+        self.lamb_eff = {l: float(lamb * reg_w[l]) for l in range(L)}
+
+        def buf(*shape):
+            return torch.empty(shape, dtype=torch.float32, device=dev)
+
+        lib = self.lib
+        # moving pyramid: pooled[i] = x pooled (i+1) times; level l >= 1 uses pooled[lk + l - 1]
+        self.pooled, s = [], self.full
+        for _ in range(lk + L - 1 if L > 1 else 0):
+            s = tuple((v + 1) // 2 for v in s)
+            self.pooled.append(buf(B, 1, *s))
+        self.yt = {l: buf(B, 1, *self.outsz[l]) for l in range(L) if self.outsz[l] != self.full}
+        self.comb = {l: buf(B, 3, *self.insz[l]) for l in range(L - 1)}          # coarsest level aliases its input
+        self.integ = {l: buf(B, 3, *self.insz[l]) for l in range(L)}
+        self.final = {l: (buf(B, 3, *self.outsz[l]) if self.outsz[l] != self.insz[l] else self.integ[l]) for l in range(L)}
+        self.moved = {l: buf(B, 1, *self.outsz[l]) for l in range(L)}
+        self.vi_ws, self.vi_scr = {}, {}
+        for l in range(L):
+            d = self.insz[l]
+            self.vi_ws[l] = buf(lib.pulpo_vecint_ws_bytes(nsteps, 1, B, *d) // 4)
+            self.vi_scr[l] = buf(lib.pulpo_vecint_bwd_scratch_bytes(B, *d) // 4)
+        self.abc = {l: buf(3, B, 1, *self.outsz[l]) for l in range(L)}
+        self.gmoved = {l: buf(B, 1, *self.outsz[l]) for l in range(L)}
+        self.gfinal = {l: buf(B, 3, *self.outsz[l]) for l in range(L)}
+        self.ginteg = {l: (buf(B, 3, *self.insz[l]) if self.outsz[l] != self.insz[l] else self.gfinal[l]) for l in range(L)}
+        self.gdf = {l: buf(B, 3, *self.insz[l]) for l in range(L)}
+        self.gmu = {l: buf(B, 3, *self.insz[l]) for l in range(L)}
+        self.gsigma = {l: buf(B, 3, *self.insz[l]) for l in range(L)}
+        self.losses = torch.zeros(3, L, dtype=torch.float32, device=dev)        # rows: kl, recon, reg
+        self.total = torch.zeros((), dtype=torch.float32, device=dev)
+        # reduction workspaces (ticket counters must start at zero; kernels reset them)
+        rbytes = lib.pulpo_reduce_ws_bytes()
+        self.ws_kl = [torch.zeros(rbytes, dtype=torch.uint8, device=dev) for _ in range(L)]
+        self.ws_l2 = [torch.zeros(rbytes, dtype=torch.uint8, device=dev) for _ in range(L)]
+        self.ws_ncc = [torch.zeros(lib.pulpo_ncc_ws_bytes(B, 1, *self.outsz[l]), dtype=torch.uint8, device=dev)
+                       for l in range(L)]
+        self.multi_stream = multi_stream
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(L + 1)] if multi_stream else None
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _loss_ptr(self, row, l):
+        return _p(self.losses, 4 * (row * self.L + l))
+
+    def run(self, x, y, dfs, mus, sigmas):
+        """Enqueue one forward+backward.  Inputs: contiguous fp32 CUDA tensors (x, y: [B,1,*full];
+        dfs/mus/sigmas: {level: [B,3,*level_size]}).  Returns the 0-d total-loss tensor; per-term
+        losses are in ``self.losses`` and gradients in ``self.gdf / gmu / gsigma``."""
+        lib, L, B, mode = self.lib, self.L, self.B, self.mode
+        cur = torch.cuda.current_stream(self.dev)
+        ms = self.multi_stream
+        lv = [self.streams[l] if ms else cur for l in range(L)]
+        aux = self.streams[L] if ms else cur
+        n = [0]
+
+        def call(fn, *a):
+            n[0] += 1
+            check(fn(*a), fn.__name__ if hasattr(fn, "__name__") else "")
+
+        def H(s):
+            return _vp(s.cuda_stream)
+
+        start = torch.cuda.Event()
+        start.record(cur)
+        # ---- moving-image pyramid on the aux stream (pulpo.py:168-179)
+        if ms:
+            aux.wait_event(start)
+        ev_lx = {}
+        src, shape = x, self.full
+        for i, dst in enumerate(self.pooled):
+            call(lib.pulpo_avgpool2_fwd, _p(src), _p(dst), B, 1, *shape, H(aux))
+            src, shape = dst, tuple(dst.shape[2:])
+            l = i - self.lk + 1
+            if l >= 1:
+                ev_lx[l] = torch.cuda.Event()
+                ev_lx[l].record(aux)
+        lx = {0: x}
+        for l in range(1, L):
+            lx[l] = self.pooled[self.lk + l - 1]
+
+        # ---- coarse-to-fine field combination on the current stream (pulpo.py:308)
+        comb = {L - 1: dfs[L - 1]}
+        ev_comb = {}
+        for l in range(L - 2, -1, -1):
+            d = self.insz[l + 1]
+            call(lib.pulpo_resize_up_fwd, _p(comb[l + 1]), _p(dfs[l]), _p(self.comb[l]), 2, 2.0, B, 3, *d, H(cur))
+            comb[l] = self.comb[l]
+            ev_comb[l] = torch.cuda.Event()
+            ev_comb[l].record(cur)
+
+        # ---- per level: integrate, resize, warp, losses and their backward, on the level's stream
+        ev_done = {}
+        for l in range(L - 1, -1, -1):
+            s = lv[l]
+            if ms:
+                s.wait_event(ev_comb[l] if l in ev_comb else start)
+            din, dout = self.insz[l], self.outsz[l]
+            nlat = 3 * din[0] * din[1] * din[2]
+            hs = H(s)
+            # KL (losses.py:47-76 with the N(0,1) prior; weight = level weight * beta)
+            call(lib.pulpo_kl_diag_fwd, _p(mus[l]), _p(sigmas[l]), None, None, 1e-10, self.kl_weight[l],
+                 self._loss_ptr(0, l), _p(self.ws_kl[l]), self.ws_kl[l].numel(), B, nlat, hs)
+            call(lib.pulpo_kl_diag_bwd, None, _p(mus[l]), _p(sigmas[l]), None, None, 1e-10, self.kl_weight[l],
+                 _p(self.gmu[l]), _p(self.gsigma[l]), B, nlat, hs)
+            # integrate (VecInt) and resize to the output size
+            ws = self.vi_ws[l]
+            call(lib.pulpo_vecint_fwd, _p(comb[l]), _p(self.integ[l]), _p(ws), ws.numel() * 4, self.nsteps, 1, B,
+                 *din, mode, hs)
+            if dout != din:
+                call(lib.pulpo_resize_up_fwd, _p(self.integ[l]), None, _p(self.final[l]), 2, 2.0, B, 3, *din, hs)
+            # warp the (pooled) moving image
+            if ms and l in ev_lx:
+                s.wait_event(ev_lx[l])
+            call(lib.pulpo_warp3d_fwd, _p(lx[l]), _p(self.final[l]), _p(self.moved[l]), None, B, 1, *dout, mode, hs)
+            # NCC against the resized fixed image (losses.py:313-318), backward immediately
+            if dout != self.full:
+                call(lib.pulpo_interp_size_fwd, _p(y), _p(self.yt[l]), B, 1, *self.full, *dout, hs)
+                yt = self.yt[l]
+            else:
+                yt = y
+            wsn = self.ws_ncc[l]
+            call(lib.pulpo_ncc_fwd, _p(self.moved[l]), _p(yt), self._loss_ptr(1, l), _p(self.abc[l]), _p(wsn),
+                 wsn.numel(), self.win[l], self.gamma_eff[l], B, 1, *dout, hs)
+            call(lib.pulpo_ncc_bwd, _p(self.abc[l]), _p(self.moved[l]), _p(yt), None, _p(self.gmoved[l]),
+                 self.win[l], self.gamma_eff[l], B, 1, *dout, hs)
+            call(lib.pulpo_warp3d_bwd, _p(self.gmoved[l]), _p(lx[l]), _p(self.final[l]), None, _p(self.gfinal[l]),
+                 B, 1, *dout, mode, hs)
+            if self.with_reg:   # L2_reg on the final field; its gradient accumulates into the warp's
+                call(lib.pulpo_l2reg_fwd, _p(self.final[l]), self.lamb_eff[l], self._loss_ptr(2, l),
+                     _p(self.ws_l2[l]), self.ws_l2[l].numel(), B, 3, *dout, hs)
+                call(lib.pulpo_l2reg_bwd, None, _p(self.final[l]), self.lamb_eff[l], _p(self.gfinal[l]), 1, B, 3,
+                     *dout, hs)
+            if dout != din:
+                call(lib.pulpo_resize_up_bwd, _p(self.gfinal[l]), _p(self.ginteg[l]), 2, 2.0, 0, B, 3, *din, hs)
+            scr = self.vi_scr[l]
+            call(lib.pulpo_vecint_bwd, _p(self.ginteg[l]), _p(ws), _p(self.gdf[l]), _p(scr), scr.numel() * 4,
+                 self.nsteps, B, *din, mode, hs)
+            ev_done[l] = torch.cuda.Event()
+            ev_done[l].record(s)
+
+        # ---- fine-to-coarse: the adjoint of the combination accumulates into the coarser gradient
+        if ms:
+            cur.wait_event(ev_done[0])
+        for l in range(1, L):
+            if ms:
+                cur.wait_event(ev_done[l])
+            call(lib.pulpo_resize_up_bwd, _p(self.gdf[l - 1]), _p(self.gdf[l]), 2, 2.0, 1, B, 3, *self.insz[l], H(cur))
+        torch.sum(self.losses, dim=(0, 1), out=self.total)
+        self.launches = n[0]
+        return self.total
+
+    # convenience -----------------------------------------------------------------------------
+    def outputs(self):
+        return {"combined": dict(self.comb), "final": dict(self.final), "moved": dict(self.moved)}

@@ -26,9 +26,9 @@ def algo_bytes(name, args):
     if name == "pulpo_resize_up_fwd":       # x, addend, out, factor, scale, B, C, d0, d1, d2
         f, B, C, n = a[3], a[5], a[6], a[7] * a[8] * a[9]
         return B * C * 4 * (n + n * f ** 3 * (2 if a[1] else 1))
-    if name == "pulpo_resize_up_bwd":       # gout, gx, factor, scale, B, C, d0, d1, d2
-        f, B, C, n = a[2], a[4], a[5], a[6] * a[7] * a[8]
-        return B * C * 4 * (n + n * f ** 3)
+    if name == "pulpo_resize_up_bwd":       # gout, gx, factor, scale, accumulate, B, C, d0, d1, d2
+        f, B, C, n = a[2], a[5], a[6], a[7] * a[8] * a[9]
+        return B * C * 4 * (n * (2 if a[4] else 1) + n * f ** 3)
     if name == "pulpo_interp_size_fwd":     # x, out, B, C, i0, i1, i2, o0, o1, o2
         return a[2] * a[3] * 4 * (a[4] * a[5] * a[6] + a[7] * a[8] * a[9])
     if name == "pulpo_avgpool2_fwd":        # x, out, B, C, D0, D1, D2
@@ -38,14 +38,14 @@ def algo_bytes(name, args):
         return a[8] * a[9] * a[10] * a[11] * a[12] * 8
     if name == "pulpo_ncc_bwd":             # abc, pred, target, gloss, gpred, win, gamma, B, C, D0..
         return a[7] * a[8] * a[9] * a[10] * a[11] * 12
-    if name == "pulpo_kl_diag_fwd":         # mu0, s0, mu1, s1, eps, out, ws, bytes, B, n
-        return a[8] * a[9] * 4 * (2 + (1 if a[2] else 0) + (1 if a[3] else 0))
-    if name == "pulpo_kl_diag_bwd":         # gloss, mu0, s0, mu1, s1, eps, gmu, gsg, B, n
-        return a[8] * a[9] * 4 * (4 + (1 if a[3] else 0) + (1 if a[4] else 0))
+    if name == "pulpo_kl_diag_fwd":         # mu0, s0, mu1, s1, eps, weight, out, ws, bytes, B, n
+        return a[9] * a[10] * 4 * (2 + (1 if a[2] else 0) + (1 if a[3] else 0))
+    if name == "pulpo_kl_diag_bwd":         # gloss, mu0, s0, mu1, s1, eps, weight, gmu, gsg, B, n
+        return a[9] * a[10] * 4 * (4 + (1 if a[3] else 0) + (1 if a[4] else 0))
     if name == "pulpo_l2reg_fwd":           # f, lamb, out, ws, bytes, B, C, D0..
         return a[5] * a[6] * a[7] * a[8] * a[9] * 4
-    if name == "pulpo_l2reg_bwd":           # gloss, f, lamb, gf, B, C, D0..
-        return a[4] * a[5] * a[6] * a[7] * a[8] * 8
+    if name == "pulpo_l2reg_bwd":           # gloss, f, lamb, gf, accumulate, B, C, D0..
+        return a[5] * a[6] * a[7] * a[8] * a[9] * (12 if a[4] else 8)
     if name == "pulpo_moments_update":
         return a[4] * 20
     if name == "pulpo_moments_merge":

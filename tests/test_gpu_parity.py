@@ -274,3 +274,71 @@ def test_hot_path_vs_torch_oracle_config1(PF):
         assert_grad_close(d[l].grad.cpu().numpy(), d_ref[l].grad.numpy(), "gdf %d" % l)
         assert_grad_close(m[l].grad.cpu().numpy(), m_ref[l].grad.numpy(), "gmu %d" % l)
         assert_grad_close(s[l].grad.cpu().numpy(), s_ref[l].grad.numpy(), "gsigma %d" % l)
+
+
+# ----------------------------------------------------------------------------- HotPathPlan (multi-stream, graph-capturable)
+def _run_plan(g_or_inputs, total, latent, size, B, multi_stream=True, graph=False):
+    from pulpo_b200.plan import HotPathPlan
+    x, y, dfs, mus, sgs = g_or_inputs
+    plan = HotPathPlan(size, total, latent, batch=B, multi_stream=multi_stream)
+    if graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            plan.run(x, y, dfs, mus, sgs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            plan.run(x, y, dfs, mus, sgs)
+        plan.losses.zero_()
+        gr.replay()
+    else:
+        plan.run(x, y, dfs, mus, sgs)
+    torch.cuda.synchronize()
+    return plan
+
+
+@pytest.mark.parametrize("multi_stream,graph", [(False, False), (True, False), (True, True)])
+def test_plan_golden(PF, multi_stream, graph):
+    g = load_golden("hot_path_3lvl")
+    total, latent = int(g["total_levels"]), int(g["latent_levels"])
+    size, B = list(g["x"].shape[2:]), g["x"].shape[0]
+    inputs = (dev(g["x"]), dev(g["y"]), {l: dev(g["df%d" % l]) for l in range(latent)},
+              {l: dev(g["mu%d" % l]) for l in range(latent)}, {l: dev(g["sigma%d" % l]) for l in range(latent)})
+    plan = _run_plan(inputs, total, latent, size, B, multi_stream, graph)
+    losses = plan.losses.cpu().numpy()
+    assert_loss_close(losses[0].sum(), g["kl"], "kl")
+    assert_loss_close(losses[1].sum(), g["recon"], "recon")
+    assert_loss_close(losses[2].sum(), g["reg"], "reg")
+    assert_loss_close(plan.total.item(), g["total"], "total")
+    for l in range(latent):
+        assert_loss_close(losses[1][l], g["recon_level%d" % l], "recon level %d" % l)
+        assert_loss_close(losses[2][l], g["reg_level%d" % l], "reg level %d" % l)
+        assert_close(plan.final[l].cpu().numpy(), g["final%d" % l], FIELD_ATOL, "final %d" % l)
+        assert_close(plan.moved[l].cpu().numpy(), g["moved%d" % l], FIELD_ATOL, "moved %d" % l)
+        assert_grad_close(plan.gdf[l].cpu().numpy(), g["gdf%d" % l], "gdf %d" % l)
+        assert_grad_close(plan.gmu[l].cpu().numpy(), g["gmu%d" % l], "gmu %d" % l)
+        assert_grad_close(plan.gsigma[l].cpu().numpy(), g["gsigma%d" % l], "gsigma %d" % l)
+
+
+def test_plan_matches_autograd_modules_config1(PF):
+    """The planned multi-stream path and the autograd drop-in modules are the same arithmetic."""
+    from pulpo_b200 import synthetic as syn
+    from pulpo_b200.models import RegistrationHotPath
+    size, total, latent = [64, 64, 64], 4, 3
+    x, y, dfs, mus, sgs = syn.make_hot_path_inputs(size, total, latent, seed=2)
+    xc, yc = x.cuda(), y.cuda()
+    d = {l: dfs[l].cuda().requires_grad_(True) for l in dfs}
+    m = {l: mus[l].cuda().requires_grad_(True) for l in dfs}
+    s = {l: sgs[l].cuda().requires_grad_(True) for l in dfs}
+    loss, parts, outs = RegistrationHotPath(size, total, latent).cuda()(xc, yc, d, m, s)
+    loss.backward()
+    plan = _run_plan((xc, yc, {l: dfs[l].cuda() for l in dfs}, {l: mus[l].cuda() for l in dfs},
+                      {l: sgs[l].cuda() for l in dfs}), total, latent, size, 1, True, True)
+    assert_loss_close(plan.total.item(), loss.item(), "total")
+    for l in range(latent):
+        assert torch.equal(plan.moved[l], outs["moved"][l]), "moved %d differs" % l
+        assert_grad_close(plan.gdf[l].cpu().numpy(), d[l].grad.cpu().numpy(), "gdf %d" % l)
+        assert_grad_close(plan.gmu[l].cpu().numpy(), m[l].grad.cpu().numpy(), "gmu %d" % l)
+        assert_grad_close(plan.gsigma[l].cpu().numpy(), s[l].grad.cpu().numpy(), "gsigma %d" % l)
