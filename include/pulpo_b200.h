@@ -60,6 +60,18 @@ int pulpo_warp3d_fwd(const float *img, const float *df, float *out, int32_t *idx
 int pulpo_warp3d_bwd(const float *gout, const float *img, const float *df, float *gimg, float *gdf,
                      int B, int C, int D0, int D1, int D2, int coord_mode, pulpo_stream_t stream);
 
+/* a2 fused with f-1 (L2_reg, src/losses.py:208-222): the warp and the regulariser read the same
+ * full-resolution field in the same step (src/models.py:160-162).  reg_out (device scalar) =
+ * L2_reg(df, lamb); ws: pulpo_reduce_ws_bytes() bytes, zeroed once by the caller. */
+int pulpo_warp3d_l2reg_fwd(const float *img, const float *df, float *out, float lamb, float *reg_out,
+                           void *ws, size_t ws_bytes, int B, int C, int D0, int D1, int D2,
+                           int coord_mode, pulpo_stream_t stream);
+/* gdf = d/d df [ <gout, warp(df, img)> + reg_gloss * L2_reg(df, lamb) ];  reg_gloss: device
+ * scalar, nullable = 1. */
+int pulpo_warp3d_l2reg_bwd(const float *gout, const float *img, const float *df, float *gdf, float lamb,
+                           const float *reg_gloss, int B, int C, int D0, int D1, int D2, int coord_mode,
+                           pulpo_stream_t stream);
+
 /* ---- a3: VecInt.forward(vec)   src/network_blocks.py:173-177 ------------------------------
  * vec,out: [B,3,D0,D1,D2].  ws holds the integration states as [*,B,S] float4 (xyz + pad):
  * save_steps=1 keeps v_0..v_{nsteps-1} for the backward (nsteps states), save_steps=0 needs

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpulpo_b200.so")
+# PULPO_B200_LIB selects a tuning variant built with `python -m pulpo_b200.build --tag=...`
+LIB_PATH = os.environ.get("PULPO_B200_LIB") or os.path.join(_HERE, "lib", "libpulpo_b200.so")
 
 CPU_EXACT = 0   # PULPO_COORD_CPU_EXACT
 CUDA_RCP = 1    # PULPO_COORD_CUDA_RCP
@@ -21,6 +22,8 @@ SIGNATURES = {
     "pulpo_strerror": (ctypes.c_char_p, [_i]),
     "pulpo_warp3d_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_warp3d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_warp3d_l2reg_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_warp3d_l2reg_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_vecint_ws_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "pulpo_vecint_fwd": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_vecint_bwd_scratch_bytes": (_sz, [_i, _i, _i, _i]),

@@ -34,15 +34,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defs=(), tag: str = "") -> str:
+    """``defs``/``tag`` build a tuning variant (``-DNAME=VALUE`` ...) as lib/libpulpo_b200_<tag>.so,
+    selected at run time with PULPO_B200_LIB (see _lib.py); the default build takes neither."""
+    lib = LIB if not tag else os.path.join(LIBDIR, "libpulpo_b200_%s.so" % tag)
+    if not force and not tag and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + \
+        obj = os.path.join(LIBDIR, src.replace(".cu", (".%s.o" % tag) if tag else ".o"))
+        cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-D" + d for d in defs] + \
               (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -54,9 +57,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libpulpo_b200")
-    subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
-    return LIB
+    subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs)
+    if tag:
+        for o in objs:
+            os.remove(o)
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    _defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    _tag = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--tag=")), "")
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defs=_defs, tag=_tag))

@@ -36,6 +36,7 @@ struct AxisConst {
     float Sm1;   // float(S-1)
     float rcp;   // RN(1 / float(S-1))
     float gmul;  // S/2: d p / d n of the unnormalise (backward)
+    float tmax;  // 2^23 + (S-2): largest low-corner index, biased (see make_tap)
 };
 
 __host__ __device__ inline AxisConst make_axis(int S)
@@ -45,6 +46,7 @@ __host__ __device__ inline AxisConst make_axis(int S)
     a.Sm1 = (float)(S - 1);
     a.rcp = 1.0f / (float)(S - 1);
     a.gmul = (float)S / 2.0f;
+    a.tmax = 8388608.0f + (float)(S - 2);
     return a;
 }
 
@@ -76,43 +78,57 @@ __device__ __forceinline__ float sample_pos(float vf, float d, const AxisConst &
     return __fmul_rn(t, 0.5f);  // "/ 2" is exact either way
 }
 
-// border padding: min(S-1, max(p, 0)) with std::max/std::min NaN behaviour
+// border padding: std::min(S-1, std::max(p, 0)) including its NaN behaviour (NaN -> S-1) in two
+// instructions: NaN-propagating max, then IEEE minNum
 __device__ __forceinline__ float clip_pos(float p, float Sm1)
 {
-    float lo = (p < 0.0f) ? 0.0f : p;
-    return (lo < Sm1) ? lo : Sm1;
+    float lo;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(lo) : "f"(p), "f"(0.0f));
+    return fminf(lo, Sm1);
 }
+
+constexpr int kTapBias = 0x4B000000;   // float bits of 2^23
 
 // one axis of the trilinear footprint
 struct Tap {
-    int i;      // index of the low corner actually read (floor(p), or S-2 when floor(p) == S-1)
+    int bits;   // float bits of 2^23 + i;  i = index of the low corner actually read
     float w0;   // weight of corner i
     float w1;   // weight of corner i+1
-    int hi;     // 1 when the footprint was shifted down at the upper border (floor(p) == i + 1)
+    int floor_p;  // floor(p) (== i except at the upper border); only the index-dump path uses it
 };
 
 template <int MODE>
-__device__ __forceinline__ Tap make_tap(float vf, float d, const AxisConst &a, int S, float *unclamped = nullptr)
+__device__ __forceinline__ Tap make_tap(float vf, float d, const AxisConst &a, float *unclamped = nullptr)
 {
     float u = sample_pos<MODE>(vf, d, a);
     if (unclamped) *unclamped = u;
     float p = clip_pos(u, a.Sm1);
     // floor of 0 <= p < 2^22 without the conversion unit: adding 2^23 in round-toward-zero
-    // truncates the fraction; the integer sits in the low mantissa bits
+    // truncates the fraction; the integer sits in the low mantissa bits of t.
     float t = __fadd_rz(p, 8388608.0f);
-    float fl = __fsub_rn(t, 8388608.0f);
-    int i = __float_as_int(t) - 0x4B000000;
-    float w0 = __fsub_rn(__fadd_rn(fl, 1.0f), p);   // (i+1) - p
-    float w1 = __fsub_rn(p, fl);                    // p - i
-    // p == S-1 exactly: corner i+1 is outside the volume and has weight 0.  Read corners
-    // (S-2, S-1) with weights (0, 1) instead, so that every footprint is 2x2x2 in-bounds and the
-    // +1 neighbours are fixed immediates; 0*x + 1*y == y keeps the result bit-identical.
+    // p == S-1 exactly: corner i+1 would be outside the volume (weight 0).  Clamp the low corner to
+    // S-2 so that every footprint is 2x2x2 in-bounds with fixed +1 neighbours; the weights become
+    // (0, 1) and 0*x + 1*y == y keeps the result bit-identical.
+    float tc = fminf(t, a.tmax);
+    float fl = __fsub_rn(tc, 8388608.0f);
     Tap tp;
-    tp.hi = (i >= S - 1) ? 1 : 0;
-    tp.i = i - tp.hi;
-    tp.w0 = tp.hi ? w1 : w0;
-    tp.w1 = tp.hi ? w0 : w1;
+    tp.bits = __float_as_int(tc);
+    tp.floor_p = __float_as_int(t) - kTapBias;
+    tp.w1 = __fsub_rn(p, fl);          // p - i   (exact)
+    tp.w0 = __fsub_rn(1.0f, tp.w1);    // == (i+1) - p bit for bit (both differences are exact or the same op)
     return tp;
+}
+
+// offset of the low corner inside one [D0,D1,D2] volume from the three taps' float bits; the
+// 2^23 biases are removed by one precomputed constant (32-bit wrap-around arithmetic)
+__device__ __forceinline__ int tap_base(const Tap &tz, const Tap &ty, const Tap &tx, int D1, int D2, int unbias)
+{
+    return (tz.bits * D1 + ty.bits) * D2 + tx.bits - unbias;
+}
+
+static inline int tap_unbias(int D1, int D2)
+{
+    return (int)((unsigned int)kTapBias * ((unsigned int)D1 * (unsigned int)D2 + (unsigned int)D2 + 1u));
 }
 
 // 32-bit division by a launch constant (q = umulhi(n, mul) >> shr, valid for n < 2^31)
@@ -179,7 +195,8 @@ __device__ __forceinline__ double block_sum(double v, double *smem)
 // partials in a fixed order and writes `scale * sum` to *out as fp32.
 struct ReduceWs {
     unsigned int ticket;
-    unsigned int pad[3];
+    unsigned int pad;
+    double acc;         // accumulator of the atomic variant (grid_reduce_finish_atomic)
     double partial[1];  // [max_ctas]
 };
 constexpr int kMaxReduceCtas = 4096;
@@ -206,6 +223,25 @@ __device__ __forceinline__ void grid_reduce_finish(double block_total, ReduceWs 
         if (threadIdx.x == 0) {
             *out = (float)(s * scale);
             ws->ticket = 0;  // ready for the next launch on this workspace
+        }
+    }
+}
+
+// Variant for grids of any size: CTAs add their double partial into ws->acc with one fp64
+// atomic; the last CTA to arrive publishes and resets.  The summation order is not fixed, but
+// the partials are doubles of fp32 data, so the fp32 result is reproducible in practice.
+__device__ __forceinline__ void grid_reduce_finish_atomic(double block_total, ReduceWs *ws, float *out, double scale)
+{
+    if (threadIdx.x == 0) {
+        const unsigned int nctas = gridDim.x * gridDim.y * gridDim.z;
+        atomicAdd(&ws->acc, block_total);
+        __threadfence();
+        unsigned int t = atomicAdd(&ws->ticket, 1u);
+        if (t == nctas - 1) {
+            __threadfence();
+            double s = __longlong_as_double(atomicExch((unsigned long long *)&ws->acc, 0ull));
+            *out = (float)(s * scale);
+            ws->ticket = 0;
         }
     }
 }

@@ -8,6 +8,14 @@
 // instead of three 32-bit ones, and the scatter half of the backward is one
 // red.global.add.v4.f32 per corner instead of three scalar atomics.  The states of one level
 // (<= 13.8 MB at 80x96x112) stay resident in the 126 MB L2 between steps.
+//
+// Work mapping: a warp owns an 8 (x) by 4 (y) patch and walks a run of z planes, so the voxel
+// decode happens once per run and neighbouring lanes are neighbouring voxels.  The backward
+// uses that adjacency to cut the global reductions, which bound it (REDG issues at ~1.3 cycles
+// per lane per SM): with a smooth field the corner (i+1) of lane t is the corner (i) of lane
+// t+1, so corner contributions are first combined across lanes in x and y with warp shuffles and
+// across consecutive planes in registers; an interior voxel then issues 2 reductions per step
+// (its own gradient + one fully combined corner) instead of 9.
 // Forward arithmetic is op-for-op the CPU grid sampler's, so results are bit-identical to
 // torch-CPU in PULPO_COORD_CPU_EXACT mode.
 #include <cooperative_groups.h>
@@ -18,11 +26,28 @@ namespace cg = cooperative_groups;
 
 namespace pulpo {
 
+constexpr int VI_PX = 8, VI_PY = 4;   // lanes of a warp: 8 along x, 4 along y
+// One CTA per SM: a CTA that reaches grid.sync() early polls the barrier with acquire loads,
+// and every poll invalidates that SM's L1 (CCTL.IVALL) -- with several CTAs per SM this slowed
+// the CTAs still working next to it.  With one CTA per SM nobody is left to disturb.
+#ifndef PULPO_VI_FWD_THREADS
+#define PULPO_VI_FWD_THREADS 1024
+#endif
+#ifndef PULPO_VI_BWD_THREADS
+#define PULPO_VI_BWD_THREADS 768
+#endif
+constexpr int VI_FWD_THREADS = PULPO_VI_FWD_THREADS;
+constexpr int VI_BWD_THREADS = PULPO_VI_BWD_THREADS;
+
 struct VGeom {
     int B, D0, D1, D2;
     int S;            // voxels per volume (< 2^31)
     unsigned int N;   // B * S
-    FastDiv dD2, dD1, dD0;
+    int unbias;
+    int npx, npy;     // patches per row / per plane column
+    int zrun, nzrun;  // planes per work item, items per column
+    unsigned int items;   // B * npy * npx * nzrun
+    FastDiv dnpx, dnpy, dnz;
     AxisConst a0, a1, a2;
 };
 
@@ -31,18 +56,47 @@ static int make_vgeom(VGeom &g, int B, int D0, int D1, int D2)
     i64 S = (i64)D0 * D1 * D2;
     if ((i64)B * S >= (1ll << 31) || D0 > (1 << 22) || D1 > (1 << 22) || D2 > (1 << 22)) return PULPO_ERR_INVALID_SHAPE;
     g.B = B; g.D0 = D0; g.D1 = D1; g.D2 = D2; g.S = (int)S; g.N = (unsigned int)(B * S);
-    g.dD2 = make_fastdiv(D2); g.dD1 = make_fastdiv(D1); g.dD0 = make_fastdiv(D0);
+    g.unbias = tap_unbias(D1, D2);
+    g.npx = (D2 + VI_PX - 1) / VI_PX;
+    g.npy = (D1 + VI_PY - 1) / VI_PY;
     g.a0 = make_axis(D0); g.a1 = make_axis(D1); g.a2 = make_axis(D2);
     return PULPO_OK;
 }
 
-__device__ __forceinline__ void decode(unsigned int i, const VGeom &g, unsigned int &b, unsigned int &z,
-                                       unsigned int &y, unsigned int &x)
+// split every patch column into z runs so that there is about one work item per resident warp
+static void set_zruns(VGeom &g, int total_warps)
 {
-    unsigned int r, zb;
-    fast_divmod(i, g.dD2, r, x);
-    fast_divmod(r, g.dD1, zb, y);
-    fast_divmod(zb, g.dD0, b, z);
+    i64 columns = (i64)g.B * g.npy * g.npx;
+    i64 per_col = total_warps / (columns > 0 ? columns : 1);
+    if (per_col < 1) per_col = 1;
+    if (per_col > g.D0) per_col = g.D0;
+    g.zrun = (int)((g.D0 + per_col - 1) / per_col);
+    g.nzrun = (g.D0 + g.zrun - 1) / g.zrun;
+    g.items = (unsigned int)(columns * g.nzrun);
+    g.dnpx = make_fastdiv(g.npx); g.dnpy = make_fastdiv(g.npy); g.dnz = make_fastdiv(g.nzrun);
+}
+
+struct Item {
+    int b, z0, z1, y, x;
+    bool valid;   // this lane's voxel column is inside the volume
+};
+
+__device__ __forceinline__ Item decode_item(unsigned int it, const VGeom &g, int lane)
+{
+    // x fastest: the warps of a CTA own x-adjacent patches of the same rows and planes, so they
+    // share the cache lines on their common borders and spread over the L1 sets
+    unsigned int r, zr, r2, px, py, b;
+    fast_divmod(it, g.dnpx, r, px);
+    fast_divmod(r, g.dnpy, r2, py);
+    fast_divmod(r2, g.dnz, b, zr);
+    Item t;
+    t.b = (int)b;
+    t.z0 = (int)zr * g.zrun;
+    t.z1 = min(g.D0, t.z0 + g.zrun);
+    t.x = (int)px * VI_PX + (lane & (VI_PX - 1));
+    t.y = (int)py * VI_PY + (lane >> 3);
+    t.valid = (t.x < g.D2) && (t.y < g.D1);
+    return t;
 }
 
 struct Corners {
@@ -79,21 +133,20 @@ __device__ __forceinline__ float interp_exact(float c0, float c1, float c2, floa
 }
 
 struct VFoot {
-    int base;
+    int base;   // offset of the low corner inside one volume
     float w[8];
     float wx0, wx1, wy0, wy1, wz0, wz1;
 };
 
 template <int MODE>
-__device__ __forceinline__ VFoot make_vfoot(unsigned int b, unsigned int z, unsigned int y, unsigned int x,
-                                            const float4 &v, const VGeom &g, float *uz = nullptr,
-                                            float *uy = nullptr, float *ux = nullptr)
+__device__ __forceinline__ VFoot make_vfoot(float zf, float yf, float xf, const float4 &v, const VGeom &g,
+                                            float *uz = nullptr, float *uy = nullptr, float *ux = nullptr)
 {
-    Tap tz = make_tap<MODE>((float)(int)z, v.x, g.a0, g.D0, uz);
-    Tap ty = make_tap<MODE>((float)(int)y, v.y, g.a1, g.D1, uy);
-    Tap tx = make_tap<MODE>((float)(int)x, v.z, g.a2, g.D2, ux);
+    Tap tz = make_tap<MODE>(zf, v.x, g.a0, uz);
+    Tap ty = make_tap<MODE>(yf, v.y, g.a1, uy);
+    Tap tx = make_tap<MODE>(xf, v.z, g.a2, ux);
     VFoot f;
-    f.base = (int)b * g.S + (tz.i * g.D1 + ty.i) * g.D2 + tx.i;
+    f.base = tap_base(tz, ty, tx, g.D1, g.D2, g.unbias);
     f.wx0 = tx.w0; f.wx1 = tx.w1; f.wy0 = ty.w0; f.wy1 = ty.w1; f.wz0 = tz.w0; f.wz1 = tz.w1;
     const float w00 = __fmul_rn(tx.w0, ty.w0), w01 = __fmul_rn(tx.w1, ty.w0);
     const float w10 = __fmul_rn(tx.w0, ty.w1), w11 = __fmul_rn(tx.w1, ty.w1);
@@ -105,13 +158,16 @@ __device__ __forceinline__ VFoot make_vfoot(unsigned int b, unsigned int z, unsi
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(VI_FWD_THREADS)
 vecint_fwd_kernel(const float *__restrict__ vec, float *__restrict__ out, float4 *ws, int nsteps, int save,
                   float scale, const VGeom g)
 {
     cg::grid_group grid = cg::this_grid();
     const unsigned int N = g.N, S = g.S;
     const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned int warp = tid >> 5, nwarps = nthr >> 5;
+    const int sy = g.D2, sz = g.D1 * g.D2;
 
     // v_0 = vec * 2^-nsteps, planar -> interleaved
     for (unsigned int i = tid; i < N; i += nthr) {
@@ -125,24 +181,32 @@ vecint_fwd_kernel(const float *__restrict__ vec, float *__restrict__ out, float4
         const float4 *src = save ? ws + (i64)k * N : ws + (i64)(k & 1) * N;
         float4 *dst = save ? ws + (i64)(k + 1) * N : ws + (i64)((k + 1) & 1) * N;
         const bool last = (k == nsteps - 1);
-        for (unsigned int i = tid; i < N; i += nthr) {
-            unsigned int b, z, y, x;
-            decode(i, g, b, z, y, x);
-            const float4 v = src[i];
-            const VFoot f = make_vfoot<MODE>(b, z, y, x, v, g);
-            Corners kc;
-            gather8(src + f.base, g.D2, g.D1 * g.D2, kc);
-            float r0 = interp_exact(kc.c[0].x, kc.c[1].x, kc.c[2].x, kc.c[3].x, kc.c[4].x, kc.c[5].x, kc.c[6].x, kc.c[7].x, f.w);
-            float r1 = interp_exact(kc.c[0].y, kc.c[1].y, kc.c[2].y, kc.c[3].y, kc.c[4].y, kc.c[5].y, kc.c[6].y, kc.c[7].y, f.w);
-            float r2 = interp_exact(kc.c[0].z, kc.c[1].z, kc.c[2].z, kc.c[3].z, kc.c[4].z, kc.c[5].z, kc.c[6].z, kc.c[7].z, f.w);
-            r0 = __fadd_rn(v.x, r0);
-            r1 = __fadd_rn(v.y, r1);
-            r2 = __fadd_rn(v.z, r2);
-            if (last) {
-                float *o = out + (i64)b * 3 * S + (i - b * S);
-                o[0] = r0; o[S] = r1; o[2 * S] = r2;
-            } else {
-                dst[i] = make_float4(r0, r1, r2, 0.0f);
+        for (unsigned int it = warp; it < g.items; it += nwarps) {
+            const Item t = decode_item(it, g, lane);
+            if (!t.valid) continue;
+            const float yf = (float)t.y, xf = (float)t.x;
+            const float4 *vol = src + (i64)t.b * S;
+            int off = (t.z0 * g.D1 + t.y) * g.D2 + t.x;
+            float4 v = vol[off];
+            for (int z = t.z0; z < t.z1; ++z, off += sz) {
+                float4 vn = v;
+                if (z + 1 < t.z1) vn = vol[off + sz];   // the next plane's own value, ahead of its use
+                const VFoot f = make_vfoot<MODE>((float)z, yf, xf, v, g);
+                Corners kc;
+                gather8(vol + f.base, sy, sz, kc);
+                float r0 = interp_exact(kc.c[0].x, kc.c[1].x, kc.c[2].x, kc.c[3].x, kc.c[4].x, kc.c[5].x, kc.c[6].x, kc.c[7].x, f.w);
+                float r1 = interp_exact(kc.c[0].y, kc.c[1].y, kc.c[2].y, kc.c[3].y, kc.c[4].y, kc.c[5].y, kc.c[6].y, kc.c[7].y, f.w);
+                float r2 = interp_exact(kc.c[0].z, kc.c[1].z, kc.c[2].z, kc.c[3].z, kc.c[4].z, kc.c[5].z, kc.c[6].z, kc.c[7].z, f.w);
+                r0 = __fadd_rn(v.x, r0);
+                r1 = __fadd_rn(v.y, r1);
+                r2 = __fadd_rn(v.z, r2);
+                if (last) {
+                    float *o = out + (i64)t.b * 3 * S + off;
+                    o[0] = r0; o[S] = r1; o[2 * S] = r2;
+                } else {
+                    dst[(i64)t.b * S + off] = make_float4(r0, r1, r2, 0.0f);
+                }
+                v = vn;
             }
         }
     }
@@ -157,23 +221,45 @@ vecint_fwd_kernel(const float *__restrict__ vec, float *__restrict__ out, float4
     }
 }
 
+struct F3 {
+    float x, y, z;
+};
+
+__device__ __forceinline__ F3 shfl_up3(const F3 &a, int d)
+{
+    F3 r;
+    r.x = __shfl_up_sync(0xffffffffu, a.x, d);
+    r.y = __shfl_up_sync(0xffffffffu, a.y, d);
+    r.z = __shfl_up_sync(0xffffffffu, a.z, d);
+    return r;
+}
+
+__device__ __forceinline__ void red3(float4 *addr, const F3 &a)
+{
+    red_add_v4(reinterpret_cast<float *>(addr), a.x, a.y, a.z, 0.0f);
+}
+
 // Backward of one step  v' = v + W(v) v :   g = g' + W(v)^T g' + (dW/dv : v)^T g'
-//   own   : g' + gather-form gradient through the sample position  -> one red.v4 on the voxel
-//   scatter: w_d * g' onto the 8 corners                            -> one red.v4 per corner
+//   own    : g' + gather-form gradient through the sample position -> one red.v4 on the voxel
+//   scatter: w_d * g' onto the 8 corners, combined across lanes / planes before the red.v4
 // All contributions go through red.global.add.v4.f32 into a pre-zeroed state, so there is no
 // ordering hazard between the plain part and the scatter part; three states rotate
 // (read / accumulate / being zeroed for the next step).
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(VI_BWD_THREADS)
 vecint_bwd_kernel(const float *__restrict__ gout, const float4 *saved, float *__restrict__ gvec, float4 *scr,
                   int nsteps, float scale, const VGeom g)
 {
     cg::grid_group grid = cg::this_grid();
     const unsigned int N = g.N, S = g.S;
     const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, lx = lane & (VI_PX - 1), ly = lane >> 3;
+    const unsigned int warp = tid >> 5, nwarps = nthr >> 5;
     float4 *X = scr, *Y = scr + N, *Z = scr + 2 * (i64)N;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float kz = 2.0f * g.a0.rcp, ky = 2.0f * g.a1.rcp, kx = 2.0f * g.a2.rcp;
+    const int sy = g.D2, sz = g.D1 * g.D2;
+    constexpr int NOADDR = -0x40000000;
 
     for (unsigned int i = tid; i < N; i += nthr) {
         unsigned int b = i / S, v = i - b * S;
@@ -184,40 +270,111 @@ vecint_bwd_kernel(const float *__restrict__ gout, const float4 *saved, float *__
     for (int k = nsteps - 1; k >= 0; --k) {
         grid.sync();
         const float4 *vk = saved + (i64)k * N;
-        for (unsigned int i = tid; i < N; i += nthr) {
-            unsigned int b, z, y, x;
-            decode(i, g, b, z, y, x);
-            const float4 G = X[i];
-            const float4 v = vk[i];
-            float uz, uy, ux;
-            const VFoot f = make_vfoot<MODE>(b, z, y, x, v, g, &uz, &uy, &ux);
-            Corners kc;
-            gather8(vk + f.base, g.D2, g.D1 * g.D2, kc);
-            // t[d] = <corner_d, G> over the 3 channels
-            float t[8];
-#pragma unroll
-            for (int d = 0; d < 8; ++d) t[d] = kc.c[d].x * G.x + kc.c[d].y * G.y + kc.c[d].z * G.z;
-            const float sx = ((t[1] - t[0]) * f.wy0 + (t[3] - t[2]) * f.wy1) * f.wz0 +
-                             ((t[5] - t[4]) * f.wy0 + (t[7] - t[6]) * f.wy1) * f.wz1;
-            const float sy_ = ((t[2] - t[0]) * f.wx0 + (t[3] - t[1]) * f.wx1) * f.wz0 +
-                             ((t[6] - t[4]) * f.wx0 + (t[7] - t[5]) * f.wx1) * f.wz1;
-            const float sz = ((t[4] - t[0]) * f.wx0 + (t[5] - t[1]) * f.wx1) * f.wy0 +
-                             ((t[6] - t[2]) * f.wx0 + (t[7] - t[3]) * f.wx1) * f.wy1;
-            const float mz = (uz <= 0.0f || uz >= g.a0.Sm1) ? 0.0f : g.a0.gmul;
-            const float my = (uy <= 0.0f || uy >= g.a1.Sm1) ? 0.0f : g.a1.gmul;
-            const float mx = (ux <= 0.0f || ux >= g.a2.Sm1) ? 0.0f : g.a2.gmul;
-            red_add_v4(reinterpret_cast<float *>(Y + i), G.x + (mz * sz) * kz, G.y + (my * sy_) * ky,
-                       G.z + (mx * sx) * kx, 0.0f);
-            // scatter half (all 8 corners are in-bounds; border corners carry weight 0)
-            float *q = reinterpret_cast<float *>(Y + f.base);
-            const int sy4 = 4 * g.D2, sz4 = 4 * g.D1 * g.D2;
-#pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                const int o = ((d & 1) ? 4 : 0) + ((d & 2) ? sy4 : 0) + ((d & 4) ? sz4 : 0);
-                const float w = f.w[d];
-                red_add_v4(q + o, w * G.x, w * G.y, w * G.z, 0.0f);
+        for (unsigned int it = warp; it < g.items; it += nwarps) {   // warp-uniform loop: all lanes shuffle
+            const Item t = decode_item(it, g, lane);
+            const float yf = (float)t.y, xf = (float)t.x;
+            const i64 vb = (i64)t.b * S;
+            const float4 *vol = vk + vb;
+            float4 *acc = Y + vb;
+            int off = t.valid ? (t.z0 * g.D1 + t.y) * g.D2 + t.x : 0;
+            F3 carry = {0.f, 0.f, 0.f};   // corner (dz=1, dy=0, dx=0) of the previous plane, already combined in x and y
+            int carry_addr = NOADDR;
+            float4 Gn = zero4, vn = zero4;
+            if (t.valid) {
+                Gn = X[vb + off];
+                vn = vol[off];
             }
-            Z[i] = zero4;  // accumulation target of the next step
+            for (int z = t.z0; z < t.z1; ++z, off += sz) {
+                const float4 G = Gn, v = vn;
+                if (t.valid && z + 1 < t.z1) {   // next plane's own values, one iteration ahead of their use
+                    Gn = X[vb + off + sz];
+                    vn = vol[off + sz];
+                }
+                float uz, uy, ux;
+                const VFoot f = make_vfoot<MODE>((float)z, yf, xf, v, g, &uz, &uy, &ux);
+                const int A = t.valid ? f.base : NOADDR;
+                if (t.valid) {
+                    Corners kc;
+                    gather8(vol + f.base, sy, sz, kc);
+                    // q[d] = <corner_d, G> over the 3 channels
+                    float q[8];
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) q[d] = kc.c[d].x * G.x + kc.c[d].y * G.y + kc.c[d].z * G.z;
+                    const float sx = ((q[1] - q[0]) * f.wy0 + (q[3] - q[2]) * f.wy1) * f.wz0 +
+                                     ((q[5] - q[4]) * f.wy0 + (q[7] - q[6]) * f.wy1) * f.wz1;
+                    const float sy_ = ((q[2] - q[0]) * f.wx0 + (q[3] - q[1]) * f.wx1) * f.wz0 +
+                                      ((q[6] - q[4]) * f.wx0 + (q[7] - q[5]) * f.wx1) * f.wz1;
+                    const float sz_ = ((q[4] - q[0]) * f.wx0 + (q[5] - q[1]) * f.wx1) * f.wy0 +
+                                      ((q[6] - q[2]) * f.wx0 + (q[7] - q[3]) * f.wx1) * f.wy1;
+                    const float mz = (uz > 0.0f && uz < g.a0.Sm1) ? g.a0.gmul : 0.0f;
+                    const float my = (uy > 0.0f && uy < g.a1.Sm1) ? g.a1.gmul : 0.0f;
+                    const float mx = (ux > 0.0f && ux < g.a2.Sm1) ? g.a2.gmul : 0.0f;
+                    red_add_v4(reinterpret_cast<float *>(acc + off), G.x + (mz * sz_) * kz, G.y + (my * sy_) * ky,
+                               G.z + (mx * sx) * kx, 0.0f);
+                    Z[vb + off] = zero4;  // accumulation target of the next step
+                }
+#if defined(PULPO_VI_BWD_EXP) && PULPO_VI_BWD_EXP == 1
+                continue;
+#endif
+                // ---- scatter half.  c[d] = w_d * G for the 8 corners (all in-bounds; border corners carry weight 0)
+                F3 c[8];
+#pragma unroll
+                for (int d = 0; d < 8; ++d) {
+                    c[d].x = f.w[d] * G.x; c[d].y = f.w[d] * G.y; c[d].z = f.w[d] * G.z;
+                }
+#if defined(PULPO_VI_BWD_EXP) && PULPO_VI_BWD_EXP == 2
+                if (t.valid) {
+                    float4 *q = acc + A;
+                    red3(q, c[0]); red3(q + 1, c[1]); red3(q + sy, c[2]); red3(q + sy + 1, c[3]);
+                    red3(q + sz, c[4]); red3(q + sz + 1, c[5]); red3(q + sz + sy, c[6]); red3(q + sz + sy + 1, c[7]);
+                }
+                continue;
+#endif
+                // combine along x: my dx=1 corners are lane+1's dx=0 corners when its footprint starts one voxel right
+                const int A_left = __shfl_up_sync(0xffffffffu, A, 1), A_right = __shfl_down_sync(0xffffffffu, A, 1);
+                const bool recv_x = (lx > 0) && (A_left + 1 == A);
+                const bool sent_x = (lx < VI_PX - 1) && (A + 1 == A_right);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {   // m = dz*2 + dy
+                    const F3 r = shfl_up3(c[2 * m + 1], 1);
+                    if (recv_x) { c[2 * m].x += r.x; c[2 * m].y += r.y; c[2 * m].z += r.z; }
+                }
+                // combine along y: my (dy=1, dx=0) corners are lane+8's (dy=0, dx=0) corners
+                const int A_up = __shfl_up_sync(0xffffffffu, A, VI_PX), A_down = __shfl_down_sync(0xffffffffu, A, VI_PX);
+                const bool recv_y = (ly > 0) && (A_up + sy == A);
+                const bool sent_y = (ly < VI_PY - 1) && (A + sy == A_down);
+#pragma unroll
+                for (int dz = 0; dz < 2; ++dz) {
+                    const F3 r = shfl_up3(c[4 * dz + 2], VI_PX);
+                    if (recv_y) { c[4 * dz].x += r.x; c[4 * dz].y += r.y; c[4 * dz].z += r.z; }
+                }
+                if (t.valid) {
+                    // combine along z: the previous plane's (dz=1,dy=0,dx=0) corner is usually this plane's (0,0,0)
+                    if (carry_addr == A) {
+                        c[0].x += carry.x; c[0].y += carry.y; c[0].z += carry.z;
+                    } else if (carry_addr != NOADDR) {
+                        red3(acc + carry_addr, carry);
+                    }
+                    carry = c[4];
+                    carry_addr = A + sz;
+                    float4 *q = acc + A;
+                    red3(q, c[0]);
+#if defined(PULPO_VI_BWD_EXP) && PULPO_VI_BWD_EXP == 5
+                    continue;
+#endif
+                    if (!sent_y) {
+                        red3(q + sy, c[2]);
+                        red3(q + sz + sy, c[6]);
+                    }
+                    if (!sent_x) {
+                        red3(q + 1, c[1]);
+                        red3(q + sy + 1, c[3]);
+                        red3(q + sz + 1, c[5]);
+                        red3(q + sz + sy + 1, c[7]);
+                    }
+                }
+            }
+            if (carry_addr != NOADDR) red3(acc + carry_addr, carry);
         }
         float4 *t = X; X = Y; Y = Z; Z = t;
     }
@@ -242,6 +399,17 @@ static int coop_grid(K kernel, i64 work, int threads)
     i64 cap = (i64)sms * per_sm;
     if (g > cap) g = cap;
     return (int)(g < 1 ? 1 : g);
+}
+
+template <typename K>
+static int launch_coop(K kernel, int threads, VGeom &g, void **args, cudaStream_t st)
+{
+    // lanes cover whole 8x4 patches, so size the grid by patch-padded voxels
+    const i64 padded = (i64)g.B * g.D0 * g.npy * VI_PY * g.npx * VI_PX;
+    const int grid = coop_grid(kernel, padded, threads);
+    set_zruns(g, grid * (threads / 32));
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)kernel, dim3(grid), dim3(threads), args, 0, st);
+    return e == cudaSuccess ? launch_status() : PULPO_ERR_CUDA;
 }
 
 }  // namespace pulpo
@@ -274,15 +442,8 @@ extern "C" int pulpo_vecint_fwd(const float *vec, float *out, void *ws, size_t w
     float scale = 1.0f / (float)(1u << nsteps);
     float4 *w4 = (float4 *)ws;
     void *args[] = {&vec, &out, &w4, &nsteps, &save_steps, &scale, &g};
-    cudaError_t e;
-    if (coord_mode == 0) {
-        int grid = coop_grid(vecint_fwd_kernel<0>, g.N, 256);
-        e = cudaLaunchCooperativeKernel((void *)vecint_fwd_kernel<0>, dim3(grid), dim3(256), args, 0, (cudaStream_t)stream);
-    } else {
-        int grid = coop_grid(vecint_fwd_kernel<1>, g.N, 256);
-        e = cudaLaunchCooperativeKernel((void *)vecint_fwd_kernel<1>, dim3(grid), dim3(256), args, 0, (cudaStream_t)stream);
-    }
-    return e == cudaSuccess ? launch_status() : PULPO_ERR_CUDA;
+    return coord_mode == 0 ? launch_coop(vecint_fwd_kernel<0>, VI_FWD_THREADS, g, args, (cudaStream_t)stream)
+                           : launch_coop(vecint_fwd_kernel<1>, VI_FWD_THREADS, g, args, (cudaStream_t)stream);
 }
 
 extern "C" int pulpo_vecint_bwd(const float *gout, const void *saved, float *gvec, void *scratch, size_t scratch_bytes,
@@ -301,13 +462,6 @@ extern "C" int pulpo_vecint_bwd(const float *gout, const void *saved, float *gve
     const float4 *sv = (const float4 *)saved;
     float4 *scr = (float4 *)scratch;
     void *args[] = {&gout, &sv, &gvec, &scr, &nsteps, &scale, &g};
-    cudaError_t e;
-    if (coord_mode == 0) {
-        int grid = coop_grid(vecint_bwd_kernel<0>, g.N, 256);
-        e = cudaLaunchCooperativeKernel((void *)vecint_bwd_kernel<0>, dim3(grid), dim3(256), args, 0, (cudaStream_t)stream);
-    } else {
-        int grid = coop_grid(vecint_bwd_kernel<1>, g.N, 256);
-        e = cudaLaunchCooperativeKernel((void *)vecint_bwd_kernel<1>, dim3(grid), dim3(256), args, 0, (cudaStream_t)stream);
-    }
-    return e == cudaSuccess ? launch_status() : PULPO_ERR_CUDA;
+    return coord_mode == 0 ? launch_coop(vecint_bwd_kernel<0>, VI_BWD_THREADS, g, args, (cudaStream_t)stream)
+                           : launch_coop(vecint_bwd_kernel<1>, VI_BWD_THREADS, g, args, (cudaStream_t)stream);
 }

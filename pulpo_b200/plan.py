@@ -40,11 +40,12 @@ def _p(t, byte_offset=0):
 
 class HotPathPlan:
     def __init__(self, input_size, total_levels, latent_levels, batch=1, beta=0.1, gamma=0.05, lamb=0.025,
-                 with_reg=True, nsteps=7, coord_mode=CPU_EXACT, device=None, multi_stream=True):
+                 with_reg=True, nsteps=7, coord_mode=CPU_EXACT, device=None, multi_stream=True, fuse_reg=True):
         self.L = L = latent_levels
         self.B = B = batch
         self.lk = lk = total_levels - latent_levels
         self.nsteps, self.mode, self.with_reg = nsteps, coord_mode, with_reg
+        self.fuse_reg = bool(fuse_reg and with_reg)   # L2_reg rides in the warp kernels (same field, same step)
         self.dev = dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.lib = _lib.lib()
         self.full = tuple(int(s) for s in input_size)
@@ -174,7 +175,11 @@ class HotPathPlan:
             # warp the (pooled) moving image
             if ms and l in ev_lx:
                 s.wait_event(ev_lx[l])
-            call(lib.pulpo_warp3d_fwd, _p(lx[l]), _p(self.final[l]), _p(self.moved[l]), None, B, 1, *dout, mode, hs)
+            if self.fuse_reg:
+                call(lib.pulpo_warp3d_l2reg_fwd, _p(lx[l]), _p(self.final[l]), _p(self.moved[l]), self.lamb_eff[l],
+                     self._loss_ptr(2, l), _p(self.ws_l2[l]), self.ws_l2[l].numel(), B, 1, *dout, mode, hs)
+            else:
+                call(lib.pulpo_warp3d_fwd, _p(lx[l]), _p(self.final[l]), _p(self.moved[l]), None, B, 1, *dout, mode, hs)
             # NCC against the resized fixed image (losses.py:313-318), backward immediately
             if dout != self.full:
                 call(lib.pulpo_interp_size_fwd, _p(y), _p(self.yt[l]), B, 1, *self.full, *dout, hs)
@@ -186,9 +191,13 @@ class HotPathPlan:
                  wsn.numel(), self.win[l], self.gamma_eff[l], B, 1, *dout, hs)
             call(lib.pulpo_ncc_bwd, _p(self.abc[l]), _p(self.moved[l]), _p(yt), None, _p(self.gmoved[l]),
                  self.win[l], self.gamma_eff[l], B, 1, *dout, hs)
-            call(lib.pulpo_warp3d_bwd, _p(self.gmoved[l]), _p(lx[l]), _p(self.final[l]), None, _p(self.gfinal[l]),
-                 B, 1, *dout, mode, hs)
-            if self.with_reg:   # L2_reg on the final field; its gradient accumulates into the warp's
+            if self.fuse_reg:
+                call(lib.pulpo_warp3d_l2reg_bwd, _p(self.gmoved[l]), _p(lx[l]), _p(self.final[l]), _p(self.gfinal[l]),
+                     self.lamb_eff[l], None, B, 1, *dout, mode, hs)
+            else:
+                call(lib.pulpo_warp3d_bwd, _p(self.gmoved[l]), _p(lx[l]), _p(self.final[l]), None, _p(self.gfinal[l]),
+                     B, 1, *dout, mode, hs)
+            if self.with_reg and not self.fuse_reg:   # L2_reg on the final field; its gradient accumulates into the warp's
                 call(lib.pulpo_l2reg_fwd, _p(self.final[l]), self.lamb_eff[l], self._loss_ptr(2, l),
                      _p(self.ws_l2[l]), self.ws_l2[l].numel(), B, 3, *dout, hs)
                 call(lib.pulpo_l2reg_bwd, None, _p(self.final[l]), self.lamb_eff[l], _p(self.gfinal[l]), 1, B, 3,

@@ -19,6 +19,12 @@ def algo_bytes(name, args):
     if name == "pulpo_warp3d_bwd":          # gout, img, df, gimg, gdf, B, C, D0..
         B, C, n = a[5], a[6], a[7] * a[8] * a[9]
         return B * n * (4 * C + 12 + 4 * C + (12 if a[4] else 0) + (4 * C if a[3] else 0))
+    if name == "pulpo_warp3d_l2reg_fwd":    # img, df, out, lamb, reg_out, ws, ws_bytes, B, C, D0, D1, D2
+        B, C, n = a[7], a[8], a[9] * a[10] * a[11]
+        return B * n * (12 + 8 * C)          # the regulariser re-uses the field the warp reads
+    if name == "pulpo_warp3d_l2reg_bwd":    # gout, img, df, gdf, lamb, reg_gloss, B, C, D0, D1, D2
+        B, C, n = a[6], a[7], a[8] * a[9] * a[10]
+        return B * n * (4 * C + 12 + 4 * C + 12)
     if name == "pulpo_vecint_fwd":          # vec, out, ws, ws_bytes, nsteps, save, B, D0, D1, D2
         return a[4] * 24 * a[6] * a[7] * a[8] * a[9]
     if name == "pulpo_vecint_bwd":          # gout, saved, gvec, scratch, bytes, nsteps, B, D0..

@@ -208,6 +208,40 @@ def test_l2reg_golden(PF):
     assert_grad_close(f.grad.cpu().numpy(), g["gf"], "l2reg grad")
 
 
+def test_warp_l2reg_fused_matches_separate_kernels(PF):
+    """pulpo_warp3d_l2reg_fwd/bwd (warp + L2_reg in one pass over the field) against the
+    golden L2_reg fixture and the separate warp kernels, ragged and vectorisable shapes."""
+    import ctypes
+    from pulpo_b200 import _lib, synthetic as syn
+    L = _lib.lib()
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = load_golden("l2reg")
+    cases = [(torch.from_numpy(g["f"]).cuda(), float(g["loss"]), g["gf"])]
+    for shape, seed in [((12, 20, 28), 1), ((9, 11, 13), 2), ((16, 24, 32), 3)]:
+        f = syn.make_field(shape, seed, batch=2, max_abs=2.5).cuda().requires_grad_(True)
+        ref = PF.l2_reg(f, 0.025)
+        ref.backward()
+        cases.append((f.detach(), ref.item(), f.grad.cpu().numpy()))
+    for f, loss_ref, gf_ref in cases:
+        B, _, D0, D1, D2 = f.shape
+        img = torch.rand(B, 2, D0, D1, D2, device="cuda")
+        gout = torch.randn(B, 2, D0, D1, D2, device="cuda")
+        out_ref = PF.warp(f, img)
+        fr = f.clone().requires_grad_(True)
+        PF.warp(fr, img).backward(gout)
+        out, reg = torch.empty_like(img), torch.zeros((), device="cuda")
+        ws = torch.zeros(L.pulpo_reduce_ws_bytes(), dtype=torch.uint8, device="cuda")
+        for _ in range(2):   # twice: the workspace must reset itself
+            _lib.check(L.pulpo_warp3d_l2reg_fwd(vp(img), vp(f), vp(out), 0.025, vp(reg), vp(ws), ws.numel(), B, 2, D0, D1, D2, 0, st))
+        assert torch.equal(out, out_ref)
+        assert_loss_close(reg.item(), loss_ref, "fused l2reg")
+        gdf = torch.empty_like(f)
+        _lib.check(L.pulpo_warp3d_l2reg_bwd(vp(gout), vp(img), vp(f), vp(gdf), 0.025, None, B, 2, D0, D1, D2, 0, st))
+        want = fr.grad.cpu().numpy() + gf_ref
+        assert_grad_close(gdf.cpu().numpy(), want, "fused warp+l2reg grad")
+
+
 # ----------------------------------------------------------------------------- decoder chain + losses (a6, a7, a10, a12)
 def test_hot_path_golden(PF):
     from pulpo_b200.models import RegistrationHotPath
@@ -277,10 +311,10 @@ def test_hot_path_vs_torch_oracle_config1(PF):
 
 
 # ----------------------------------------------------------------------------- HotPathPlan (multi-stream, graph-capturable)
-def _run_plan(g_or_inputs, total, latent, size, B, multi_stream=True, graph=False):
+def _run_plan(g_or_inputs, total, latent, size, B, multi_stream=True, graph=False, **kw):
     from pulpo_b200.plan import HotPathPlan
     x, y, dfs, mus, sgs = g_or_inputs
-    plan = HotPathPlan(size, total, latent, batch=B, multi_stream=multi_stream)
+    plan = HotPathPlan(size, total, latent, batch=B, multi_stream=multi_stream, **kw)
     if graph:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -299,14 +333,14 @@ def _run_plan(g_or_inputs, total, latent, size, B, multi_stream=True, graph=Fals
     return plan
 
 
-@pytest.mark.parametrize("multi_stream,graph", [(False, False), (True, False), (True, True)])
-def test_plan_golden(PF, multi_stream, graph):
+@pytest.mark.parametrize("multi_stream,graph,fuse_reg", [(False, False, True), (True, False, False), (True, True, True)])
+def test_plan_golden(PF, multi_stream, graph, fuse_reg):
     g = load_golden("hot_path_3lvl")
     total, latent = int(g["total_levels"]), int(g["latent_levels"])
     size, B = list(g["x"].shape[2:]), g["x"].shape[0]
     inputs = (dev(g["x"]), dev(g["y"]), {l: dev(g["df%d" % l]) for l in range(latent)},
               {l: dev(g["mu%d" % l]) for l in range(latent)}, {l: dev(g["sigma%d" % l]) for l in range(latent)})
-    plan = _run_plan(inputs, total, latent, size, B, multi_stream, graph)
+    plan = _run_plan(inputs, total, latent, size, B, multi_stream, graph, fuse_reg=fuse_reg)
     losses = plan.losses.cpu().numpy()
     assert_loss_close(losses[0].sum(), g["kl"], "kl")
     assert_loss_close(losses[1].sum(), g["recon"], "recon")
