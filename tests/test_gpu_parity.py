@@ -376,3 +376,56 @@ def test_plan_matches_autograd_modules_config1(PF):
         assert_grad_close(plan.gdf[l].cpu().numpy(), d[l].grad.cpu().numpy(), "gdf %d" % l)
         assert_grad_close(plan.gmu[l].cpu().numpy(), m[l].grad.cpu().numpy(), "gmu %d" % l)
         assert_grad_close(plan.gsigma[l].cpu().numpy(), s[l].grad.cpu().numpy(), "gsigma %d" % l)
+
+
+# ----------------------------------------------------------------------------- MC moments (f-3, config 3)
+def test_moments_kernels_match_torch_std(PF):
+    from pulpo_b200 import mc
+    g = torch.Generator(device="cuda").manual_seed(5)
+    stack = torch.randn(9, 3, 10, 12, 14, device="cuda", generator=g) * 0.7 + 2.0
+    a, b = mc.MCMoments(stack.shape[1:], "cuda"), mc.MCMoments(stack.shape[1:], "cuda")
+    for i in range(5):
+        a.update(stack[i])
+    for i in range(5, 9):
+        b.update(stack[i])
+    a.merge_state(b.mean, b.m2, b.count)
+    assert a.count == 9
+    ref = stack.double()
+    assert_close(a.mean.cpu().numpy(), ref.mean(0).cpu().numpy(), 1e-5, "mc mean")
+    assert_close(a.std().cpu().numpy(), ref.std(0).cpu().numpy(), 1e-5, "mc std")
+    assert_close(a.std_channel_mean().cpu().numpy(), ref.std(0).mean(0).cpu().numpy(), 1e-5, "mc std channel mean")
+
+
+def test_mc_uncertainty_hot_path_matches_stacked_reference_semantics(PF):
+    """Config 3 at small size: N MC samples of (gauss_sampler -> combine -> integrate -> warp), streamed
+    through the moments kernels, against torch.std over explicit stacks (evaluate.py:243-251) of the
+    oracle's CPU path on the same per-sample noise."""
+    from oracle import torch_ref as T
+    from pulpo_b200 import mc, synthetic as syn
+    from pulpo_b200.models import combine_dfs
+    from pulpo_b200.network_blocks import SpatialTransformer, gauss_sampler
+    size, total, latent, N = [32, 32, 32], 4, 3, 6
+    x, y, dfs, mus, sgs = syn.make_hot_path_inputs(size, total, latent, seed=3)
+    xc = x.cuda()
+    mu = {l: dfs[l].cuda() for l in dfs}          # posterior mean of the velocity field
+    sg = {l: (0.3 * sgs[l]).cuda() for l in dfs}
+    st = SpatialTransformer(size)
+
+    def sample_fn(i, gen):
+        v = {l: gauss_sampler(mu[l], sg[l], generator=gen) for l in mu}
+        _, final = combine_dfs(v, size)
+        return {"final0": final[0][0], "moved0": st(final[0], xc)[0]}
+
+    res = mc.mc_uncertainty(sample_fn, N, seed0=11)
+    # reference semantics on CPU with the very same noise (drawn on the GPU generator, copied)
+    finals, moveds = [], []
+    for i in range(N):
+        gen = mc.sample_generator(11, i, "cuda")
+        v = {l: gauss_sampler(mu[l], sg[l], generator=gen).cpu() for l in mu}
+        _, final = T.combine_dfs(v, size)
+        finals.append(final[0][0])
+        moveds.append(T.warp(final[0], x)[0])
+    f_std = torch.stack(finals).std(dim=0).mean(dim=0)
+    m_std = torch.stack(moveds).std(dim=0).mean(dim=0)
+    assert_close(res["final0"].std_channel_mean().cpu().numpy(), f_std.numpy(), FIELD_ATOL, "final df std")
+    assert_close(res["moved0"].variance_map().cpu().numpy(), (m_std ** 2).numpy(), FIELD_ATOL, "variance map")

@@ -1,0 +1,91 @@
+"""World-size-2 `gloo` tests (CPU) of the multi-rank host logic:
+MC-sample sharding + all-gather + Chan merge of the per-voxel moments (config 3), and the
+pair-sharded loss all-reduce (config 5: every loss term is a batch mean, so averaging equal
+shards reproduces the global-batch loss).  The numerical kernels are CUDA-only; here the
+oracle's CPU implementation is injected through the `ops` seam of pulpo_b200.mc."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle.moments_ref import TorchCpuOps
+from pulpo_b200 import mc
+
+SHAPE = (3, 6, 5, 4)
+N_SAMPLES = 11
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _sample(i, gen):
+    # deterministic in (seed0 + i) only: any rank that draws sample i gets the same tensor
+    base = torch.linspace(-1.0, 1.0, steps=int(torch.tensor(SHAPE).prod())).reshape(SHAPE)
+    noise = torch.randn(SHAPE, generator=gen)
+    return {"final0": base + 0.5 * noise, "moved0": (0.1 * noise[:1]).abs()}
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res = mc.mc_uncertainty(_sample, N_SAMPLES, seed0=123, device=torch.device("cpu"), ops=TorchCpuOps, dst=0)
+        # config 5: per-rank batch-mean losses averaged over equal shards == global batch mean
+        g = torch.Generator().manual_seed(7)
+        per_pair = torch.rand(4, generator=g)              # 4 pairs, 2 per rank
+        local = per_pair[rank * 2:(rank + 1) * 2].mean()
+        t = local.clone()
+        dist.all_reduce(t)
+        t /= world
+        if rank == 0:
+            torch.save({"count": res["final0"].count, "std": res["final0"].std(), "mean": res["final0"].mean,
+                        "var_map": res["moved0"].variance_map(), "loss": t, "loss_ref": per_pair.mean()},
+                       os.path.join(out_dir, "r0.pt"))
+        else:
+            assert res["final0"].count == len(mc.shard_samples(N_SAMPLES, rank, world))   # untouched local state
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_samples_partition():
+    for n, w in [(128, 8), (11, 2), (5, 4), (3, 3)]:
+        ids = [mc.shard_samples(n, r, w) for r in range(w)]
+        assert sorted(i for part in ids for i in part) == list(range(n))
+        assert max(len(p) for p in ids) - min(len(p) for p in ids) <= 1
+    with pytest.raises(ValueError):
+        mc.shard_samples(4, 2, 2)
+
+
+def test_mc_moments_single_process_matches_torch_std():
+    states = mc.mc_uncertainty(_sample, N_SAMPLES, seed0=123, device=torch.device("cpu"), ops=TorchCpuOps)
+    stack = torch.stack([_sample(i, mc.sample_generator(123, i, "cpu"))["final0"] for i in range(N_SAMPLES)])
+    assert states["final0"].count == N_SAMPLES
+    torch.testing.assert_close(states["final0"].std(), stack.std(dim=0), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(states["final0"].mean, stack.mean(dim=0), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(states["final0"].std_channel_mean(), stack.std(dim=0).mean(dim=0), rtol=1e-5, atol=1e-6)
+
+
+def test_product_ops_refuse_cpu_tensors():
+    st = mc.MCMoments(SHAPE, "cpu")          # default ops = the CUDA kernels
+    with pytest.raises(RuntimeError):
+        st.update(torch.zeros(SHAPE))
+
+
+@pytest.mark.timeout(180)
+def test_mc_sharded_over_two_gloo_ranks_matches_unsharded(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "r0.pt"))
+    stack = torch.stack([_sample(i, mc.sample_generator(123, i, "cpu"))["final0"] for i in range(N_SAMPLES)])
+    moved = torch.stack([_sample(i, mc.sample_generator(123, i, "cpu"))["moved0"] for i in range(N_SAMPLES)])
+    assert got["count"] == N_SAMPLES
+    torch.testing.assert_close(got["std"], stack.std(dim=0), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(got["mean"], stack.mean(dim=0), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(got["var_map"], moved.std(dim=0).mean(dim=0) ** 2, rtol=1e-4, atol=1e-8)
+    torch.testing.assert_close(got["loss"], got["loss_ref"], rtol=1e-6, atol=0)
