@@ -44,6 +44,8 @@ typedef enum pulpo_status {
  * bit-exact against torch-CPU in mode 0 and against torch-CUDA in mode 1. */
 #define PULPO_COORD_CPU_EXACT 0 /* loc/(S-1) true division; ((n+1)*S-1)/2 rounded op by op */
 #define PULPO_COORD_CUDA_RCP 1  /* loc*(1/(S-1)); fma(n+1, S, -1)/2 */
+#define PULPO_COORD_FAST 2      /* VecInt only: p = fma(loc, S/(S-1), -0.5), FMA interpolation; within
+                                 * ~1e-5 voxel of either torch path (no index contract on this op) */
 
 int pulpo_version(void);
 const char *pulpo_strerror(int status);
@@ -80,7 +82,8 @@ size_t pulpo_vecint_ws_bytes(int nsteps, int save_steps, int B, int D0, int D1, 
 int pulpo_vecint_fwd(const float *vec, float *out, void *ws, size_t ws_bytes, int nsteps,
                      int save_steps, int B, int D0, int D1, int D2, int coord_mode,
                      pulpo_stream_t stream);
-/* gvec = d loss/d vec.  `saved` = the ws of a save_steps=1 forward; scratch: 3 states. */
+/* gvec = d loss/d vec.  `saved` = the ws of a save_steps=1 forward; scratch: 4 states
+ * (two (own, scatter) gradient pairs that ping-pong between steps). */
 size_t pulpo_vecint_bwd_scratch_bytes(int B, int D0, int D1, int D2);
 int pulpo_vecint_bwd(const float *gout, const void *saved, float *gvec, void *scratch,
                      size_t scratch_bytes, int nsteps, int B, int D0, int D1, int D2,

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("PULPO_B200_LIB") or os.path.join(_HERE, "lib", "libpu
 
 CPU_EXACT = 0   # PULPO_COORD_CPU_EXACT
 CUDA_RCP = 1    # PULPO_COORD_CUDA_RCP
+FAST = 2        # PULPO_COORD_FAST (VecInt only)
 
 _vp, _i, _f, _sz, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_longlong
 

@@ -3,6 +3,8 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/pulpo_b200.h"
 
@@ -23,7 +25,10 @@ constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
 
 static inline int launch_status()
 {
-    return cudaPeekAtLastError() == cudaSuccess ? PULPO_OK : PULPO_ERR_CUDA;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e == cudaSuccess) return PULPO_OK;
+    if (getenv("PULPO_B200_DEBUG")) fprintf(stderr, "libpulpo_b200: CUDA error: %s\n", cudaGetErrorString(e));
+    return PULPO_ERR_CUDA;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -37,6 +42,7 @@ struct AxisConst {
     float rcp;   // RN(1 / float(S-1))
     float gmul;  // S/2: d p / d n of the unnormalise (backward)
     float tmax;  // 2^23 + (S-2): largest low-corner index, biased (see make_tap)
+    float kf;    // RN(S / (S-1)): d p / d loc; the whole normalise/unnormalise chain in one factor (MODE 2)
 };
 
 __host__ __device__ inline AxisConst make_axis(int S)
@@ -47,6 +53,7 @@ __host__ __device__ inline AxisConst make_axis(int S)
     a.rcp = 1.0f / (float)(S - 1);
     a.gmul = (float)S / 2.0f;
     a.tmax = 8388608.0f + (float)(S - 2);
+    a.kf = (float)S / (float)(S - 1);
     return a;
 }
 
@@ -71,6 +78,9 @@ template <int MODE>
 __device__ __forceinline__ float sample_pos(float vf, float d, const AxisConst &a)
 {
     float loc = __fadd_rn(vf, d);
+    // MODE 2 (PULPO_COORD_FAST): p = loc * S/(S-1) - 0.5 in one FMA.  Same value as the chain below
+    // up to a few ulp of p (~1e-5 voxel at p ~ 200); not index-exact, so only VecInt offers it.
+    if (MODE == PULPO_COORD_FAST) return __fmaf_rn(loc, a.kf, -0.5f);
     float q = (MODE == PULPO_COORD_CPU_EXACT) ? div_by_axis(loc, a) : __fmul_rn(loc, a.rcp);
     float n = __fmul_rn(2.0f, __fsub_rn(q, 0.5f));
     float t = (MODE == PULPO_COORD_CPU_EXACT) ? __fsub_rn(__fmul_rn(__fadd_rn(n, 1.0f), a.S), 1.0f)

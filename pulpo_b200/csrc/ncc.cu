@@ -20,6 +20,7 @@
 // gradient; backward runs the same box kernel on them (packed (a,b) + scalar c).
 // Algorithmic bytes: fwd 8 B/voxel (+12 when saving a,b,c), bwd 12 B/voxel (+12 reading a,b,c).
 #include "common.cuh"
+#include "ncc_common.cuh"
 
 namespace pulpo {
 
@@ -40,41 +41,6 @@ struct NccParams {
     float Wf, rcpW;                // win^3 and RN(1/win^3)
     int BC, D0, D1, D2, zchunk, nzchunks;
 };
-
-__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float add2(float a, float b) { return __fadd_rn(a, b); }
-
-// sums of W consecutive values for 4 consecutive outputs: o[j] = sum a[j .. j+W-1]
-template <int W, typename T>
-__device__ __forceinline__ void xsum4(const T (&a)[W + 3], T (&o)[4])
-{
-    if (W >= 5) {
-        T core = a[3];
-#pragma unroll
-        for (int t = 4; t < W; ++t) core = add2(core, a[t]);
-        const T p12 = add2(a[1], a[2]), pw = add2(a[W], a[W + 1]);
-        o[0] = add2(core, add2(a[0], p12));
-        o[1] = add2(core, add2(p12, a[W]));
-        o[2] = add2(core, add2(a[2], pw));
-        o[3] = add2(core, add2(pw, a[W + 2]));
-    } else {  // W == 3
-        const T p12 = add2(a[1], a[2]), p34 = add2(a[3], a[4]);
-        o[0] = add2(a[0], p12);
-        o[1] = add2(p12, a[3]);
-        o[2] = add2(a[2], p34);
-        o[3] = add2(p34, a[5]);
-    }
-}
-
-// correctly rounded x / W with the precomputed reciprocal (see div_by_axis)
-__device__ __forceinline__ float div_by_W(float x, float Wf, float rcpW)
-{
-    float q0 = __fmul_rn(x, rcpW);
-    float r0 = __fmaf_rn(-Wf, q0, x);
-    float q1 = __fmaf_rn(r0, rcpW, q0);
-    float r1 = __fmaf_rn(-Wf, q1, x);
-    return __fmaf_rn(r1, rcpW, q1);
-}
 
 template <int W, bool FWD, bool VECLOAD>
 __global__ void __launch_bounds__(NCC_THREADS, 2)
@@ -320,6 +286,7 @@ extern "C" size_t pulpo_ncc_ws_bytes(int B, int C, int D0, int D1, int D2)
     // worst case over the supported windows: the grid is largest for the smallest window
     NccGrid g = ncc_grid(B * C, D0, D1, D2, 3);
     size_t ctas = (size_t)g.grid.x * g.grid.y * g.grid.z;
+    if (ctas < 1024) ctas = 1024;   // the persistent TMA kernel deposits one partial per SM
     return 16 + sizeof(double) * ctas;
 }
 
@@ -331,10 +298,21 @@ extern "C" int pulpo_ncc_fwd(const float *pred, const float *target, float *loss
     PULPO_REQUIRE(B > 0 && C > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE((i64)D0 * D1 * D2 < (1ll << 31), PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(win >= 3 && win <= 11 && (win & 1), PULPO_ERR_UNSUPPORTED);
+    const i64 n = (i64)B * C * D0 * D1 * D2;
+    if (ncc_tma_eligible(target, pred, nullptr, D0, D1, D2, win) &&
+        ws_bytes >= 16 + sizeof(double) * (size_t)ncc_tma_grid(B * C, D0, D1, D2, win)) {
+        NccTmaParams t{};
+        t.o0 = abc; t.o1 = abc ? abc + n : nullptr; t.o2 = abc ? abc + 2 * n : nullptr;
+        t.loss = loss; t.ws = (ReduceWs *)ws;
+        t.loss_scale = -(double)gamma / (double)B;
+        t.Wf = (float)(win * win * win);
+        t.rcpW = 1.0f / t.Wf;
+        t.BC = B * C; t.D0 = D0; t.D1 = D1; t.D2 = D2;
+        return ncc_tma_launch(target, pred, nullptr, t, win, (cudaStream_t)stream);
+    }
     NccGrid g = ncc_grid(B * C, D0, D1, D2, win);
     PULPO_REQUIRE(g.grid.y <= 65535 && g.grid.z <= 65535, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(ws_bytes >= 16 + sizeof(double) * (size_t)g.grid.x * g.grid.y * g.grid.z, PULPO_ERR_WORKSPACE);
-    const i64 n = (i64)B * C * D0 * D1 * D2;
     NccParams p{};
     p.in0 = target; p.in1 = pred; p.in2 = nullptr;
     p.o0 = abc; p.o1 = abc ? abc + n : nullptr; p.o2 = abc ? abc + 2 * n : nullptr;
@@ -354,9 +332,18 @@ extern "C" int pulpo_ncc_bwd(const float *abc, const float *pred, const float *t
     PULPO_REQUIRE(B > 0 && C > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE((i64)D0 * D1 * D2 < (1ll << 31), PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(win >= 3 && win <= 11 && (win & 1), PULPO_ERR_UNSUPPORTED);
+    const i64 n = (i64)B * C * D0 * D1 * D2;
+    if (ncc_tma_eligible(abc, abc + n, abc + 2 * n, D0, D1, D2, win) && aligned16(gpred)) {
+        NccTmaParams t{};
+        t.I = target; t.J = pred; t.o0 = gpred; t.gloss = gloss;
+        t.k = -gamma / (float)B;
+        t.Wf = (float)(win * win * win);
+        t.rcpW = 1.0f / t.Wf;
+        t.BC = B * C; t.D0 = D0; t.D1 = D1; t.D2 = D2;
+        return ncc_tma_launch(abc, abc + n, abc + 2 * n, t, win, (cudaStream_t)stream);
+    }
     NccGrid g = ncc_grid(B * C, D0, D1, D2, win);
     PULPO_REQUIRE(g.grid.y <= 65535 && g.grid.z <= 65535, PULPO_ERR_INVALID_SHAPE);
-    const i64 n = (i64)B * C * D0 * D1 * D2;
     NccParams p{};
     p.in0 = abc; p.in1 = abc + n; p.in2 = abc + 2 * n;
     p.I = target; p.J = pred; p.o0 = gpred; p.gloss = gloss;

@@ -2,22 +2,26 @@
 //     v <- vec * 2^-nsteps ;  nsteps times:  v <- v + warp(v, v)
 //
 // B200 design.  The field is both the image and the displacement, so each step is a full
-// grid-wide dependency.  All steps run in ONE cooperative launch with grid.sync() between
-// steps instead of 7 launches; the integration states live in a channel-interleaved float4
-// layout ([B,S] x (c0,c1,c2,pad)) so that every trilinear corner is one 128-bit gather
-// instead of three 32-bit ones, and the scatter half of the backward is one
-// red.global.add.v4.f32 per corner instead of three scalar atomics.  The states of one level
+// grid-wide dependency.  All steps run in ONE cooperative launch with grid.sync() (1.25 us measured,
+// scripts/micro/sync_bench.cu) between steps instead of 7 launches; the integration states live in
+// a channel-interleaved float4 layout ([B,S] x (c0,c1,c2,pad)) so that every trilinear corner is one
+// 128-bit gather and every scatter one red.global.add.v4.f32.  The states of one level
 // (<= 13.8 MB at 80x96x112) stay resident in the 126 MB L2 between steps.
 //
-// Work mapping: a warp owns an 8 (x) by 4 (y) patch and walks a run of z planes, so the voxel
-// decode happens once per run and neighbouring lanes are neighbouring voxels.  The backward
-// uses that adjacency to cut the global reductions, which bound it (REDG issues at ~1.3 cycles
-// per lane per SM): with a smooth field the corner (i+1) of lane t is the corner (i) of lane
-// t+1, so corner contributions are first combined across lanes in x and y with warp shuffles and
-// across consecutive planes in registers; an interior voxel then issues 2 reductions per step
-// (its own gradient + one fully combined corner) instead of 9.
-// Forward arithmetic is op-for-op the CPU grid sampler's, so results are bit-identical to
-// torch-CPU in PULPO_COORD_CPU_EXACT mode.
+// What bounds it (ncu, profiles/): not HBM and not instruction issue but the SM's L1 load/store
+// pipe -- a 128-bit warp gather that touches n cache lines occupies it for ~2n cycles, a vector
+// reduction for ~0.6 cycles per lane -- plus the grid barrier.  Hence:
+//   * work mapping: a warp owns an 8 (x) by 4 (y) patch (4 lines per aligned gather) and walks a
+//     run of z planes, one work item per resident warp (one CTA per SM);
+//   * z reuse: the four upper corners of one plane are the four lower corners of the next when the
+//     footprint moved by exactly one plane (the usual case for a smooth field) -> 4 gathers per
+//     plane instead of 8; the backward mirrors it for the scatter (the four upper-corner
+//     contributions are carried in registers and merged into the next plane's) -> 4 reductions;
+//   * ordered loads: the next plane's own values are requested before this plane's gathers (volatile
+//     asm keeps the order), otherwise every plane pays two serialised L2 round trips;
+//   * PULPO_COORD_FAST: sample position in one FMA, FMA interpolation (no index contract here).
+// In the exact modes the forward arithmetic is op-for-op the CPU grid sampler's: results are
+// bit-identical to torch-CPU (PULPO_COORD_CPU_EXACT).
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -34,7 +38,7 @@ constexpr int VI_PX = 8, VI_PY = 4;   // lanes of a warp: 8 along x, 4 along y
 #define PULPO_VI_FWD_THREADS 1024
 #endif
 #ifndef PULPO_VI_BWD_THREADS
-#define PULPO_VI_BWD_THREADS 768
+#define PULPO_VI_BWD_THREADS 640
 #endif
 constexpr int VI_FWD_THREADS = PULPO_VI_FWD_THREADS;
 constexpr int VI_BWD_THREADS = PULPO_VI_BWD_THREADS;
@@ -102,25 +106,54 @@ __device__ __forceinline__ Item decode_item(unsigned int it, const VGeom &g, int
 struct Corners {
     float4 c[8];  // index = dz*4 + dy*2 + dx
 };
+constexpr int NOBASE = -0x40000000;   // "no previous footprint" (never equals base - plane stride)
 
-// the footprint is always 2x2x2 in-bounds (see make_tap): fixed +1 / +D2 / +D1*D2 neighbours
-__device__ __forceinline__ void gather8(const float4 *p, int sy, int sz, Corners &k)
+// 128-bit load whose position in the instruction stream is kept (volatile asms are not reordered
+// against each other): the next plane's own value must be requested BEFORE this plane's corner
+// gathers, otherwise its latency is serialised behind theirs (two L2 round trips per plane).
+__device__ __forceinline__ float4 ld4v(const float4 *p)
+{
+    float4 r;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+// The footprint is always 2x2x2 in-bounds (see make_tap): fixed +1 / +D2 / +D1*D2 neighbours.
+// Walking a z run, the upper four corners of one plane are the lower four of the next whenever the
+// footprint moved by exactly one plane (the usual case for a smooth field): those are kept in
+// registers, so a plane costs four 128-bit gathers instead of eight.
+__device__ __forceinline__ void gather8(const float4 *p, int sy, int sz, bool reuse_lower, Corners &k)
 {
     const float4 *py = p + sy, *pz = p + sz, *pzy = pz + sy;
-    k.c[0] = p[0];
-    k.c[1] = p[1];
-    k.c[2] = py[0];
-    k.c[3] = py[1];
-    k.c[4] = pz[0];
-    k.c[5] = pz[1];
-    k.c[6] = pzy[0];
-    k.c[7] = pzy[1];
+    if (reuse_lower) {
+        k.c[0] = k.c[4]; k.c[1] = k.c[5]; k.c[2] = k.c[6]; k.c[3] = k.c[7];
+    } else {
+        k.c[0] = ld4v(p);
+        k.c[1] = ld4v(p + 1);
+        k.c[2] = ld4v(py);
+        k.c[3] = ld4v(py + 1);
+    }
+    k.c[4] = ld4v(pz);
+    k.c[5] = ld4v(pz + 1);
+    k.c[6] = ld4v(pzy);
+    k.c[7] = ld4v(pzy + 1);
 }
 
 // same corner order / op order as the CPU grid sampler (tnw, tne, tsw, tse, bnw, ...)
-__device__ __forceinline__ float interp_exact(float c0, float c1, float c2, float c3, float c4, float c5, float c6,
-                                              float c7, const float w[8])
+template <int MODE>
+__device__ __forceinline__ float interp8(float c0, float c1, float c2, float c3, float c4, float c5, float c6,
+                                         float c7, const float w[8], float own)
 {
+    if (MODE == PULPO_COORD_FAST) {   // one FMA chain seeded with the voxel's own value: v + sum w_d c_d
+        float acc = __fmaf_rn(c0, w[0], own);
+        acc = __fmaf_rn(c1, w[1], acc);
+        acc = __fmaf_rn(c2, w[2], acc);
+        acc = __fmaf_rn(c3, w[3], acc);
+        acc = __fmaf_rn(c4, w[4], acc);
+        acc = __fmaf_rn(c5, w[5], acc);
+        acc = __fmaf_rn(c6, w[6], acc);
+        return __fmaf_rn(c7, w[7], acc);
+    }
     float acc = __fmul_rn(c0, w[0]);
     acc = __fadd_rn(acc, __fmul_rn(c1, w[1]));
     acc = __fadd_rn(acc, __fmul_rn(c2, w[2]));
@@ -129,7 +162,7 @@ __device__ __forceinline__ float interp_exact(float c0, float c1, float c2, floa
     acc = __fadd_rn(acc, __fmul_rn(c5, w[5]));
     acc = __fadd_rn(acc, __fmul_rn(c6, w[6]));
     acc = __fadd_rn(acc, __fmul_rn(c7, w[7]));
-    return acc;
+    return __fadd_rn(own, acc);
 }
 
 struct VFoot {
@@ -158,7 +191,7 @@ __device__ __forceinline__ VFoot make_vfoot(float zf, float yf, float xf, const 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(VI_FWD_THREADS)
+__global__ void __launch_bounds__(VI_FWD_THREADS, 1)
 vecint_fwd_kernel(const float *__restrict__ vec, float *__restrict__ out, float4 *ws, int nsteps, int save,
                   float scale, const VGeom g)
 {
@@ -187,19 +220,18 @@ vecint_fwd_kernel(const float *__restrict__ vec, float *__restrict__ out, float4
             const float yf = (float)t.y, xf = (float)t.x;
             const float4 *vol = src + (i64)t.b * S;
             int off = (t.z0 * g.D1 + t.y) * g.D2 + t.x;
-            float4 v = vol[off];
+            float4 v = ld4v(vol + off);
+            Corners kc;
+            int prev_base = NOBASE;
             for (int z = t.z0; z < t.z1; ++z, off += sz) {
                 float4 vn = v;
-                if (z + 1 < t.z1) vn = vol[off + sz];   // the next plane's own value, ahead of its use
+                if (z + 1 < t.z1) vn = ld4v(vol + off + sz);   // the next plane's own value, ahead of this plane's gathers
                 const VFoot f = make_vfoot<MODE>((float)z, yf, xf, v, g);
-                Corners kc;
-                gather8(vol + f.base, sy, sz, kc);
-                float r0 = interp_exact(kc.c[0].x, kc.c[1].x, kc.c[2].x, kc.c[3].x, kc.c[4].x, kc.c[5].x, kc.c[6].x, kc.c[7].x, f.w);
-                float r1 = interp_exact(kc.c[0].y, kc.c[1].y, kc.c[2].y, kc.c[3].y, kc.c[4].y, kc.c[5].y, kc.c[6].y, kc.c[7].y, f.w);
-                float r2 = interp_exact(kc.c[0].z, kc.c[1].z, kc.c[2].z, kc.c[3].z, kc.c[4].z, kc.c[5].z, kc.c[6].z, kc.c[7].z, f.w);
-                r0 = __fadd_rn(v.x, r0);
-                r1 = __fadd_rn(v.y, r1);
-                r2 = __fadd_rn(v.z, r2);
+                gather8(vol + f.base, sy, sz, f.base == prev_base + sz, kc);
+                prev_base = f.base;
+                const float r0 = interp8<MODE>(kc.c[0].x, kc.c[1].x, kc.c[2].x, kc.c[3].x, kc.c[4].x, kc.c[5].x, kc.c[6].x, kc.c[7].x, f.w, v.x);
+                const float r1 = interp8<MODE>(kc.c[0].y, kc.c[1].y, kc.c[2].y, kc.c[3].y, kc.c[4].y, kc.c[5].y, kc.c[6].y, kc.c[7].y, f.w, v.y);
+                const float r2 = interp8<MODE>(kc.c[0].z, kc.c[1].z, kc.c[2].z, kc.c[3].z, kc.c[4].z, kc.c[5].z, kc.c[6].z, kc.c[7].z, f.w, v.z);
                 if (last) {
                     float *o = out + (i64)t.b * 3 * S + off;
                     o[0] = r0; o[S] = r1; o[2 * S] = r2;
@@ -240,13 +272,15 @@ __device__ __forceinline__ void red3(float4 *addr, const F3 &a)
 }
 
 // Backward of one step  v' = v + W(v) v :   g = g' + W(v)^T g' + (dW/dv : v)^T g'
-//   own    : g' + gather-form gradient through the sample position -> one red.v4 on the voxel
-//   scatter: w_d * g' onto the 8 corners, combined across lanes / planes before the red.v4
-// All contributions go through red.global.add.v4.f32 into a pre-zeroed state, so there is no
-// ordering hazard between the plain part and the scatter part; three states rotate
-// (read / accumulate / being zeroed for the next step).
-template <int MODE>
-__global__ void __launch_bounds__(VI_BWD_THREADS)
+//   own    : g' + gather-form gradient through the sample position -> plain 128-bit store into P
+//   scatter: w_d * g' onto the 8 corners -> red.global.add.v4.f32 into Y, combined across lanes
+//            and planes first (COMBINE)
+// The incoming gradient of a step is P + Y.  Two (P, Y) pairs ping-pong: a step reads pair A and
+// zeroes A's Y behind itself (each voxel is read by exactly one thread), writes own parts to
+// B's P and scatters into B's Y (zeroed one step earlier), so no pass over memory is spent on
+// clearing and no ordering hazard exists between the plain stores and the reductions.
+template <int MODE, int COMBINE>
+__global__ void __launch_bounds__(VI_BWD_THREADS, 1)
 vecint_bwd_kernel(const float *__restrict__ gout, const float4 *saved, float *__restrict__ gvec, float4 *scr,
                   int nsteps, float scale, const VGeom g)
 {
@@ -255,17 +289,21 @@ vecint_bwd_kernel(const float *__restrict__ gout, const float4 *saved, float *__
     const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, lx = lane & (VI_PX - 1), ly = lane >> 3;
     const unsigned int warp = tid >> 5, nwarps = nthr >> 5;
-    float4 *X = scr, *Y = scr + N, *Z = scr + 2 * (i64)N;
+    float4 *Pa = scr, *Ya = scr + N, *Pb = scr + 2 * (i64)N, *Yb = scr + 3 * (i64)N;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float kz = 2.0f * g.a0.rcp, ky = 2.0f * g.a1.rcp, kx = 2.0f * g.a2.rcp;
+    // autograd chain of the sample position: (S/2) * 2/(S-1) per axis where the clamp is inactive
+    const float kz = (MODE == PULPO_COORD_FAST) ? g.a0.kf : g.a0.gmul * (2.0f * g.a0.rcp);
+    const float ky = (MODE == PULPO_COORD_FAST) ? g.a1.kf : g.a1.gmul * (2.0f * g.a1.rcp);
+    const float kx = (MODE == PULPO_COORD_FAST) ? g.a2.kf : g.a2.gmul * (2.0f * g.a2.rcp);
     const int sy = g.D2, sz = g.D1 * g.D2;
-    constexpr int NOADDR = -0x40000000;
+    constexpr int NOADDR = NOBASE;
 
     for (unsigned int i = tid; i < N; i += nthr) {
         unsigned int b = i / S, v = i - b * S;
         const float *f = gout + (i64)b * 3 * S + v;
-        X[i] = make_float4(__ldg(f), __ldg(f + S), __ldg(f + 2 * S), 0.0f);
-        Y[i] = zero4;
+        Pa[i] = make_float4(__ldg(f), __ldg(f + S), __ldg(f + 2 * S), 0.0f);
+        Ya[i] = zero4;
+        Yb[i] = zero4;
     }
     for (int k = nsteps - 1; k >= 0; --k) {
         grid.sync();
@@ -275,27 +313,37 @@ vecint_bwd_kernel(const float *__restrict__ gout, const float4 *saved, float *__
             const float yf = (float)t.y, xf = (float)t.x;
             const i64 vb = (i64)t.b * S;
             const float4 *vol = vk + vb;
-            float4 *acc = Y + vb;
+            float4 *acc = Yb + vb;
             int off = t.valid ? (t.z0 * g.D1 + t.y) * g.D2 + t.x : 0;
             F3 carry = {0.f, 0.f, 0.f};   // corner (dz=1, dy=0, dx=0) of the previous plane, already combined in x and y
+            F3 up[4];                     // COMBINE == 2: all four upper corners of the previous plane
+#pragma unroll
+            for (int d = 0; d < 4; ++d) up[d] = carry;
             int carry_addr = NOADDR;
             float4 Gn = zero4, vn = zero4;
             if (t.valid) {
-                Gn = X[vb + off];
-                vn = vol[off];
+                const float4 p = ld4v(Pa + vb + off), y = ld4v(Ya + vb + off);
+                Gn = make_float4(p.x + y.x, p.y + y.y, p.z + y.z, 0.0f);
+                vn = ld4v(vol + off);
             }
+            Corners kc;
+            int prev_base = NOBASE;
             for (int z = t.z0; z < t.z1; ++z, off += sz) {
                 const float4 G = Gn, v = vn;
-                if (t.valid && z + 1 < t.z1) {   // next plane's own values, one iteration ahead of their use
-                    Gn = X[vb + off + sz];
-                    vn = vol[off + sz];
+                if (t.valid) {
+                    Ya[vb + off] = zero4;   // read above (or one iteration ago): clear it for the step after next
+                    if (z + 1 < t.z1) {     // next plane's own values, requested ahead of this plane's gathers
+                        const float4 p = ld4v(Pa + vb + off + sz), y = ld4v(Ya + vb + off + sz);
+                        Gn = make_float4(p.x + y.x, p.y + y.y, p.z + y.z, 0.0f);
+                        vn = ld4v(vol + off + sz);
+                    }
                 }
                 float uz, uy, ux;
                 const VFoot f = make_vfoot<MODE>((float)z, yf, xf, v, g, &uz, &uy, &ux);
                 const int A = t.valid ? f.base : NOADDR;
                 if (t.valid) {
-                    Corners kc;
-                    gather8(vol + f.base, sy, sz, kc);
+                    gather8(vol + f.base, sy, sz, f.base == prev_base + sz, kc);
+                    prev_base = f.base;
                     // q[d] = <corner_d, G> over the 3 channels
                     float q[8];
 #pragma unroll
@@ -306,30 +354,54 @@ vecint_bwd_kernel(const float *__restrict__ gout, const float4 *saved, float *__
                                       ((q[6] - q[4]) * f.wx0 + (q[7] - q[5]) * f.wx1) * f.wz1;
                     const float sz_ = ((q[4] - q[0]) * f.wx0 + (q[5] - q[1]) * f.wx1) * f.wy0 +
                                       ((q[6] - q[2]) * f.wx0 + (q[7] - q[3]) * f.wx1) * f.wy1;
-                    const float mz = (uz > 0.0f && uz < g.a0.Sm1) ? g.a0.gmul : 0.0f;
-                    const float my = (uy > 0.0f && uy < g.a1.Sm1) ? g.a1.gmul : 0.0f;
-                    const float mx = (ux > 0.0f && ux < g.a2.Sm1) ? g.a2.gmul : 0.0f;
-                    red_add_v4(reinterpret_cast<float *>(acc + off), G.x + (mz * sz_) * kz, G.y + (my * sy_) * ky,
-                               G.z + (mx * sx) * kx, 0.0f);
-                    Z[vb + off] = zero4;  // accumulation target of the next step
+                    const float mz = (uz > 0.0f && uz < g.a0.Sm1) ? kz : 0.0f;
+                    const float my = (uy > 0.0f && uy < g.a1.Sm1) ? ky : 0.0f;
+                    const float mx = (ux > 0.0f && ux < g.a2.Sm1) ? kx : 0.0f;
+                    Pb[vb + off] = make_float4(G.x + mz * sz_, G.y + my * sy_, G.z + mx * sx, 0.0f);
                 }
-#if defined(PULPO_VI_BWD_EXP) && PULPO_VI_BWD_EXP == 1
-                continue;
-#endif
                 // ---- scatter half.  c[d] = w_d * G for the 8 corners (all in-bounds; border corners carry weight 0)
                 F3 c[8];
 #pragma unroll
                 for (int d = 0; d < 8; ++d) {
                     c[d].x = f.w[d] * G.x; c[d].y = f.w[d] * G.y; c[d].z = f.w[d] * G.z;
                 }
-#if defined(PULPO_VI_BWD_EXP) && PULPO_VI_BWD_EXP == 2
-                if (t.valid) {
-                    float4 *q = acc + A;
-                    red3(q, c[0]); red3(q + 1, c[1]); red3(q + sy, c[2]); red3(q + sy + 1, c[3]);
-                    red3(q + sz, c[4]); red3(q + sz + 1, c[5]); red3(q + sz + sy, c[6]); red3(q + sz + sy + 1, c[7]);
+                if (COMBINE == 0) {        // one reduction per corner
+                    if (t.valid) {
+                        float4 *q = acc + A;
+                        red3(q, c[0]); red3(q + 1, c[1]); red3(q + sy, c[2]); red3(q + sy + 1, c[3]);
+                        red3(q + sz, c[4]); red3(q + sz + 1, c[5]); red3(q + sz + sy, c[6]); red3(q + sz + sy + 1, c[7]);
+                    }
+                    continue;
                 }
-                continue;
-#endif
+                if (COMBINE == 3) continue;   // timing experiment only: no scatter at all
+                if (COMBINE == 4) {           // timing experiment only: plain stores instead of reductions
+                    if (t.valid) {
+                        float4 *q = acc + A;
+#pragma unroll
+                        for (int d = 0; d < 8; ++d)
+                            q[(d & 1) + ((d >> 1) & 1) * sy + (d >> 2) * sz] = make_float4(c[d].x, c[d].y, c[d].z, 0.f);
+                    }
+                    continue;
+                }
+                if (COMBINE == 2) {
+                    // z-carry only: the four upper corners of the previous plane are this plane's lower corners
+                    // whenever the footprint moved by exactly one plane -> 4 reductions per voxel, no shuffles
+                    if (t.valid) {
+                        if (carry_addr == A) {
+#pragma unroll
+                            for (int d = 0; d < 4; ++d) { c[d].x += up[d].x; c[d].y += up[d].y; c[d].z += up[d].z; }
+                        } else if (carry_addr != NOADDR) {
+                            float4 *q = acc + carry_addr;
+                            red3(q, up[0]); red3(q + 1, up[1]); red3(q + sy, up[2]); red3(q + sy + 1, up[3]);
+                        }
+                        float4 *q = acc + A;
+                        red3(q, c[0]); red3(q + 1, c[1]); red3(q + sy, c[2]); red3(q + sy + 1, c[3]);
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) up[d] = c[4 + d];
+                        carry_addr = A + sz;
+                    }
+                    continue;
+                }
                 // combine along x: my dx=1 corners are lane+1's dx=0 corners when its footprint starts one voxel right
                 const int A_left = __shfl_up_sync(0xffffffffu, A, 1), A_right = __shfl_down_sync(0xffffffffu, A, 1);
                 const bool recv_x = (lx > 0) && (A_left + 1 == A);
@@ -359,9 +431,6 @@ vecint_bwd_kernel(const float *__restrict__ gout, const float4 *saved, float *__
                     carry_addr = A + sz;
                     float4 *q = acc + A;
                     red3(q, c[0]);
-#if defined(PULPO_VI_BWD_EXP) && PULPO_VI_BWD_EXP == 5
-                    continue;
-#endif
                     if (!sent_y) {
                         red3(q + sy, c[2]);
                         red3(q + sz + sy, c[6]);
@@ -374,16 +443,21 @@ vecint_bwd_kernel(const float *__restrict__ gout, const float4 *saved, float *__
                     }
                 }
             }
-            if (carry_addr != NOADDR) red3(acc + carry_addr, carry);
+            if (COMBINE == 1 && carry_addr != NOADDR) red3(acc + carry_addr, carry);
+            if (COMBINE == 2 && carry_addr != NOADDR) {
+                float4 *q = acc + carry_addr;
+                red3(q, up[0]); red3(q + 1, up[1]); red3(q + sy, up[2]); red3(q + sy + 1, up[3]);
+            }
         }
-        float4 *t = X; X = Y; Y = Z; Z = t;
+        float4 *t = Pa; Pa = Pb; Pb = t;
+        t = Ya; Ya = Yb; Yb = t;
     }
     grid.sync();
     for (unsigned int i = tid; i < N; i += nthr) {
         unsigned int b = i / S, v = i - b * S;
-        float4 gq = X[i];
+        const float4 p = Pa[i], y = Ya[i];
         float *o = gvec + (i64)b * 3 * S + v;
-        o[0] = gq.x * scale; o[S] = gq.y * scale; o[2 * S] = gq.z * scale;
+        o[0] = (p.x + y.x) * scale; o[S] = (p.y + y.y) * scale; o[2 * S] = (p.z + y.z) * scale;
     }
 }
 
@@ -425,7 +499,7 @@ extern "C" size_t pulpo_vecint_ws_bytes(int nsteps, int save_steps, int B, int D
 
 extern "C" size_t pulpo_vecint_bwd_scratch_bytes(int B, int D0, int D1, int D2)
 {
-    return (size_t)B * D0 * D1 * D2 * sizeof(float4) * 3;
+    return (size_t)B * D0 * D1 * D2 * sizeof(float4) * 4;   // two (P, Y) pairs
 }
 
 extern "C" int pulpo_vecint_fwd(const float *vec, float *out, void *ws, size_t ws_bytes, int nsteps, int save_steps,
@@ -433,7 +507,8 @@ extern "C" int pulpo_vecint_fwd(const float *vec, float *out, void *ws, size_t w
 {
     PULPO_REQUIRE(vec && out && ws, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2 && nsteps >= 0 && nsteps <= 30, PULPO_ERR_INVALID_SHAPE);
-    PULPO_REQUIRE(coord_mode == 0 || coord_mode == 1, PULPO_ERR_UNSUPPORTED);
+    coord_mode &= 0xff;   // high bits: backward tuning switches
+    PULPO_REQUIRE(coord_mode >= 0 && coord_mode <= 2, PULPO_ERR_UNSUPPORTED);
     PULPO_REQUIRE(ws_bytes >= pulpo_vecint_ws_bytes(nsteps, save_steps, B, D0, D1, D2) && aligned16(ws),
                   PULPO_ERR_WORKSPACE);
     VGeom g;
@@ -442,8 +517,10 @@ extern "C" int pulpo_vecint_fwd(const float *vec, float *out, void *ws, size_t w
     float scale = 1.0f / (float)(1u << nsteps);
     float4 *w4 = (float4 *)ws;
     void *args[] = {&vec, &out, &w4, &nsteps, &save_steps, &scale, &g};
-    return coord_mode == 0 ? launch_coop(vecint_fwd_kernel<0>, VI_FWD_THREADS, g, args, (cudaStream_t)stream)
-                           : launch_coop(vecint_fwd_kernel<1>, VI_FWD_THREADS, g, args, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (coord_mode == 0) return launch_coop(vecint_fwd_kernel<0>, VI_FWD_THREADS, g, args, st);
+    if (coord_mode == 1) return launch_coop(vecint_fwd_kernel<1>, VI_FWD_THREADS, g, args, st);
+    return launch_coop(vecint_fwd_kernel<2>, VI_FWD_THREADS, g, args, st);
 }
 
 extern "C" int pulpo_vecint_bwd(const float *gout, const void *saved, float *gvec, void *scratch, size_t scratch_bytes,
@@ -451,7 +528,9 @@ extern "C" int pulpo_vecint_bwd(const float *gout, const void *saved, float *gve
 {
     PULPO_REQUIRE(gout && gvec && scratch && (saved || nsteps == 0), PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2 && nsteps >= 0 && nsteps <= 30, PULPO_ERR_INVALID_SHAPE);
-    PULPO_REQUIRE(coord_mode == 0 || coord_mode == 1, PULPO_ERR_UNSUPPORTED);
+    const int variant = (coord_mode >> 8) & 0xf;   // tuning switch, see below; 0 = default
+    coord_mode &= 0xff;
+    PULPO_REQUIRE(coord_mode >= 0 && coord_mode <= 2, PULPO_ERR_UNSUPPORTED);
     PULPO_REQUIRE(scratch_bytes >= pulpo_vecint_bwd_scratch_bytes(B, D0, D1, D2) && aligned16(scratch) &&
                       aligned16(saved),
                   PULPO_ERR_WORKSPACE);
@@ -462,6 +541,16 @@ extern "C" int pulpo_vecint_bwd(const float *gout, const void *saved, float *gve
     const float4 *sv = (const float4 *)saved;
     float4 *scr = (float4 *)scratch;
     void *args[] = {&gout, &sv, &gvec, &scr, &nsteps, &scale, &g};
-    return coord_mode == 0 ? launch_coop(vecint_bwd_kernel<0>, VI_BWD_THREADS, g, args, (cudaStream_t)stream)
-                           : launch_coop(vecint_bwd_kernel<1>, VI_BWD_THREADS, g, args, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    // scatter strategy: default z-carry (2); 0x100 -> per-corner (0), 0x200 -> lane+plane combining (1);
+    // 0x300 / 0x400 -> timing experiments (no scatter / plain stores; wrong results)
+    const int comb = variant == 0 ? 2 : variant == 1 ? 0 : variant == 2 ? 1 : variant;
+#define PULPO_VI_BWD_CASE(M, C) \
+    if (coord_mode == M && comb == C) return launch_coop(vecint_bwd_kernel<M, C>, VI_BWD_THREADS, g, args, st);
+    PULPO_VI_BWD_CASE(0, 2) PULPO_VI_BWD_CASE(1, 2) PULPO_VI_BWD_CASE(2, 2)
+    PULPO_VI_BWD_CASE(0, 0) PULPO_VI_BWD_CASE(2, 0)
+    PULPO_VI_BWD_CASE(0, 1) PULPO_VI_BWD_CASE(2, 1)
+    PULPO_VI_BWD_CASE(2, 3) PULPO_VI_BWD_CASE(2, 4)
+#undef PULPO_VI_BWD_CASE
+    return PULPO_ERR_UNSUPPORTED;
 }

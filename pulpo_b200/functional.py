@@ -12,7 +12,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import CPU_EXACT, CUDA_RCP, check  # noqa: F401
+from ._lib import CPU_EXACT, CUDA_RCP, FAST, check  # noqa: F401
 
 _vp = ctypes.c_void_p
 
@@ -133,7 +133,10 @@ class _VecInt(torch.autograd.Function):
 
 
 def vecint(vec, nsteps=7, coord_mode=CPU_EXACT):
-    """VecInt.forward (src/network_blocks.py:173-177)."""
+    """VecInt.forward (src/network_blocks.py:173-177).  ``CPU_EXACT`` (default) reproduces torch-CPU bit
+    for bit; ``FAST`` computes the sample position in one FMA and interpolates with FMAs (fields within
+    ~3e-5 of the reference -- inside the 1e-4 contract, but NCC gradients downstream amplify it to ~1e-3
+    relative, and the kernel is bound by the L1 pipe, not by instruction issue, so it buys little)."""
     return _VecInt.apply(vec, nsteps, coord_mode)
 
 

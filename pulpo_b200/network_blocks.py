@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as PF
-from ._lib import CPU_EXACT
+from ._lib import CPU_EXACT, FAST
 
 
 def gauss_sampler(mu: torch.Tensor, sigma: torch.Tensor, var: Optional[int] = 1,
@@ -102,7 +102,7 @@ class VecInt(nn.Module):
         self.nsteps = nsteps
         self.scale = 1.0 / (2 ** self.nsteps)
         # kept for attribute / state-dict compatibility (reference: self.transformer.grid)
-        self.transformer = SpatialTransformer(inshape, coord_mode=coord_mode)
+        self.transformer = SpatialTransformer(inshape)
         self.coord_mode = coord_mode
 
     def forward(self, vec):

@@ -27,7 +27,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import CPU_EXACT, check
+from ._lib import CPU_EXACT, FAST, check
 from .models import loss_config
 from .synthetic import level_sizes
 
@@ -40,11 +40,13 @@ def _p(t, byte_offset=0):
 
 class HotPathPlan:
     def __init__(self, input_size, total_levels, latent_levels, batch=1, beta=0.1, gamma=0.05, lamb=0.025,
-                 with_reg=True, nsteps=7, coord_mode=CPU_EXACT, device=None, multi_stream=True, fuse_reg=True):
+                 with_reg=True, nsteps=7, coord_mode=CPU_EXACT, device=None, multi_stream=True, fuse_reg=True,
+                 vecint_mode=CPU_EXACT):
         self.L = L = latent_levels
         self.B = B = batch
         self.lk = lk = total_levels - latent_levels
         self.nsteps, self.mode, self.with_reg = nsteps, coord_mode, with_reg
+        self.vi_mode = vecint_mode   # CPU_EXACT: bit-identical fields; FAST is within 1e-4 but buys little (L1-pipe bound)
         self.fuse_reg = bool(fuse_reg and with_reg)   # L2_reg rides in the warp kernels (same field, same step)
         self.dev = dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.lib = _lib.lib()
@@ -169,7 +171,7 @@ class HotPathPlan:
             # integrate (VecInt) and resize to the output size
             ws = self.vi_ws[l]
             call(lib.pulpo_vecint_fwd, _p(comb[l]), _p(self.integ[l]), _p(ws), ws.numel() * 4, self.nsteps, 1, B,
-                 *din, mode, hs)
+                 *din, self.vi_mode, hs)
             if dout != din:
                 call(lib.pulpo_resize_up_fwd, _p(self.integ[l]), None, _p(self.final[l]), 2, 2.0, B, 3, *din, hs)
             # warp the (pooled) moving image
@@ -206,7 +208,7 @@ class HotPathPlan:
                 call(lib.pulpo_resize_up_bwd, _p(self.gfinal[l]), _p(self.ginteg[l]), 2, 2.0, 0, B, 3, *din, hs)
             scr = self.vi_scr[l]
             call(lib.pulpo_vecint_bwd, _p(self.ginteg[l]), _p(ws), _p(self.gdf[l]), _p(scr), scr.numel() * 4,
-                 self.nsteps, B, *din, mode, hs)
+                 self.nsteps, B, *din, self.vi_mode, hs)
             ev_done[l] = torch.cuda.Event()
             ev_done[l].record(s)
 

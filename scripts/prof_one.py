@@ -18,6 +18,8 @@ def main():
     shape = tuple(int(v) for v in sys.argv[2:5])
     reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 5
     win = int(sys.argv[sys.argv.index("--win") + 1]) if "--win" in sys.argv else 9
+    nsteps = int(sys.argv[sys.argv.index("--nsteps") + 1]) if "--nsteps" in sys.argv else 7
+    mode = int(sys.argv[sys.argv.index("--mode") + 1], 0) if "--mode" in sys.argv else 0
     x, y = (t.cuda() for t in syn.make_pair(shape, 0))
     f = syn.make_field(shape, 1, max_abs=3.0).cuda()
     flush = torch.empty(160 * 1024 * 1024 // 4, device="cuda")
@@ -25,7 +27,7 @@ def main():
     def run():
         if op == "vecint":
             v = f.clone().requires_grad_(True)
-            o = PF.vecint(v, 7)
+            o = PF.vecint(v, nsteps, mode)
         elif op == "warp":
             v = f.clone().requires_grad_(True)
             o = PF.warp(v, x)

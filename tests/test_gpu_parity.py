@@ -93,16 +93,59 @@ def test_warp_cuda_rcp_mode_matches_oracle_mode1(PF):
 # ----------------------------------------------------------------------------- VecInt (a3)
 @pytest.mark.parametrize("case", ["vecint_small", "vecint_large_disp"])
 def test_vecint_golden(PF, case):
+    """CPU_EXACT mode: bit-identical to the reference (torch-CPU) forward."""
     g = load_golden(case)
     vec = dev(g["vec"], True)
-    out = PF.vecint(vec, 7)
+    out = PF.vecint(vec, 7, PF.CPU_EXACT)
     assert np.array_equal(out.detach().cpu().numpy(), g["out"]), \
         "vecint fwd not bit-identical: max-abs %.3e" % np.abs(out.detach().cpu().numpy() - g["out"]).max()
     out.backward(dev(g["gout"]))
     assert_grad_close(vec.grad.cpu().numpy(), g["gvec"], case + " gvec")
     with torch.no_grad():   # ping-pong (no saved states) variant
-        out2 = PF.vecint(dev(g["vec"]), 7)
+        out2 = PF.vecint(dev(g["vec"]), 7, PF.CPU_EXACT)
     assert np.array_equal(out2.cpu().numpy(), g["out"])
+
+
+@pytest.mark.parametrize("case", ["vecint_small", "vecint_large_disp"])
+@pytest.mark.parametrize("mode", ["FAST", "CUDA_RCP"])
+def test_vecint_golden_lean_modes(PF, case, mode):
+    """Default FAST mode (one-FMA sample position, FMA interpolation) and the torch-CUDA rounding:
+    within the north_star field tolerance of the reference, gradients within the gradient tolerance."""
+    g = load_golden(case)
+    vec = dev(g["vec"], True)
+    out = PF.vecint(vec, 7, getattr(PF, mode))
+    assert_close(out.detach().cpu().numpy(), g["out"], FIELD_ATOL, case + " out " + mode)
+    out.backward(dev(g["gout"]))
+    assert_grad_close(vec.grad.cpu().numpy(), g["gvec"], case + " gvec " + mode)
+    with torch.no_grad():
+        out2 = PF.vecint(dev(g["vec"]), 7, getattr(PF, mode))
+    assert torch.equal(out2, out.detach())
+
+
+def test_vecint_scatter_variants_agree_at_level0_size(PF):
+    """Full config-2 level-0 size (80x96x112): lane/plane-combined scatter vs one reduction per corner,
+    and FAST vs CPU_EXACT, through the C ABI (size-independent property: same adjoint)."""
+    import ctypes
+    from pulpo_b200 import _lib, synthetic as syn
+    L = _lib.lib()
+    shape = (80, 96, 112)
+    v = syn.make_field(shape, 3, max_abs=3.0).cuda()
+    gout = syn.make_field(shape, 4, max_abs=1.0).cuda()
+    B = 1
+    res = {}
+    for name, fmode, bmode in [("exact", 0, 0), ("fast", 2, 2), ("fast_naive", 2, 2 | 0x100)]:
+        ws = torch.empty(L.pulpo_vecint_ws_bytes(7, 1, B, *shape) // 4, device="cuda")
+        scr = torch.empty(L.pulpo_vecint_bwd_scratch_bytes(B, *shape) // 4, device="cuda")
+        out, gv = torch.empty_like(v), torch.empty_like(v)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(L.pulpo_vecint_fwd(P(v), P(out), P(ws), ws.numel() * 4, 7, 1, B, *shape, fmode, st))
+        _lib.check(L.pulpo_vecint_bwd(P(gout), P(ws), P(gv), P(scr), scr.numel() * 4, 7, B, *shape, bmode, st))
+        torch.cuda.synchronize()
+        res[name] = (out.cpu().numpy(), gv.cpu().numpy())
+    assert_close(res["fast"][0], res["exact"][0], FIELD_ATOL, "fast vs exact out")
+    assert_grad_close(res["fast"][1], res["exact"][1], "fast vs exact gvec")
+    assert_grad_close(res["fast_naive"][1], res["fast"][1], "combined vs per-corner scatter")
 
 
 def test_vecint_zero_steps_and_zero_field(PF):
@@ -180,6 +223,43 @@ def test_ncc_vs_oracle_midsize_ragged(PF):
         ref, gref = cport.ncc(x.numpy(), y.numpy(), win, 0.05, want_grad=True)
         assert_loss_close(loss.item(), ref, "ncc ragged w=%d" % win)
         assert_grad_close(p.grad.cpu().numpy(), gref, "ncc ragged grad w=%d" % win)
+
+
+@pytest.mark.parametrize("shape,win,batch", [((40, 48, 56), 5, 1), ((33, 50, 60), 3, 2), ((30, 41, 44), 9, 1),
+                                             ((47, 70, 100), 7, 1), ((64, 64, 64), 9, 1)])
+def test_ncc_tma_path_vs_oracle(PF, shape, win, batch):
+    """Volumes that take the persistent TMA kernel (D2 % 4 == 0, D2 >= 44): ragged tiles in D1 and D2,
+    CTAs whose z range crosses a column boundary, batch > 1, every window size."""
+    from oracle import cport
+    from pulpo_b200 import synthetic as syn
+    x, y = syn.make_pair(shape, 7, batch=batch)
+    p = x.cuda().requires_grad_(True)
+    loss = PF.ncc_loss(p, y.cuda(), win, 0.05)
+    loss.backward()
+    ref, gref = cport.ncc(x.numpy(), y.numpy(), win, 0.05, want_grad=True)
+    assert_loss_close(loss.item(), ref, "ncc tma %s w=%d" % (shape, win))
+    assert_grad_close(p.grad.cpu().numpy(), gref, "ncc tma grad %s w=%d" % (shape, win))
+    with torch.no_grad():   # no coefficient volumes saved
+        assert_loss_close(PF.ncc_loss(x.cuda(), y.cuda(), win, 0.05).item(), ref, "ncc tma no-grad")
+
+
+def test_ncc_full_size_properties(PF):
+    """BASELINE config-2 size (160x192x224, win 9), where the oracle is too slow: size-independent
+    properties -- symmetry in the two images, linearity in gamma, NCC(x, x) below NCC(x, y) < 0, and
+    the backward equals gamma-scaled backward (closed form is linear in the upstream scale)."""
+    from pulpo_b200 import synthetic as syn
+    x, y = (t.cuda() for t in syn.make_pair((160, 192, 224), 1))
+    p = x.clone().requires_grad_(True)
+    lxy = PF.ncc_loss(p, y, 9, 0.05)
+    lxy.backward()
+    g1 = p.grad.clone()
+    assert_loss_close(lxy.item(), PF.ncc_loss(y, x, 9, 0.05).item(), "ncc symmetry")
+    p.grad = None
+    l2 = PF.ncc_loss(p, y, 9, 0.1)
+    l2.backward()
+    assert_loss_close(l2.item(), 2.0 * lxy.item(), "ncc linear in gamma")
+    assert_grad_close(p.grad.cpu().numpy(), 2.0 * g1.cpu().numpy(), "ncc grad linear in gamma")
+    assert PF.ncc_loss(x, x, 9, 0.05).item() < lxy.item() < 0.0
 
 
 # ----------------------------------------------------------------------------- KL (a11) / L2 (f-1)
