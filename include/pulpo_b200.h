@@ -89,6 +89,25 @@ int pulpo_vecint_bwd(const float *gout, const void *saved, float *gvec, void *sc
                      size_t scratch_bytes, int nsteps, int B, int D0, int D1, int D2,
                      int coord_mode, pulpo_stream_t stream);
 
+/* Several pyramid levels in ONE cooperative launch (SVFDecoder.integrate of every level,
+ * src/components/pulpo.py:311; PULPo.combine_dfs loop, src/models.py:362-367).  A cooperative kernel owns
+ * every SM, so per-level launches serialise and each pays its own grid barriers; the levels are
+ * independent fields with the same step count.  `levels` is a HOST array (read during the call);
+ * at most 6 levels. */
+typedef struct pulpo_vecint_level {
+    const float *in;      /* fwd: vec [B,3,D0,D1,D2]        bwd: gout */
+    float *out;           /* fwd: integrated field          bwd: gvec */
+    void *ws;             /* fwd: states (pulpo_vecint_ws_bytes)   bwd: the saved states of the forward */
+    size_t ws_bytes;      /* fwd only */
+    void *scratch;        /* bwd only (pulpo_vecint_bwd_scratch_bytes) */
+    size_t scratch_bytes; /* bwd only */
+    int D0, D1, D2;
+} pulpo_vecint_level;
+int pulpo_vecint_multi_fwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int save_steps,
+                           int B, int coord_mode, pulpo_stream_t stream);
+int pulpo_vecint_multi_bwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int B,
+                           int coord_mode, pulpo_stream_t stream);
+
 /* ---- a4 + a5: ResizeTransform.forward (factor>1) fused with DFAdder.forward ---------------
  * src/network_blocks.py:138-150, :152-158; used at src/components/pulpo.py:308,314 and
  * src/models.py:356-367.   out = trilinear_up_f(scale * x) (+ addend),  x: [B,C,d0,d1,d2],

@@ -17,6 +17,14 @@ FAST = 2        # PULPO_COORD_FAST (VecInt only)
 
 _vp, _i, _f, _sz, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_longlong
 
+
+
+class VecIntLevel(ctypes.Structure):
+    """pulpo_vecint_level (include/pulpo_b200.h)."""
+    _fields_ = [("inp", _vp), ("out", _vp), ("ws", _vp), ("ws_bytes", _sz), ("scratch", _vp), ("scratch_bytes", _sz),
+                ("D0", _i), ("D1", _i), ("D2", _i)]
+
+
 # name -> (restype, argtypes); mirrors include/pulpo_b200.h one to one
 SIGNATURES = {
     "pulpo_version": (_i, []),
@@ -29,6 +37,8 @@ SIGNATURES = {
     "pulpo_vecint_fwd": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_vecint_bwd_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "pulpo_vecint_bwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_vecint_multi_fwd": (_i, [ctypes.POINTER(VecIntLevel), _i, _i, _i, _i, _i, _vp]),
+    "pulpo_vecint_multi_bwd": (_i, [ctypes.POINTER(VecIntLevel), _i, _i, _i, _i, _vp]),
     "pulpo_resize_up_fwd": (_i, [_vp, _vp, _vp, _i, _f, _i, _i, _i, _i, _i, _vp]),
     "pulpo_resize_up_bwd": (_i, [_vp, _vp, _i, _f, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_interp_size_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -55,6 +55,24 @@ struct VGeom {
     AxisConst a0, a1, a2;
 };
 
+// One launch integrates several pyramid levels at once (they are independent fields with the same
+// step count): a cooperative kernel owns every SM, so per-level launches would serialise and each
+// would pay its own grid barriers.  Work items of all levels form one list.
+constexpr int VI_MAXL = 6;
+struct VLevel {
+    const float *in;    // fwd: vec ; bwd: gout            [B,3,D0,D1,D2]
+    float *out;         // fwd: integrated field ; bwd: gvec
+    float4 *ws;         // fwd: states ; bwd: saved states
+    float4 *scr;        // bwd: two (own, scatter) pairs
+    unsigned int item0; // first work item of this level in the joint list
+    VGeom g;
+};
+struct VMulti {
+    int n;
+    unsigned int items;   // total
+    VLevel l[VI_MAXL];
+};
+
 static int make_vgeom(VGeom &g, int B, int D0, int D1, int D2)
 {
     i64 S = (i64)D0 * D1 * D2;
@@ -65,19 +83,6 @@ static int make_vgeom(VGeom &g, int B, int D0, int D1, int D2)
     g.npy = (D1 + VI_PY - 1) / VI_PY;
     g.a0 = make_axis(D0); g.a1 = make_axis(D1); g.a2 = make_axis(D2);
     return PULPO_OK;
-}
-
-// split every patch column into z runs so that there is about one work item per resident warp
-static void set_zruns(VGeom &g, int total_warps)
-{
-    i64 columns = (i64)g.B * g.npy * g.npx;
-    i64 per_col = total_warps / (columns > 0 ? columns : 1);
-    if (per_col < 1) per_col = 1;
-    if (per_col > g.D0) per_col = g.D0;
-    g.zrun = (int)((g.D0 + per_col - 1) / per_col);
-    g.nzrun = (g.D0 + g.zrun - 1) / g.zrun;
-    g.items = (unsigned int)(columns * g.nzrun);
-    g.dnpx = make_fastdiv(g.npx); g.dnpy = make_fastdiv(g.npy); g.dnz = make_fastdiv(g.nzrun);
 }
 
 struct Item {
@@ -192,30 +197,38 @@ __device__ __forceinline__ VFoot make_vfoot(float zf, float yf, float xf, const 
 
 template <int MODE>
 __global__ void __launch_bounds__(VI_FWD_THREADS, 1)
-vecint_fwd_kernel(const float *__restrict__ vec, float *__restrict__ out, float4 *ws, int nsteps, int save,
-                  float scale, const VGeom g)
+vecint_fwd_kernel(const VMulti m, int nsteps, int save, float scale)
 {
     cg::grid_group grid = cg::this_grid();
-    const unsigned int N = g.N, S = g.S;
     const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     const unsigned int warp = tid >> 5, nwarps = nthr >> 5;
-    const int sy = g.D2, sz = g.D1 * g.D2;
 
     // v_0 = vec * 2^-nsteps, planar -> interleaved
-    for (unsigned int i = tid; i < N; i += nthr) {
-        unsigned int b = i / S, v = i - b * S;
-        const float *f = vec + (i64)b * 3 * S + v;
-        ws[i] = make_float4(__fmul_rn(__ldg(f), scale), __fmul_rn(__ldg(f + S), scale),
-                            __fmul_rn(__ldg(f + 2 * S), scale), 0.0f);
+    for (int lv = 0; lv < m.n; ++lv) {
+        const VLevel &L = m.l[lv];
+        const unsigned int N = L.g.N, S = L.g.S;
+        for (unsigned int i = tid; i < N; i += nthr) {
+            unsigned int b = i / S, v = i - b * S;
+            const float *f = L.in + (i64)b * 3 * S + v;
+            L.ws[i] = make_float4(__fmul_rn(__ldg(f), scale), __fmul_rn(__ldg(f + S), scale),
+                                  __fmul_rn(__ldg(f + 2 * S), scale), 0.0f);
+        }
     }
     for (int k = 0; k < nsteps; ++k) {
         grid.sync();
-        const float4 *src = save ? ws + (i64)k * N : ws + (i64)(k & 1) * N;
-        float4 *dst = save ? ws + (i64)(k + 1) * N : ws + (i64)((k + 1) & 1) * N;
         const bool last = (k == nsteps - 1);
-        for (unsigned int it = warp; it < g.items; it += nwarps) {
-            const Item t = decode_item(it, g, lane);
+        for (unsigned int it = warp; it < m.items; it += nwarps) {
+            int lv = 0;
+#pragma unroll
+            for (int j = 1; j < VI_MAXL; ++j) lv += (j < m.n && it >= m.l[j].item0) ? 1 : 0;
+            const VLevel &L = m.l[lv];
+            const VGeom &g = L.g;
+            const unsigned int N = g.N, S = g.S;
+            const int sy = g.D2, sz = g.D1 * g.D2;
+            const float4 *src = save ? L.ws + (i64)k * N : L.ws + (i64)(k & 1) * N;
+            float4 *dst = save ? L.ws + (i64)(k + 1) * N : L.ws + (i64)((k + 1) & 1) * N;
+            const Item t = decode_item(it - L.item0, g, lane);
             if (!t.valid) continue;
             const float yf = (float)t.y, xf = (float)t.x;
             const float4 *vol = src + (i64)t.b * S;
@@ -233,7 +246,7 @@ vecint_fwd_kernel(const float *__restrict__ vec, float *__restrict__ out, float4
                 const float r1 = interp8<MODE>(kc.c[0].y, kc.c[1].y, kc.c[2].y, kc.c[3].y, kc.c[4].y, kc.c[5].y, kc.c[6].y, kc.c[7].y, f.w, v.y);
                 const float r2 = interp8<MODE>(kc.c[0].z, kc.c[1].z, kc.c[2].z, kc.c[3].z, kc.c[4].z, kc.c[5].z, kc.c[6].z, kc.c[7].z, f.w, v.z);
                 if (last) {
-                    float *o = out + (i64)t.b * 3 * S + off;
+                    float *o = L.out + (i64)t.b * 3 * S + off;
                     o[0] = r0; o[S] = r1; o[2 * S] = r2;
                 } else {
                     dst[(i64)t.b * S + off] = make_float4(r0, r1, r2, 0.0f);
@@ -244,11 +257,15 @@ vecint_fwd_kernel(const float *__restrict__ vec, float *__restrict__ out, float4
     }
     if (nsteps == 0) {
         grid.sync();
-        for (unsigned int i = tid; i < N; i += nthr) {
-            unsigned int b = i / S, v = i - b * S;
-            float4 t = ws[i];
-            float *o = out + (i64)b * 3 * S + v;
-            o[0] = t.x; o[S] = t.y; o[2 * S] = t.z;
+        for (int lv = 0; lv < m.n; ++lv) {
+            const VLevel &L = m.l[lv];
+            const unsigned int N = L.g.N, S = L.g.S;
+            for (unsigned int i = tid; i < N; i += nthr) {
+                unsigned int b = i / S, v = i - b * S;
+                float4 t = L.ws[i];
+                float *o = L.out + (i64)b * 3 * S + v;
+                o[0] = t.x; o[S] = t.y; o[2 * S] = t.z;
+            }
         }
     }
 }
@@ -281,35 +298,47 @@ __device__ __forceinline__ void red3(float4 *addr, const F3 &a)
 // clearing and no ordering hazard exists between the plain stores and the reductions.
 template <int MODE, int COMBINE>
 __global__ void __launch_bounds__(VI_BWD_THREADS, 1)
-vecint_bwd_kernel(const float *__restrict__ gout, const float4 *saved, float *__restrict__ gvec, float4 *scr,
-                  int nsteps, float scale, const VGeom g)
+vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
 {
     cg::grid_group grid = cg::this_grid();
-    const unsigned int N = g.N, S = g.S;
     const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, lx = lane & (VI_PX - 1), ly = lane >> 3;
     const unsigned int warp = tid >> 5, nwarps = nthr >> 5;
-    float4 *Pa = scr, *Ya = scr + N, *Pb = scr + 2 * (i64)N, *Yb = scr + 3 * (i64)N;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    // autograd chain of the sample position: (S/2) * 2/(S-1) per axis where the clamp is inactive
-    const float kz = (MODE == PULPO_COORD_FAST) ? g.a0.kf : g.a0.gmul * (2.0f * g.a0.rcp);
-    const float ky = (MODE == PULPO_COORD_FAST) ? g.a1.kf : g.a1.gmul * (2.0f * g.a1.rcp);
-    const float kx = (MODE == PULPO_COORD_FAST) ? g.a2.kf : g.a2.gmul * (2.0f * g.a2.rcp);
-    const int sy = g.D2, sz = g.D1 * g.D2;
     constexpr int NOADDR = NOBASE;
+    (void)lx; (void)ly;
 
-    for (unsigned int i = tid; i < N; i += nthr) {
-        unsigned int b = i / S, v = i - b * S;
-        const float *f = gout + (i64)b * 3 * S + v;
-        Pa[i] = make_float4(__ldg(f), __ldg(f + S), __ldg(f + 2 * S), 0.0f);
-        Ya[i] = zero4;
-        Yb[i] = zero4;
+    for (int lv = 0; lv < m.n; ++lv) {
+        const VLevel &L = m.l[lv];
+        const unsigned int N = L.g.N, S = L.g.S;
+        float4 *Pa = L.scr, *Ya = L.scr + N, *Yb = L.scr + 3 * (i64)N;
+        for (unsigned int i = tid; i < N; i += nthr) {
+            unsigned int b = i / S, v = i - b * S;
+            const float *f = L.in + (i64)b * 3 * S + v;
+            Pa[i] = make_float4(__ldg(f), __ldg(f + S), __ldg(f + 2 * S), 0.0f);
+            Ya[i] = zero4;
+            Yb[i] = zero4;
+        }
     }
-    for (int k = nsteps - 1; k >= 0; --k) {
+    int flip = 0;   // which (P, Y) pair holds the incoming gradient of the current step
+    for (int k = nsteps - 1; k >= 0; --k, flip ^= 1) {
         grid.sync();
-        const float4 *vk = saved + (i64)k * N;
-        for (unsigned int it = warp; it < g.items; it += nwarps) {   // warp-uniform loop: all lanes shuffle
-            const Item t = decode_item(it, g, lane);
+        for (unsigned int it = warp; it < m.items; it += nwarps) {   // warp-uniform loop: all lanes shuffle
+            int lv = 0;
+#pragma unroll
+            for (int j = 1; j < VI_MAXL; ++j) lv += (j < m.n && it >= m.l[j].item0) ? 1 : 0;
+            const VLevel &L = m.l[lv];
+            const VGeom &g = L.g;
+            const unsigned int N = g.N, S = g.S;
+            const int sy = g.D2, sz = g.D1 * g.D2;
+            float4 *Pa = L.scr + (flip ? 2 : 0) * (i64)N, *Ya = Pa + N;
+            float4 *Pb = L.scr + (flip ? 0 : 2) * (i64)N, *Yb = Pb + N;
+            // autograd chain of the sample position: (S/2) * 2/(S-1) per axis where the clamp is inactive
+            const float kz = (MODE == PULPO_COORD_FAST) ? g.a0.kf : g.a0.gmul * (2.0f * g.a0.rcp);
+            const float ky = (MODE == PULPO_COORD_FAST) ? g.a1.kf : g.a1.gmul * (2.0f * g.a1.rcp);
+            const float kx = (MODE == PULPO_COORD_FAST) ? g.a2.kf : g.a2.gmul * (2.0f * g.a2.rcp);
+            const float4 *vk = L.ws + (i64)k * N;
+            const Item t = decode_item(it - L.item0, g, lane);
             const float yf = (float)t.y, xf = (float)t.x;
             const i64 vb = (i64)t.b * S;
             const float4 *vol = vk + vb;
@@ -449,41 +478,103 @@ vecint_bwd_kernel(const float *__restrict__ gout, const float4 *saved, float *__
                 red3(q, up[0]); red3(q + 1, up[1]); red3(q + sy, up[2]); red3(q + sy + 1, up[3]);
             }
         }
-        float4 *t = Pa; Pa = Pb; Pb = t;
-        t = Ya; Ya = Yb; Yb = t;
     }
     grid.sync();
-    for (unsigned int i = tid; i < N; i += nthr) {
-        unsigned int b = i / S, v = i - b * S;
-        const float4 p = Pa[i], y = Ya[i];
-        float *o = gvec + (i64)b * 3 * S + v;
-        o[0] = (p.x + y.x) * scale; o[S] = (p.y + y.y) * scale; o[2 * S] = (p.z + y.z) * scale;
+    for (int lv = 0; lv < m.n; ++lv) {
+        const VLevel &L = m.l[lv];
+        const unsigned int N = L.g.N, S = L.g.S;
+        const float4 *Pa = L.scr + (flip ? 2 : 0) * (i64)N, *Ya = Pa + N;
+        for (unsigned int i = tid; i < N; i += nthr) {
+            unsigned int b = i / S, v = i - b * S;
+            const float4 p = Pa[i], y = Ya[i];
+            float *o = L.out + (i64)b * 3 * S + v;
+            o[0] = (p.x + y.x) * scale; o[S] = (p.y + y.y) * scale; o[2 * S] = (p.z + y.z) * scale;
+        }
     }
 }
 
 template <typename K>
-static int coop_grid(K kernel, i64 work, int threads)
+static int coop_ctas(K kernel, int threads)
 {
     int dev = 0, sms = kSMs, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
     if (per_sm < 1) per_sm = 1;
-    i64 g = (work + threads - 1) / threads;
-    i64 cap = (i64)sms * per_sm;
-    if (g > cap) g = cap;
-    return (int)(g < 1 ? 1 : g);
+    return sms * per_sm;
+}
+
+// Split every patch column of every level into z runs of (at most) t planes, t the smallest run length
+// for which the joint item list fits the resident warps: one work item per warp, no second round.
+static void plan_items(VMulti &m, int total_warps)
+{
+    i64 colplanes = 0;
+    for (int l = 0; l < m.n; ++l) colplanes += (i64)m.l[l].g.B * m.l[l].g.npy * m.l[l].g.npx * m.l[l].g.D0;
+    int t = (int)((colplanes + total_warps - 1) / total_warps);
+    if (t < 1) t = 1;
+    for (;; ++t) {
+        i64 items = 0;
+        int maxd = 1;
+        for (int l = 0; l < m.n; ++l) {
+            VGeom &g = m.l[l].g;
+            g.zrun = t < g.D0 ? t : g.D0;
+            g.nzrun = (g.D0 + g.zrun - 1) / g.zrun;
+            items += (i64)g.B * g.npy * g.npx * g.nzrun;
+            if (g.D0 > maxd) maxd = g.D0;
+        }
+        if (items <= total_warps || t >= maxd) break;
+    }
+    unsigned int first = 0;
+    for (int l = 0; l < m.n; ++l) {
+        VGeom &g = m.l[l].g;
+        g.items = (unsigned int)((i64)g.B * g.npy * g.npx * g.nzrun);
+        g.dnpx = make_fastdiv(g.npx); g.dnpy = make_fastdiv(g.npy); g.dnz = make_fastdiv(g.nzrun);
+        m.l[l].item0 = first;
+        first += g.items;
+    }
+    m.items = first;
 }
 
 template <typename K>
-static int launch_coop(K kernel, int threads, VGeom &g, void **args, cudaStream_t st)
+static int launch_coop(K kernel, int threads, VMulti &m, void **args, cudaStream_t st)
 {
+    const int ctas = coop_ctas(kernel, threads);
     // lanes cover whole 8x4 patches, so size the grid by patch-padded voxels
-    const i64 padded = (i64)g.B * g.D0 * g.npy * VI_PY * g.npx * VI_PX;
-    const int grid = coop_grid(kernel, padded, threads);
-    set_zruns(g, grid * (threads / 32));
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)kernel, dim3(grid), dim3(threads), args, 0, st);
+    i64 padded = 0;
+    for (int l = 0; l < m.n; ++l) padded += (i64)m.l[l].g.B * m.l[l].g.D0 * m.l[l].g.npy * VI_PY * m.l[l].g.npx * VI_PX;
+    i64 grid = (padded + threads - 1) / threads;
+    if (grid > ctas) grid = ctas;
+    if (grid < 1) grid = 1;
+    plan_items(m, (int)grid * (threads / 32));
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)kernel, dim3((unsigned int)grid), dim3(threads), args, 0, st);
     return e == cudaSuccess ? launch_status() : PULPO_ERR_CUDA;
+}
+
+static int fill_levels(VMulti &m, const pulpo_vecint_level *levels, int nlevels, int B, bool bwd, int nsteps, int save)
+{
+    PULPO_REQUIRE(levels && nlevels >= 1 && nlevels <= VI_MAXL, PULPO_ERR_INVALID_SHAPE);
+    m.n = nlevels;
+    i64 total = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        const pulpo_vecint_level &v = levels[l];
+        PULPO_REQUIRE(v.in && v.out && v.ws, PULPO_ERR_NULL_POINTER);
+        PULPO_REQUIRE(v.D0 >= 2 && v.D1 >= 2 && v.D2 >= 2, PULPO_ERR_INVALID_SHAPE);
+        int rc = make_vgeom(m.l[l].g, B, v.D0, v.D1, v.D2);
+        if (rc != PULPO_OK) return rc;
+        if (bwd) {
+            PULPO_REQUIRE(v.scratch, PULPO_ERR_NULL_POINTER);
+            PULPO_REQUIRE(v.scratch_bytes >= pulpo_vecint_bwd_scratch_bytes(B, v.D0, v.D1, v.D2) && aligned16(v.scratch) &&
+                              aligned16(v.ws),
+                          PULPO_ERR_WORKSPACE);
+        } else {
+            PULPO_REQUIRE(v.ws_bytes >= pulpo_vecint_ws_bytes(nsteps, save, B, v.D0, v.D1, v.D2) && aligned16(v.ws),
+                          PULPO_ERR_WORKSPACE);
+        }
+        m.l[l].in = v.in; m.l[l].out = v.out; m.l[l].ws = (float4 *)v.ws; m.l[l].scr = (float4 *)v.scratch;
+        total += (i64)B * v.D0 * v.D1 * v.D2;
+    }
+    PULPO_REQUIRE(total < (1ll << 31), PULPO_ERR_INVALID_SHAPE);
+    return PULPO_OK;
 }
 
 }  // namespace pulpo
@@ -502,55 +593,61 @@ extern "C" size_t pulpo_vecint_bwd_scratch_bytes(int B, int D0, int D1, int D2)
     return (size_t)B * D0 * D1 * D2 * sizeof(float4) * 4;   // two (P, Y) pairs
 }
 
-extern "C" int pulpo_vecint_fwd(const float *vec, float *out, void *ws, size_t ws_bytes, int nsteps, int save_steps,
-                                int B, int D0, int D1, int D2, int coord_mode, pulpo_stream_t stream)
+extern "C" int pulpo_vecint_multi_fwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int save_steps, int B,
+                                      int coord_mode, pulpo_stream_t stream)
 {
-    PULPO_REQUIRE(vec && out && ws, PULPO_ERR_NULL_POINTER);
-    PULPO_REQUIRE(B > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2 && nsteps >= 0 && nsteps <= 30, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(B > 0 && nsteps >= 0 && nsteps <= 30, PULPO_ERR_INVALID_SHAPE);
     coord_mode &= 0xff;   // high bits: backward tuning switches
     PULPO_REQUIRE(coord_mode >= 0 && coord_mode <= 2, PULPO_ERR_UNSUPPORTED);
-    PULPO_REQUIRE(ws_bytes >= pulpo_vecint_ws_bytes(nsteps, save_steps, B, D0, D1, D2) && aligned16(ws),
-                  PULPO_ERR_WORKSPACE);
-    VGeom g;
-    int rc = make_vgeom(g, B, D0, D1, D2);
+    VMulti m;
+    int rc = fill_levels(m, levels, nlevels, B, false, nsteps, save_steps);
     if (rc != PULPO_OK) return rc;
     float scale = 1.0f / (float)(1u << nsteps);
-    float4 *w4 = (float4 *)ws;
-    void *args[] = {&vec, &out, &w4, &nsteps, &save_steps, &scale, &g};
+    void *args[] = {&m, &nsteps, &save_steps, &scale};
     cudaStream_t st = (cudaStream_t)stream;
-    if (coord_mode == 0) return launch_coop(vecint_fwd_kernel<0>, VI_FWD_THREADS, g, args, st);
-    if (coord_mode == 1) return launch_coop(vecint_fwd_kernel<1>, VI_FWD_THREADS, g, args, st);
-    return launch_coop(vecint_fwd_kernel<2>, VI_FWD_THREADS, g, args, st);
+    if (coord_mode == 0) return launch_coop(vecint_fwd_kernel<0>, VI_FWD_THREADS, m, args, st);
+    if (coord_mode == 1) return launch_coop(vecint_fwd_kernel<1>, VI_FWD_THREADS, m, args, st);
+    return launch_coop(vecint_fwd_kernel<2>, VI_FWD_THREADS, m, args, st);
 }
 
-extern "C" int pulpo_vecint_bwd(const float *gout, const void *saved, float *gvec, void *scratch, size_t scratch_bytes,
-                                int nsteps, int B, int D0, int D1, int D2, int coord_mode, pulpo_stream_t stream)
+extern "C" int pulpo_vecint_multi_bwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int B, int coord_mode,
+                                      pulpo_stream_t stream)
 {
-    PULPO_REQUIRE(gout && gvec && scratch && (saved || nsteps == 0), PULPO_ERR_NULL_POINTER);
-    PULPO_REQUIRE(B > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2 && nsteps >= 0 && nsteps <= 30, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(B > 0 && nsteps >= 0 && nsteps <= 30, PULPO_ERR_INVALID_SHAPE);
     const int variant = (coord_mode >> 8) & 0xf;   // tuning switch, see below; 0 = default
     coord_mode &= 0xff;
     PULPO_REQUIRE(coord_mode >= 0 && coord_mode <= 2, PULPO_ERR_UNSUPPORTED);
-    PULPO_REQUIRE(scratch_bytes >= pulpo_vecint_bwd_scratch_bytes(B, D0, D1, D2) && aligned16(scratch) &&
-                      aligned16(saved),
-                  PULPO_ERR_WORKSPACE);
-    VGeom g;
-    int rc = make_vgeom(g, B, D0, D1, D2);
+    VMulti m;
+    int rc = fill_levels(m, levels, nlevels, B, true, nsteps, 1);
     if (rc != PULPO_OK) return rc;
     float scale = 1.0f / (float)(1u << nsteps);
-    const float4 *sv = (const float4 *)saved;
-    float4 *scr = (float4 *)scratch;
-    void *args[] = {&gout, &sv, &gvec, &scr, &nsteps, &scale, &g};
+    void *args[] = {&m, &nsteps, &scale};
     cudaStream_t st = (cudaStream_t)stream;
     // scatter strategy: default z-carry (2); 0x100 -> per-corner (0), 0x200 -> lane+plane combining (1);
     // 0x300 / 0x400 -> timing experiments (no scatter / plain stores; wrong results)
     const int comb = variant == 0 ? 2 : variant == 1 ? 0 : variant == 2 ? 1 : variant;
 #define PULPO_VI_BWD_CASE(M, C) \
-    if (coord_mode == M && comb == C) return launch_coop(vecint_bwd_kernel<M, C>, VI_BWD_THREADS, g, args, st);
+    if (coord_mode == M && comb == C) return launch_coop(vecint_bwd_kernel<M, C>, VI_BWD_THREADS, m, args, st);
     PULPO_VI_BWD_CASE(0, 2) PULPO_VI_BWD_CASE(1, 2) PULPO_VI_BWD_CASE(2, 2)
     PULPO_VI_BWD_CASE(0, 0) PULPO_VI_BWD_CASE(2, 0)
     PULPO_VI_BWD_CASE(0, 1) PULPO_VI_BWD_CASE(2, 1)
     PULPO_VI_BWD_CASE(2, 3) PULPO_VI_BWD_CASE(2, 4)
 #undef PULPO_VI_BWD_CASE
     return PULPO_ERR_UNSUPPORTED;
+}
+
+extern "C" int pulpo_vecint_fwd(const float *vec, float *out, void *ws, size_t ws_bytes, int nsteps, int save_steps,
+                                int B, int D0, int D1, int D2, int coord_mode, pulpo_stream_t stream)
+{
+    pulpo_vecint_level lv = {vec, out, ws, ws_bytes, nullptr, 0, D0, D1, D2};
+    return pulpo_vecint_multi_fwd(&lv, 1, nsteps, save_steps, B, coord_mode, stream);
+}
+
+extern "C" int pulpo_vecint_bwd(const float *gout, const void *saved, float *gvec, void *scratch, size_t scratch_bytes,
+                                int nsteps, int B, int D0, int D1, int D2, int coord_mode, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(saved || nsteps == 0 || !gout, PULPO_ERR_NULL_POINTER);
+    pulpo_vecint_level lv = {gout, gvec, const_cast<void *>(saved), 0, scratch, scratch_bytes, D0, D1, D2};
+    if (!saved && nsteps == 0) lv.ws = scratch;   // unused by the kernel when there are no steps
+    return pulpo_vecint_multi_bwd(&lv, 1, nsteps, B, coord_mode, stream);
 }

@@ -154,12 +154,23 @@ class HotPathPlan:
             ev_comb[l] = torch.cuda.Event()
             ev_comb[l].record(cur)
 
-        # ---- per level: integrate, resize, warp, losses and their backward, on the level's stream
+        # ---- integrate every level in ONE cooperative launch (a cooperative kernel owns all SMs, so
+        #      per-level launches would serialise; pulpo.py:311 for each decoder)
+        lv_arr = (_lib.VecIntLevel * L)()
+        for l in range(L):
+            ws, scr = self.vi_ws[l], self.vi_scr[l]
+            lv_arr[l] = _lib.VecIntLevel(comb[l].data_ptr(), self.integ[l].data_ptr(), ws.data_ptr(), ws.numel() * 4,
+                                         scr.data_ptr(), scr.numel() * 4, *self.insz[l])
+        call(lib.pulpo_vecint_multi_fwd, lv_arr, L, self.nsteps, 1, B, self.vi_mode, H(cur))
+        ev_int = torch.cuda.Event()
+        ev_int.record(cur)
+
+        # ---- per level: resize, warp, losses and their backward, on the level's stream
         ev_done = {}
         for l in range(L - 1, -1, -1):
             s = lv[l]
             if ms:
-                s.wait_event(ev_comb[l] if l in ev_comb else start)
+                s.wait_event(start)
             din, dout = self.insz[l], self.outsz[l]
             nlat = 3 * din[0] * din[1] * din[2]
             hs = H(s)
@@ -168,10 +179,9 @@ class HotPathPlan:
                  self._loss_ptr(0, l), _p(self.ws_kl[l]), self.ws_kl[l].numel(), B, nlat, hs)
             call(lib.pulpo_kl_diag_bwd, None, _p(mus[l]), _p(sigmas[l]), None, None, 1e-10, self.kl_weight[l],
                  _p(self.gmu[l]), _p(self.gsigma[l]), B, nlat, hs)
-            # integrate (VecInt) and resize to the output size
-            ws = self.vi_ws[l]
-            call(lib.pulpo_vecint_fwd, _p(comb[l]), _p(self.integ[l]), _p(ws), ws.numel() * 4, self.nsteps, 1, B,
-                 *din, self.vi_mode, hs)
+            if ms:
+                s.wait_event(ev_int)
+            # resize the integrated field to the output size
             if dout != din:
                 call(lib.pulpo_resize_up_fwd, _p(self.integ[l]), None, _p(self.final[l]), 2, 2.0, B, 3, *din, hs)
             # warp the (pooled) moving image
@@ -206,18 +216,19 @@ class HotPathPlan:
                      *dout, hs)
             if dout != din:
                 call(lib.pulpo_resize_up_bwd, _p(self.gfinal[l]), _p(self.ginteg[l]), 2, 2.0, 0, B, 3, *din, hs)
-            scr = self.vi_scr[l]
-            call(lib.pulpo_vecint_bwd, _p(self.ginteg[l]), _p(ws), _p(self.gdf[l]), _p(scr), scr.numel() * 4,
-                 self.nsteps, B, *din, self.vi_mode, hs)
             ev_done[l] = torch.cuda.Event()
             ev_done[l].record(s)
 
-        # ---- fine-to-coarse: the adjoint of the combination accumulates into the coarser gradient
+        # ---- backward of the integration, again one launch for all levels
         if ms:
-            cur.wait_event(ev_done[0])
-        for l in range(1, L):
-            if ms:
+            for l in range(L):
                 cur.wait_event(ev_done[l])
+        for l in range(L):
+            lv_arr[l].inp, lv_arr[l].out = self.ginteg[l].data_ptr(), self.gdf[l].data_ptr()
+        call(lib.pulpo_vecint_multi_bwd, lv_arr, L, self.nsteps, B, self.vi_mode, H(cur))
+
+        # ---- fine-to-coarse: the adjoint of the combination accumulates into the coarser gradient
+        for l in range(1, L):
             call(lib.pulpo_resize_up_bwd, _p(self.gdf[l - 1]), _p(self.gdf[l]), 2, 2.0, 1, B, 3, *self.insz[l], H(cur))
         torch.sum(self.losses, dim=(0, 1), out=self.total)
         self.launches = n[0]

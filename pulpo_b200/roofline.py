@@ -29,6 +29,10 @@ def algo_bytes(name, args):
         return a[4] * 24 * a[6] * a[7] * a[8] * a[9]
     if name == "pulpo_vecint_bwd":          # gout, saved, gvec, scratch, bytes, nsteps, B, D0..
         return a[5] * 36 * a[6] * a[7] * a[8] * a[9]
+    if name == "pulpo_vecint_multi_fwd":    # levels*, nlevels, nsteps, save, B, mode
+        return sum(a[2] * 24 * a[4] * lv.D0 * lv.D1 * lv.D2 for lv in args[0][:a[1]])
+    if name == "pulpo_vecint_multi_bwd":    # levels*, nlevels, nsteps, B, mode
+        return sum(a[2] * 36 * a[3] * lv.D0 * lv.D1 * lv.D2 for lv in args[0][:a[1]])
     if name == "pulpo_resize_up_fwd":       # x, addend, out, factor, scale, B, C, d0, d1, d2
         f, B, C, n = a[3], a[5], a[6], a[7] * a[8] * a[9]
         return B * C * 4 * (n + n * f ** 3 * (2 if a[1] else 1))
