@@ -194,25 +194,31 @@ def run_ours(args):
     plan = None
     if args.engine == "plan":
         from pulpo_b200.plan import HotPathPlan
-        plan = HotPathPlan(size, total, latent, batch=B, device=dev)
+        plan = HotPathPlan(size, total, latent, batch=B, device=dev, fuse_reg=bool(args.fuse_reg))
         dd = {l: d[l].detach() for l in d}
         mm = {l: m[l].detach() for l in m}
         ss = {l: s[l].detach() for l in s}
 
-    def step():
+    def exchange(parts3):
+        # the only exchange this path has: the three loss scalars (gradients of the convs live upstream)
+        if world > 1:
+            scal.copy_(parts3)
+            dist.all_reduce(scal)
+
+    def compute():
+        """One hot-path forward+backward (the part that is captured as a CUDA graph)."""
         if plan is not None:     # pre-planned multi-stream launch sequence (same kernels, no autograd)
-            loss = plan.run(x, y, dd, mm, ss)
-            if world > 1:
-                scal.copy_(plan.losses.sum(dim=1))
-                dist.all_reduce(scal)
-            return loss
+            return plan.run(x, y, dd, mm, ss)
         for t in leaves:
             t.grad = None
         loss, parts, _ = hp(x, y, d, m, s)
         loss.backward()
-        if world > 1:   # the only exchange this path has: loss scalars (gradients of the convs live upstream)
-            scal.copy_(torch.stack([parts["kl"], parts["recon"], parts["reg"]]).detach())
-            dist.all_reduce(scal)
+        step.parts = torch.stack([parts["kl"], parts["recon"], parts["reg"]]).detach()
+        return loss
+
+    def step():
+        loss = compute()
+        exchange(plan.losses.sum(dim=1) if plan is not None else step.parts)
         return loss
 
     # ---- warm-up (eager), then capture the step as ONE CUDA graph
@@ -221,18 +227,18 @@ def run_ours(args):
     torch.cuda.synchronize()
     launch_mode = "cuda_graph"
     graph = None
-    if not args.no_graph and world == 1:
+    if not args.no_graph and plan is not None:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    step()
+                    compute()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_loss = step()
+                static_loss = compute()
             for _ in range(2):
                 graph.replay()
             torch.cuda.synchronize()
@@ -245,6 +251,7 @@ def run_ours(args):
     def run_step():
         if graph is not None:
             graph.replay()
+            exchange(plan.losses.sum(dim=1))   # NCCL all-reduce of the loss scalars stays outside the graph
         else:
             step()
 
@@ -282,19 +289,42 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = world * B * nvox / (ms_step * 1e-3) / 1e9
 
-    # ---- e2e: public module API, pinned host inputs, H2D + D2H inside the timed region
-    def e2e_step():
-        xx, yy, dd, mm, ss = to_dev(True)
-        loss, _, _ = hp(xx, yy, dd, mm, ss)
-        loss.backward()
-        return float(loss.item())     # D2H read of the step's result
-    for _ in range(2):
-        e2e_step()
+    # ---- e2e: public API, pinned host inputs, H2D + D2H inside the timed region
+    e2e_steps = max(4, min(args.steps, 20))
+    if plan is not None:
+        # HotPathPipeline: one packed pinned buffer per step -> one H2D copy on a copy stream, double-buffered
+        # against the graph-replayed compute; the loss scalars are read back (D2H) for every step
+        from pulpo_b200.pipeline import HotPathPipeline
+        pipe = HotPathPipeline(size, total, latent, batch=B, device=dev, fuse_reg=bool(args.fuse_reg))
+        hbs = [pipe.host_batch().fill(x_h, y_h, d_h, m_h, s_h) for _ in range(2)]
+        h2d_bytes, d2h_bytes = pipe.h2d_bytes, 16
+        e2e_api = "pulpo_b200.pipeline.HotPathPipeline.submit/result (packed pinned batch, copy/compute overlap)"
+
+        def e2e_run(n):
+            last = None
+            for k in range(n):
+                t = pipe.submit(hbs[k % 2])
+                if last is not None:
+                    r = pipe.result(last)        # D2H read of the previous step's result
+                    exchange(torch.tensor(r[1:], device=dev)) if world > 1 else None
+                last = t
+            return pipe.result(last)
+    else:
+        d2h_bytes = 4
+        e2e_api = "pulpo_b200.models.RegistrationHotPath forward + backward (autograd modules)"
+
+        def e2e_run(n):
+            out = None
+            for _ in range(n):
+                xx, yy, dd_, mm_, ss_ = to_dev(True)
+                loss, _, _ = hp(xx, yy, dd_, mm_, ss_)
+                loss.backward()
+                out = float(loss.item())     # D2H read of the step's result
+            return out
+    e2e_run(3)
     barrier()
     e0.record()
-    e2e_steps = max(2, min(args.steps, 10))
-    for _ in range(e2e_steps):
-        e2e_step()
+    e2e_run(e2e_steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -310,7 +340,7 @@ def run_ours(args):
     prof_step = step
     if plan is not None:
         from pulpo_b200.plan import HotPathPlan
-        plan1 = HotPathPlan(size, total, latent, batch=B, device=dev, multi_stream=False)
+        plan1 = HotPathPlan(size, total, latent, batch=B, device=dev, multi_stream=False, fuse_reg=bool(args.fuse_reg))
         prof_step = lambda: plan1.run(x, y, dd, mm, ss)
         prof_step()
         torch.cuda.synchronize()
@@ -356,8 +386,8 @@ def run_ours(args):
                        "levels": "%d total / %d latent, level_res, 7 integration steps" % (total, latent),
                        "launch": launch_mode, "engine": args.engine, "parallelism": "pairs sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "per-step working set ~1.5 GB >> 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "api": e2e_api},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "clocks": clk,
@@ -384,6 +414,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="pairs per GPU")
     ap.add_argument("--engine", default="plan", choices=["plan", "autograd"],
                     help="plan: pre-planned multi-stream C-ABI sequence; autograd: the drop-in nn.Modules")
+    ap.add_argument("--fuse-reg", type=int, default=1, help="plan engine: L2_reg fused into the warp kernels (1) or separate kernels (0)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -34,11 +34,14 @@ constexpr int VI_PX = 8, VI_PY = 4;   // lanes of a warp: 8 along x, 4 along y
 // One CTA per SM: a CTA that reaches grid.sync() early polls the barrier with acquire loads,
 // and every poll invalidates that SM's L1 (CCTL.IVALL) -- with several CTAs per SM this slowed
 // the CTAs still working next to it.  With one CTA per SM nobody is left to disturb.
+// Thread counts from a sweep on B200 (config-2 levels, bench kernel table): fewer, longer z runs win
+// (more corner reuse / scatter carry per run, no spills): forward 1024 -> 768: 126 -> 118 us,
+// backward 768 / 640 / 512 / 448 / 384: 343 / 347 / 322 / 356 / 414 us.
 #ifndef PULPO_VI_FWD_THREADS
-#define PULPO_VI_FWD_THREADS 1024
+#define PULPO_VI_FWD_THREADS 768
 #endif
 #ifndef PULPO_VI_BWD_THREADS
-#define PULPO_VI_BWD_THREADS 640
+#define PULPO_VI_BWD_THREADS 512
 #endif
 constexpr int VI_FWD_THREADS = PULPO_VI_FWD_THREADS;
 constexpr int VI_BWD_THREADS = PULPO_VI_BWD_THREADS;
@@ -517,8 +520,8 @@ static void plan_items(VMulti &m, int total_warps)
         int maxd = 1;
         for (int l = 0; l < m.n; ++l) {
             VGeom &g = m.l[l].g;
-            g.zrun = t < g.D0 ? t : g.D0;
-            g.nzrun = (g.D0 + g.zrun - 1) / g.zrun;
+            g.nzrun = (g.D0 + t - 1) / t;
+            g.zrun = (g.D0 + g.nzrun - 1) / g.nzrun;   // balanced runs: no warp gets more than ceil(D0 / nzrun) planes
             items += (i64)g.B * g.npy * g.npx * g.nzrun;
             if (g.D0 > maxd) maxd = g.D0;
         }

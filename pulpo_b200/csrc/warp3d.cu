@@ -3,35 +3,48 @@
 // optionally fused with L2_reg of the displacement field (src/losses.py:208-222), which reads the
 // same full-resolution field in the same step (src/models.py:160-162).
 //
-// HBM-bound streaming gather.  One thread owns VEC consecutive voxels along D2: the three
-// displacement channels are read with 128-bit loads, the 8 corner gathers go through L1/L2
-// (neighbouring voxels share cache lines), the output is written with 128-bit stores.
-// At 20 B/voxel (C=1) the HBM roofline leaves ~110 issue slots per voxel per SM, so the kernel is
-// written for instruction count: no 64-bit div/mod (FastDiv decode), 32-bit offsets, exact
-// constant division in 5 FMAs, floor via an RZ add whose float bits index memory directly, a
-// footprint that is always 2x2x2 in-bounds (fixed +1 neighbours, no predicated loads).
+// HBM-bound streaming gather: at 20 B/voxel (C=1) the roofline leaves ~110 issue slots and ~1 L1-pipe
+// cycle per voxel per SM, so the kernel is written for both: lane = x (every field load / store one
+// cache line, corner gathers 1-2 lines; see the work-mapping note below), no 64-bit div/mod
+// (FastDiv decode), 32-bit offsets, exact constant division in 5 FMAs, floor via an RZ add whose
+// float bits index memory directly, a footprint that is always 2x2x2 in-bounds (fixed +1
+// neighbours, no predicated gathers).
 // Algorithmic bytes: fwd 12 + 8C per voxel; bwd 4C (gout) + 12 (df) + 4C (img) + 12 (gdf) [+ 4C gimg].
 #include "common.cuh"
 
 namespace pulpo {
 
+// Work mapping.  A warp owns 32 consecutive voxels along D2 times WR consecutive rows along D1 at
+// one plane; lane = x.  What bounds these kernels after HBM is the SM's L1 load/store pipe: a warp
+// load that touches n cache lines occupies it for ~2n cycles.  With lane = x every field load and
+// every store is one line, and each of the 8 corner gathers of a smooth field touches 1-2 lines
+// (the previous mapping, 4 consecutive voxels per thread and 128-bit field loads, spread every
+// gather over 4 lines: 2.3 pipe cycles per voxel against 1.0 now).  WR rows per thread keep
+// several independent gathers in flight and let the fused regulariser take its y neighbours from
+// registers and its x neighbours from warp shuffles.
+constexpr int WR = 4;
+
 struct WarpGeom {
-    int B, C, D0, D1, D2, XG;
-    unsigned int groups;
+    int B, C, D0, D1, D2, S;
+    int nxb, nyb;            // 32-voxel blocks per row, WR-row blocks per plane
+    unsigned int items;      // B * D0 * nyb * nxb  (one per warp)
     int unbias;
-    FastDiv dXG, dD1, dD0;
+    FastDiv dnxb, dnyb, dD0;
     AxisConst a0, a1, a2;
 };
 
-static int make_geom(WarpGeom &g, int B, int C, int D0, int D1, int D2, int vec)
+static int make_geom(WarpGeom &g, int B, int C, int D0, int D1, int D2)
 {
     i64 S = (i64)D0 * D1 * D2;
-    if (S >= (1ll << 31) || (i64)B * S / vec >= (1ll << 31) || D0 > (1 << 22) || D1 > (1 << 22) || D2 > (1 << 22))
-        return PULPO_ERR_INVALID_SHAPE;
-    g.B = B; g.C = C; g.D0 = D0; g.D1 = D1; g.D2 = D2; g.XG = D2 / vec;
-    g.groups = (unsigned int)((i64)B * D0 * D1 * g.XG);
+    if (S >= (1ll << 31) || D0 > (1 << 22) || D1 > (1 << 22) || D2 > (1 << 22)) return PULPO_ERR_INVALID_SHAPE;
+    g.B = B; g.C = C; g.D0 = D0; g.D1 = D1; g.D2 = D2; g.S = (int)S;
+    g.nxb = (D2 + 31) / 32;
+    g.nyb = (D1 + WR - 1) / WR;
+    i64 items = (i64)B * D0 * g.nyb * g.nxb;
+    if (items * 32 >= (1ll << 32)) return PULPO_ERR_INVALID_SHAPE;
+    g.items = (unsigned int)items;
     g.unbias = tap_unbias(D1, D2);
-    g.dXG = make_fastdiv(g.XG); g.dD1 = make_fastdiv(D1); g.dD0 = make_fastdiv(D0);
+    g.dnxb = make_fastdiv(g.nxb); g.dnyb = make_fastdiv(g.nyb); g.dD0 = make_fastdiv(D0);
     g.a0 = make_axis(D0); g.a1 = make_axis(D1); g.a2 = make_axis(D2);
     return PULPO_OK;
 }
@@ -54,37 +67,6 @@ __device__ __forceinline__ Foot make_foot(float zf, float yf, float xf, float dz
     f.wx0 = tx.w0; f.wx1 = tx.w1; f.wy0 = ty.w0; f.wy1 = ty.w1; f.wz0 = tz.w0; f.wz1 = tz.w1;
     if (fl) { fl[0] = tz.floor_p; fl[1] = ty.floor_p; fl[2] = tx.floor_p; }
     return f;
-}
-
-template <int VEC>
-__device__ __forceinline__ void load_vec(const float *p, float (&v)[VEC])
-{
-    if (VEC == 4) {
-        float4 t = ld_stream4(p);
-        v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
-    } else {
-        v[0] = __ldg(p);
-    }
-}
-
-template <int VEC>
-__device__ __forceinline__ void load_vec_cached(const float *p, float (&v)[VEC])
-{
-    if (VEC == 4) {
-        float4 t = __ldg(reinterpret_cast<const float4 *>(p));
-        v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
-    } else {
-        v[0] = __ldg(p);
-    }
-}
-
-template <int VEC>
-__device__ __forceinline__ void store_vec(float *p, const float (&v)[VEC])
-{
-    if (VEC == 4)
-        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
-    else
-        p[0] = v[0];
 }
 
 // 8 corners of one footprint (fixed neighbour offsets)
@@ -117,173 +99,223 @@ __device__ __forceinline__ float interp8(const C8 &k, const Foot &f)
     return acc;
 }
 
-// L2_reg of the field at the VEC voxels this thread owns (forward differences on the
-// [1:,1:,1:] crop, src/losses.py:217-221): returns sum of squared differences
-template <int VEC>
-__device__ __forceinline__ float l2_fwd_terms(const float *f, const float (&c)[VEC], int x0, bool crop_zy, int sy, int sz)
+struct WItem {
+    int b, z, y0, x;
+    bool xok;
+};
+
+__device__ __forceinline__ WItem decode_witem(unsigned int w, int lane, const WarpGeom &g)
 {
-    if (!crop_zy) return 0.0f;
-    float pz[VEC], py[VEC];
-    load_vec_cached<VEC>(f - sz, pz);
-    load_vec_cached<VEC>(f - sy, py);
-    float acc = 0.0f;
-    if (x0 > 0) {
-        const float px = __ldg(f - 1);
-        float t = c[0] - pz[0]; acc += t * t;
-        t = c[0] - py[0]; acc += t * t;
-        t = c[0] - px; acc += t * t;
-    }
+    unsigned int r, xb, r2, yb, b, z;
+    fast_divmod(w, g.dnxb, r, xb);
+    fast_divmod(r, g.dnyb, r2, yb);
+    fast_divmod(r2, g.dD0, b, z);
+    WItem t;
+    t.b = (int)b; t.z = (int)z; t.y0 = (int)yb * WR; t.x = (int)xb * 32 + lane;
+    t.xok = t.x < g.D2;
+    return t;
+}
+
+// the WR values of one field channel this thread owns (0 outside the volume)
+__device__ __forceinline__ void load_rows(const float *f, int sy, const bool (&ok)[WR], float (&v)[WR])
+{
 #pragma unroll
-    for (int j = 1; j < VEC; ++j) {
-        float t = c[j] - pz[j]; acc += t * t;
-        t = c[j] - py[j]; acc += t * t;
-        t = c[j] - c[j - 1]; acc += t * t;
+    for (int j = 0; j < WR; ++j) v[j] = ok[j] ? __ldg(f + j * sy) : 0.0f;
+}
+
+// L2_reg of one field channel at the WR voxels this thread owns (forward differences on the
+// [1:,1:,1:] crop, src/losses.py:217-221): sum of squared differences.  y neighbours come from the
+// thread's own registers, x neighbours from the lane to the left.  `inner` (warp-uniform): the block
+// lies inside the crop in z and y and inside the volume, so only the x edge needs a per-lane mask.
+__device__ __forceinline__ float l2_fwd_terms(const float *f, const float (&c)[WR], const bool (&ok)[WR], const WItem &t,
+                                              int lane, int sy, int sz, bool inner)
+{
+    float acc = 0.0f;
+    if (inner) {
+        const float xin = t.x > 0 ? 1.0f : 0.0f;
+        float py = __ldg(f - sy);
+#pragma unroll
+        for (int j = 0; j < WR; ++j) {
+            float left = __shfl_up_sync(0xffffffffu, c[j], 1);
+            if (lane == 0 && t.x > 0) left = __ldg(f + j * sy - 1);
+            const float dzz = c[j] - __ldg(f + j * sy - sz), dyy = c[j] - py, dxx = c[j] - left;
+            acc += xin * (dzz * dzz + dyy * dyy + dxx * dxx);
+            py = c[j];
+        }
+        return acc;
+    }
+    const bool zin = t.z > 0;
+    // row above the block (needed by row 0)
+    const float up = (ok[0] && t.y0 > 0) ? __ldg(f - sy) : 0.0f;
+#pragma unroll
+    for (int j = 0; j < WR; ++j) {
+        float left = __shfl_up_sync(0xffffffffu, c[j], 1);
+        if (lane == 0 && ok[j] && t.x > 0) left = __ldg(f + j * sy - 1);
+        const bool in = ok[j] && zin && (t.y0 + j > 0) && (t.x > 0);
+        if (in) {
+            const float pz = __ldg(f + j * sy - sz);
+            const float py = j > 0 ? c[j > 0 ? j - 1 : 0] : up;
+            float d = c[j] - pz; acc += d * d;
+            d = c[j] - py; acc += d * d;
+            d = c[j] - left; acc += d * d;
+        }
     }
     return acc;
 }
 
-template <int MODE, int VEC, bool IDX, bool REG>
-__global__ void __launch_bounds__(256, REG ? 2 : 3)
+template <int MODE, bool IDX, bool REG>
+__global__ void __launch_bounds__(256, 3)
 warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, float *__restrict__ out,
                   int32_t *__restrict__ idx, float *reg_out, ReduceWs *ws, double reg_scale, const WarpGeom g)
 {
     __shared__ double red[32];
-    const unsigned int gid = blockIdx.x * 256u + threadIdx.x;
+    const unsigned int nwarps = gridDim.x * 8u;
+    const int lane = threadIdx.x & 31;
+    const int S = g.S, sy = g.D2, sz = g.D1 * g.D2;
     float reg_acc = 0.0f;
-    if (gid < g.groups) {
-        unsigned int row, xg, zb, y, b, z;
-        fast_divmod(gid, g.dXG, row, xg);
-        fast_divmod(row, g.dD1, zb, y);
-        fast_divmod(zb, g.dD0, b, z);
-        const int S = g.D0 * g.D1 * g.D2;
-        const int x0 = xg * VEC;
-        const int v0 = (z * g.D1 + y) * g.D2 + x0;
-        const int sy = g.D2, sz = g.D1 * g.D2;
-        const float *f = df + (i64)b * 3 * S + v0;
-
-        float dz[VEC], dy[VEC], dx[VEC];
-        if (REG) {   // the field is re-read by neighbouring threads for the differences: keep it cached
-            load_vec_cached<VEC>(f, dz);
-            load_vec_cached<VEC>(f + S, dy);
-            load_vec_cached<VEC>(f + 2 * S, dx);
-        } else {
-            load_vec<VEC>(f, dz);
-            load_vec<VEC>(f + S, dy);
-            load_vec<VEC>(f + 2 * S, dx);
-        }
-        if (REG) {   // first, while only the field values are live
-            const bool crop = (z > 0 && y > 0);
-            reg_acc = l2_fwd_terms<VEC>(f, dz, x0, crop, sy, sz) + l2_fwd_terms<VEC>(f + S, dy, x0, crop, sy, sz) +
-                      l2_fwd_terms<VEC>(f + 2 * S, dx, x0, crop, sy, sz);
-        }
-        const float zf = (float)(int)z, yf = (float)(int)y, xf0 = (float)x0;
-
-        Foot ft[VEC];
+    // persistent: whole waves of resident CTAs stride over the work items (one warp-item at a time)
+    for (unsigned int w = (blockIdx.x * 256u + threadIdx.x) >> 5; w < g.items; w += nwarps) {
+        const WItem t = decode_witem(w, lane, g);
+        const int v0 = (t.z * g.D1 + t.y0) * g.D2 + t.x;
+        bool ok[WR];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
+        for (int j = 0; j < WR; ++j) ok[j] = t.xok && (t.y0 + j < g.D1);
+        const float *f = df + (i64)t.b * 3 * S + v0;
+        float dz[WR], dy[WR], dx[WR];
+        load_rows(f, sy, ok, dz);
+        load_rows(f + S, sy, ok, dy);
+        load_rows(f + 2 * S, sy, ok, dx);
+        if (REG) {
+            const bool inner = t.z > 0 && t.y0 > 0 && t.y0 + WR <= g.D1 && __all_sync(0xffffffffu, t.xok);
+            reg_acc += l2_fwd_terms(f, dz, ok, t, lane, sy, sz, inner) + l2_fwd_terms(f + S, dy, ok, t, lane, sy, sz, inner) +
+                       l2_fwd_terms(f + 2 * S, dx, ok, t, lane, sy, sz, inner);
+        }
+        const float zf = (float)t.z, xf = (float)t.x;
+        Foot ft[WR];
+#pragma unroll
+        for (int j = 0; j < WR; ++j) {
             int fl[3];
-            ft[j] = make_foot<MODE>(zf, yf, xf0 + (float)j, dz[j], dy[j], dx[j], g, nullptr, nullptr, nullptr,
+            ft[j] = make_foot<MODE>(zf, (float)(t.y0 + j), xf, dz[j], dy[j], dx[j], g, nullptr, nullptr, nullptr,
                                     IDX ? fl : nullptr);
-            if (IDX) {
-                int32_t *o = idx + (i64)b * 3 * S + v0 + j;
+            if (IDX && ok[j]) {
+                int32_t *o = idx + (i64)t.b * 3 * S + v0 + j * sy;
                 o[0] = fl[0]; o[S] = fl[1]; o[2 * S] = fl[2];
             }
         }
         for (int c = 0; c < g.C; ++c) {
-            const float *im = img + ((i64)b * g.C + c) * S;
-            float res[VEC];
+            const float *im = img + ((i64)t.b * g.C + c) * S;
+            float *o = out + ((i64)t.b * g.C + c) * S + v0;
+            float res[WR];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) res[j] = interp8(gather8(im + ft[j].base, sy, sz), ft[j]);
-            store_vec<VEC>(out + ((i64)b * g.C + c) * S + v0, res);
+            for (int j = 0; j < WR; ++j) res[j] = ok[j] ? interp8(gather8(im + ft[j].base, sy, sz), ft[j]) : 0.0f;
+#pragma unroll
+            for (int j = 0; j < WR; ++j)
+                if (ok[j]) o[j * sy] = res[j];
         }
     }
     if (REG) {
         double bt = block_sum((double)reg_acc, red);
-        grid_reduce_finish_atomic(bt, ws, reg_out, reg_scale);
+        grid_reduce_finish(bt, ws, reg_out, reg_scale, red);
     }
 }
 
-// gradient of L2_reg w.r.t. the field at the VEC voxels this thread owns, gather form (see
+// gradient of L2_reg w.r.t. one field channel at the WR voxels this thread owns, gather form (see
 // l2reg_bwd_v4_kernel in losses.cu): voxel v collects its own three differences if it is inside
-// the crop, minus the difference of each forward neighbour that is inside the crop
-template <int VEC>
-__device__ __forceinline__ void l2_bwd_terms(const float *f, const float (&c)[VEC], float (&r)[VEC], int x0, int D2,
-                                             bool zin, bool yin, bool zn, bool yn, int sy, int sz)
+// the crop, minus the difference of each forward neighbour that is inside the crop.  `inner`
+// (warp-uniform): every row of the block has all four z / y neighbours inside the volume and the
+// crop, which leaves the discrete Laplacian with per-lane masks for the two x edges.
+__device__ __forceinline__ void l2_bwd_terms(const float *f, const float (&c)[WR], const bool (&ok)[WR], float (&r)[WR],
+                                             const WItem &t, int lane, const WarpGeom &g, int sy, int sz, bool inner)
 {
-    float pz[VEC], py[VEC], nz[VEC], ny[VEC];
+    const bool xin = t.x > 0, xn = t.x + 1 < g.D2;
+    if (inner) {
+        const float mi = xin ? 1.0f : 0.0f, mn = xn ? 1.0f : 0.0f;
+        float py = __ldg(f - sy);
+        const float down = __ldg(f + WR * sy);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) pz[j] = py[j] = nz[j] = ny[j] = 0.0f;
-    if (zin) load_vec_cached<VEC>(f - sz, pz);
-    if (yin) load_vec_cached<VEC>(f - sy, py);
-    if (zn) load_vec_cached<VEC>(f + sz, nz);
-    if (yn) load_vec_cached<VEC>(f + sy, ny);
-    const float left = x0 > 0 ? __ldg(f - 1) : 0.0f;
-    const float right = x0 + VEC < D2 ? __ldg(f + VEC) : 0.0f;
+        for (int j = 0; j < WR; ++j) {
+            float left = __shfl_up_sync(0xffffffffu, c[j], 1), right = __shfl_down_sync(0xffffffffu, c[j], 1);
+            if (lane == 0 && xin) left = __ldg(f + j * sy - 1);
+            if (lane == 31 && xn) right = __ldg(f + j * sy + 1);
+            const float cc = c[j];
+            const float ny = j + 1 < WR ? c[j + 1 < WR ? j + 1 : 0] : down;
+            const float nb = (__ldg(f + j * sy - sz) + __ldg(f + j * sy + sz)) + (py + ny);
+            r[j] = mi * ((5.0f * cc - left) - nb) - mn * (right - cc);
+            py = cc;
+        }
+        return;
+    }
+    const bool zin = t.z > 0, zn = t.z + 1 < g.D0;
+    const float up = (ok[0] && t.y0 > 0) ? __ldg(f - sy) : 0.0f;
+    const float down = (t.xok && t.y0 + WR < g.D1) ? __ldg(f + WR * sy) : 0.0f;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        const int x = x0 + j;
-        const bool xin = x > 0, xn = x + 1 < D2;
-        const float cc = c[j];
-        const float cl = j > 0 ? c[j > 0 ? j - 1 : 0] : left;
-        const float cr = j + 1 < VEC ? c[j + 1 < VEC ? j + 1 : 0] : right;
+    for (int j = 0; j < WR; ++j) {
+        float left = __shfl_up_sync(0xffffffffu, c[j], 1), right = __shfl_down_sync(0xffffffffu, c[j], 1);
+        if (lane == 0 && ok[j] && xin) left = __ldg(f + j * sy - 1);
+        if (lane == 31 && ok[j] && xn) right = __ldg(f + j * sy + 1);
         float a = 0.0f;
-        if (xin && yin && zin) a += (cc - pz[j]) + (cc - py[j]) + (cc - cl);
-        if (zn && yin && xin) a -= nz[j] - cc;
-        if (yn && zin && xin) a -= ny[j] - cc;
-        if (xn && zin && yin) a -= cr - cc;
+        if (ok[j]) {
+            const bool yin = t.y0 + j > 0, yn = t.y0 + j + 1 < g.D1;
+            const float cc = c[j];
+            const float pz = zin ? __ldg(f + j * sy - sz) : 0.0f, nz = zn ? __ldg(f + j * sy + sz) : 0.0f;
+            const float py = j > 0 ? c[j > 0 ? j - 1 : 0] : up;
+            const float ny = j + 1 < WR ? c[j + 1 < WR ? j + 1 : 0] : down;
+            if (xin && yin && zin) a += (cc - pz) + (cc - py) + (cc - left);
+            if (zn && yin && xin) a -= nz - cc;
+            if (yn && zin && xin) a -= ny - cc;
+            if (xn && zin && yin) a -= right - cc;
+        }
         r[j] = a;
     }
 }
 
 // Backward: gather half (gdf) always, scatter half (gimg) only when requested.  REG adds the
 // gradient of the fused L2_reg term to gdf.
-template <int MODE, int VEC, bool SCATTER, bool REG>
+template <int MODE, bool SCATTER, bool REG>
 __global__ void __launch_bounds__(256, 2)
 warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ df,
                   float *__restrict__ gimg, float *__restrict__ gdf, const float *__restrict__ reg_gloss,
                   float reg_k, const WarpGeom g)
 {
-    const unsigned int gid = blockIdx.x * 256u + threadIdx.x;
-    if (gid >= g.groups) return;
-    unsigned int row, xg, zb, y, b, z;
-    fast_divmod(gid, g.dXG, row, xg);
-    fast_divmod(row, g.dD1, zb, y);
-    fast_divmod(zb, g.dD0, b, z);
-    const int S = g.D0 * g.D1 * g.D2;
-    const int x0 = xg * VEC;
-    const int v0 = (z * g.D1 + y) * g.D2 + x0;
-    const float *f = df + (i64)b * 3 * S + v0;
-
-    float dz[VEC], dy[VEC], dx[VEC];
-    if (REG) {
-        load_vec_cached<VEC>(f, dz);
-        load_vec_cached<VEC>(f + S, dy);
-        load_vec_cached<VEC>(f + 2 * S, dx);
-    } else {
-        load_vec<VEC>(f, dz);
-        load_vec<VEC>(f + S, dy);
-        load_vec<VEC>(f + 2 * S, dx);
-    }
-    const float zf = (float)(int)z, yf = (float)(int)y, xf0 = (float)x0;
-
-    const int sy = g.D2, sz = g.D1 * g.D2;
-    float rz[VEC], ry[VEC], rx[VEC];
+    const unsigned int nwarps = gridDim.x * 8u;
+    const int lane = threadIdx.x & 31;
+    const int S = g.S, sy = g.D2, sz = g.D1 * g.D2;
+    const float reg_scale_k = REG ? (reg_gloss ? __ldg(reg_gloss) : 1.0f) * reg_k : 0.0f;
+    for (unsigned int w = (blockIdx.x * 256u + threadIdx.x) >> 5; w < g.items; w += nwarps) {   // persistent, warp-uniform
+    const WItem t = decode_witem(w, lane, g);
+    const int v0 = (t.z * g.D1 + t.y0) * g.D2 + t.x;
+    bool ok[WR];
+#pragma unroll
+    for (int j = 0; j < WR; ++j) ok[j] = t.xok && (t.y0 + j < g.D1);
+    const float *f = df + (i64)t.b * 3 * S + v0;
+    float dz[WR], dy[WR], dx[WR];
+    load_rows(f, sy, ok, dz);
+    load_rows(f + S, sy, ok, dy);
+    load_rows(f + 2 * S, sy, ok, dx);
+    const float zf = (float)t.z, xf = (float)t.x;
     // autograd chain of 2*(loc/(S-1)-0.5) after the sampler's S/2:  (m*g*2)/(S-1)
     const float kz = 2.0f * g.a0.rcp, ky = 2.0f * g.a1.rcp, kx = 2.0f * g.a2.rcp;
-    float go1[VEC];
-    if (g.C == 1) load_vec<VEC>(gout + (i64)b * S + v0, go1);   // the common case: one 128-bit load
+    float rz[WR], ry[WR], rx[WR];
+    Foot ft[WR];
+    float mz[WR], my[WR], mx[WR];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
+    for (int j = 0; j < WR; ++j) {
         float uz, uy, ux;
-        const Foot k = make_foot<MODE>(zf, yf, xf0 + (float)j, dz[j], dy[j], dx[j], g, &uz, &uy, &ux);
+        ft[j] = make_foot<MODE>(zf, (float)(t.y0 + j), xf, dz[j], dy[j], dx[j], g, &uz, &uy, &ux);
         // zero gradient wherever the border clamp is active (p <= 0 or p >= S-1)
-        const float mz = (uz > 0.0f && uz < g.a0.Sm1) ? g.a0.gmul : 0.0f;
-        const float my = (uy > 0.0f && uy < g.a1.Sm1) ? g.a1.gmul : 0.0f;
-        const float mx = (ux > 0.0f && ux < g.a2.Sm1) ? g.a2.gmul : 0.0f;
-        float gz = 0.0f, gy = 0.0f, gx = 0.0f;
-        for (int c = 0; c < g.C; ++c) {
-            const i64 off = ((i64)b * g.C + c) * S;
-            const float go = (g.C == 1) ? go1[j] : __ldg(gout + off + v0 + j);
+        mz[j] = (uz > 0.0f && uz < g.a0.Sm1) ? g.a0.gmul : 0.0f;
+        my[j] = (uy > 0.0f && uy < g.a1.Sm1) ? g.a1.gmul : 0.0f;
+        mx[j] = (ux > 0.0f && ux < g.a2.Sm1) ? g.a2.gmul : 0.0f;
+        rz[j] = ry[j] = rx[j] = 0.0f;
+    }
+    for (int c = 0; c < g.C; ++c) {
+        const i64 off = ((i64)t.b * g.C + c) * S;
+        float go[WR];
+        load_rows(gout + off + v0, sy, ok, go);
+#pragma unroll
+        for (int j = 0; j < WR; ++j) {
+            if (!ok[j]) continue;
+            const Foot &k = ft[j];
             const C8 q = gather8(img + off + k.base, sy, sz);
             // d/dx: difference along x, interpolated along y and z; likewise for y and z
             const float sx = ((q.c001 - q.c000) * k.wy0 + (q.c011 - q.c010) * k.wy1) * k.wz0 +
@@ -292,13 +324,13 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
                               ((q.c110 - q.c100) * k.wx0 + (q.c111 - q.c101) * k.wx1) * k.wz1;
             const float sz_ = ((q.c100 - q.c000) * k.wx0 + (q.c101 - q.c001) * k.wx1) * k.wy0 +
                               ((q.c110 - q.c010) * k.wx0 + (q.c111 - q.c011) * k.wx1) * k.wy1;
-            gx += sx * go;
-            gy += sy_ * go;
-            gz += sz_ * go;
+            rx[j] += sx * go[j];
+            ry[j] += sy_ * go[j];
+            rz[j] += sz_ * go[j];
             if (SCATTER) {
                 float *o = gimg + off + k.base;
                 const float w00 = k.wx0 * k.wy0, w01 = k.wx1 * k.wy0, w10 = k.wx0 * k.wy1, w11 = k.wx1 * k.wy1;
-                const float g0 = go * k.wz0, g1 = go * k.wz1;
+                const float g0 = go[j] * k.wz0, g1 = go[j] * k.wz1;
                 atomicAdd(o, w00 * g0);
                 atomicAdd(o + 1, w01 * g0);
                 atomicAdd(o + sy, w10 * g0);
@@ -309,91 +341,103 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
                 atomicAdd(o + sz + sy + 1, w11 * g1);
             }
         }
-        rz[j] = (mz * gz) * kz;
-        ry[j] = (my * gy) * ky;
-        rx[j] = (mx * gx) * kx;
+    }
+#pragma unroll
+    for (int j = 0; j < WR; ++j) {
+        rz[j] = (mz[j] * rz[j]) * kz;
+        ry[j] = (my[j] * ry[j]) * ky;
+        rx[j] = (mx[j] * rx[j]) * kx;
     }
     if (REG) {
-        const float k = (reg_gloss ? __ldg(reg_gloss) : 1.0f) * reg_k;
-        const bool zin = z > 0, yin = y > 0, zn = (int)z + 1 < g.D0, yn = (int)y + 1 < g.D1;
-        float t[VEC];
-        l2_bwd_terms<VEC>(f, dz, t, x0, g.D2, zin, yin, zn, yn, sy, sz);
+        const float k = reg_scale_k;
+        const bool inner = t.z > 0 && t.z + 1 < g.D0 && t.y0 > 0 && t.y0 + WR < g.D1 && __all_sync(0xffffffffu, t.xok);
+        float tt[WR];
+        l2_bwd_terms(f, dz, ok, tt, t, lane, g, sy, sz, inner);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) rz[j] += k * t[j];
-        l2_bwd_terms<VEC>(f + S, dy, t, x0, g.D2, zin, yin, zn, yn, sy, sz);
+        for (int j = 0; j < WR; ++j) rz[j] += k * tt[j];
+        l2_bwd_terms(f + S, dy, ok, tt, t, lane, g, sy, sz, inner);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) ry[j] += k * t[j];
-        l2_bwd_terms<VEC>(f + 2 * S, dx, t, x0, g.D2, zin, yin, zn, yn, sy, sz);
+        for (int j = 0; j < WR; ++j) ry[j] += k * tt[j];
+        l2_bwd_terms(f + 2 * S, dx, ok, tt, t, lane, g, sy, sz, inner);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) rx[j] += k * t[j];
+        for (int j = 0; j < WR; ++j) rx[j] += k * tt[j];
     }
     if (gdf) {
-        float *o = gdf + (i64)b * 3 * S + v0;
-        store_vec<VEC>(o, rz);
-        store_vec<VEC>(o + S, ry);
-        store_vec<VEC>(o + 2 * S, rx);
+        float *o = gdf + (i64)t.b * 3 * S + v0;
+#pragma unroll
+        for (int j = 0; j < WR; ++j)
+            if (ok[j]) {
+                o[j * sy] = rz[j];
+                o[S + j * sy] = ry[j];
+                o[2 * S + j * sy] = rx[j];
+            }
     }
+    }   // persistent loop
 }
 
-template <int MODE, int VEC>
+// 8 warps per CTA; at most `per_sm` resident CTAs per SM, each striding over the items
+static unsigned int persistent_grid(unsigned int items, int per_sm)
+{
+    int dev = 0, sms = kSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned int want = (items + 7) / 8, cap = (unsigned int)(sms * per_sm);
+    return want < cap ? (want ? want : 1) : cap;
+}
+
+template <int MODE>
 static int launch_fwd(const float *img, const float *df, float *out, int32_t *idx, float *reg_out, ReduceWs *ws,
                       double reg_scale, int B, int C, int D0, int D1, int D2, cudaStream_t st)
 {
     WarpGeom g;
-    int rc = make_geom(g, B, C, D0, D1, D2, VEC);
+    int rc = make_geom(g, B, C, D0, D1, D2);
     if (rc != PULPO_OK) return rc;
-    const unsigned int grid = (g.groups + 255) / 256;
+    const unsigned int grid = persistent_grid(g.items, 3);
     if (idx)
-        warp3d_fwd_kernel<MODE, VEC, true, false><<<grid, 256, 0, st>>>(img, df, out, idx, nullptr, nullptr, 0.0, g);
+        warp3d_fwd_kernel<MODE, true, false><<<grid, 256, 0, st>>>(img, df, out, idx, nullptr, nullptr, 0.0, g);
     else if (reg_out)
-        warp3d_fwd_kernel<MODE, VEC, false, true><<<grid, 256, 0, st>>>(img, df, out, nullptr, reg_out, ws, reg_scale, g);
+        warp3d_fwd_kernel<MODE, false, true><<<grid, 256, 0, st>>>(img, df, out, nullptr, reg_out, ws, reg_scale, g);
     else
-        warp3d_fwd_kernel<MODE, VEC, false, false><<<grid, 256, 0, st>>>(img, df, out, nullptr, nullptr, nullptr, 0.0, g);
+        warp3d_fwd_kernel<MODE, false, false><<<grid, 256, 0, st>>>(img, df, out, nullptr, nullptr, nullptr, 0.0, g);
     return launch_status();
 }
 
-template <int MODE, int VEC>
+template <int MODE>
 static int launch_bwd(const float *gout, const float *img, const float *df, float *gimg, float *gdf,
                       const float *reg_gloss, float reg_k, bool reg, int B, int C, int D0, int D1, int D2,
                       cudaStream_t st)
 {
     WarpGeom g;
-    int rc = make_geom(g, B, C, D0, D1, D2, VEC);
+    int rc = make_geom(g, B, C, D0, D1, D2);
     if (rc != PULPO_OK) return rc;
-    const unsigned int grid = (g.groups + 255) / 256;
+    const unsigned int grid = persistent_grid(g.items, 2);
     if (gimg && reg)
-        warp3d_bwd_kernel<MODE, VEC, true, true><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, reg_gloss, reg_k, g);
+        warp3d_bwd_kernel<MODE, true, true><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, reg_gloss, reg_k, g);
     else if (gimg)
-        warp3d_bwd_kernel<MODE, VEC, true, false><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, nullptr, 0.0f, g);
+        warp3d_bwd_kernel<MODE, true, false><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, nullptr, 0.0f, g);
     else if (reg)
-        warp3d_bwd_kernel<MODE, VEC, false, true><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, reg_gloss, reg_k, g);
+        warp3d_bwd_kernel<MODE, false, true><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, reg_gloss, reg_k, g);
     else
-        warp3d_bwd_kernel<MODE, VEC, false, false><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, nullptr, 0.0f, g);
+        warp3d_bwd_kernel<MODE, false, false><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, nullptr, 0.0f, g);
     return launch_status();
 }
 
 static int warp_fwd_dispatch(const float *img, const float *df, float *out, int32_t *idx, float *reg_out, void *ws,
                              double reg_scale, int B, int C, int D0, int D1, int D2, int coord_mode, cudaStream_t st)
 {
-    bool v4 = (D2 % 4 == 0) && aligned16(df) && aligned16(out);
     ReduceWs *w = (ReduceWs *)ws;
     if (coord_mode == PULPO_COORD_CPU_EXACT)
-        return v4 ? launch_fwd<0, 4>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, st)
-                  : launch_fwd<0, 1>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, st);
-    return v4 ? launch_fwd<1, 4>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, st)
-              : launch_fwd<1, 1>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, st);
+        return launch_fwd<0>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, st);
+    return launch_fwd<1>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, st);
 }
 
 static int warp_bwd_dispatch(const float *gout, const float *img, const float *df, float *gimg, float *gdf,
                              const float *reg_gloss, float reg_k, bool reg, int B, int C, int D0, int D1, int D2,
                              int coord_mode, cudaStream_t st)
 {
-    bool v4 = (D2 % 4 == 0) && aligned16(df) && aligned16(gout) && (!gdf || aligned16(gdf));
     if (coord_mode == PULPO_COORD_CPU_EXACT)
-        return v4 ? launch_bwd<0, 4>(gout, img, df, gimg, gdf, reg_gloss, reg_k, reg, B, C, D0, D1, D2, st)
-                  : launch_bwd<0, 1>(gout, img, df, gimg, gdf, reg_gloss, reg_k, reg, B, C, D0, D1, D2, st);
-    return v4 ? launch_bwd<1, 4>(gout, img, df, gimg, gdf, reg_gloss, reg_k, reg, B, C, D0, D1, D2, st)
-              : launch_bwd<1, 1>(gout, img, df, gimg, gdf, reg_gloss, reg_k, reg, B, C, D0, D1, D2, st);
+        return launch_bwd<0>(gout, img, df, gimg, gdf, reg_gloss, reg_k, reg, B, C, D0, D1, D2, st);
+    return launch_bwd<1>(gout, img, df, gimg, gdf, reg_gloss, reg_k, reg, B, C, D0, D1, D2, st);
 }
 
 static double l2reg_scale(float lamb, int B, int D0, int D1, int D2)

@@ -540,3 +540,32 @@ def test_mc_uncertainty_hot_path_matches_stacked_reference_semantics(PF):
     m_std = torch.stack(moveds).std(dim=0).mean(dim=0)
     assert_close(res["final0"].std_channel_mean().cpu().numpy(), f_std.numpy(), FIELD_ATOL, "final df std")
     assert_close(res["moved0"].variance_map().cpu().numpy(), (m_std ** 2).numpy(), FIELD_ATOL, "variance map")
+
+
+def test_pipeline_matches_plan_across_slots(PF):
+    """HotPathPipeline (packed pinned inputs, copy stream, graph per slot): every ticket returns the loss
+    the plan computes for that step's inputs, also when slots are reused and results are read late."""
+    from pulpo_b200 import synthetic as syn
+    from pulpo_b200.pipeline import HotPathPipeline
+    size, total, latent = [32, 32, 32], 4, 3
+    pipe = HotPathPipeline(size, total, latent)
+    inputs = [syn.make_hot_path_inputs(size, total, latent, seed=s) for s in range(5)]
+    hbs = [pipe.host_batch().fill(*inp) for inp in inputs]
+    ref = []
+    for inp in inputs:
+        x, y, dfs, mus, sgs = inp
+        plan = _run_plan((x.cuda(), y.cuda(), {l: dfs[l].cuda() for l in dfs}, {l: mus[l].cuda() for l in dfs},
+                          {l: sgs[l].cuda() for l in dfs}), total, latent, size, 1, True, False)
+        ref.append((plan.total.item(), plan.losses.sum(dim=1).cpu().numpy()))
+    tickets, got = [], {}
+    for k, hb in enumerate(hbs):
+        tickets.append(pipe.submit(hb))
+        if k >= 1:
+            got[k - 1] = pipe.result(tickets[k - 1])
+    got[len(hbs) - 1] = pipe.result(tickets[-1])
+    for k in range(len(hbs)):
+        assert_loss_close(got[k][0], ref[k][0], "pipeline total %d" % k)
+        for j in range(3):
+            assert_loss_close(got[k][1 + j], ref[k][1][j], "pipeline part %d/%d" % (k, j))
+    with pytest.raises(RuntimeError):
+        pipe.result(tickets[0])       # slot long reused
