@@ -135,6 +135,36 @@ def cpu_baseline(budget_s, steps=1, warmup=0, want_workload=None):
                       % (steps, name, torch.__version__, cores, tot / steps)}, tot / steps, name
 
 
+def torch_cuda_baseline(dev, inputs, total_levels, steps=3):
+    """Context row: the same reference restatement (the ATen ops the reference calls) on THIS GPU through
+    stock PyTorch eager CUDA kernels, TF32 off -- "what you get by moving the reference to a B200"."""
+    import torch
+    from oracle import torch_ref as T
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        x, y, dfs, mus, sgs = inputs
+        x, y = x.to(dev), y.to(dev)
+
+        def one():
+            d = {l: dfs[l].to(dev).requires_grad_(True) for l in dfs}
+            m = {l: mus[l].to(dev).requires_grad_(True) for l in dfs}
+            s = {l: sgs[l].to(dev).requires_grad_(True) for l in dfs}
+            loss, _, _ = T.hot_path_losses(x, y, d, m, s, total_levels)
+            loss.backward()
+        one()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / steps
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -365,8 +395,22 @@ def run_ours(args):
     (dname, dbytes), dg = max(shapes.items(), key=lambda kv: kv[1]["ms"])
     d_ms = dg["ms"] / dg["n"]
     achieved = dbytes / (d_ms * 1e-3) / 1e9
+    # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture of this same command
+    # (profiles/<tag>_traffic.json, written by scripts/summarize_ncu_full.py); None when no capture is committed
+    traffic, traffic_src = None, None
+    kmap = {"pulpo_vecint_multi_bwd": "vecint_bwd_kernel<0, 2>", "pulpo_vecint_multi_fwd": "vecint_fwd_kernel<0>",
+            "pulpo_warp3d_l2reg_bwd": "warp3d_bwd_kernel<0, 0, 1>", "pulpo_warp3d_l2reg_fwd": "warp3d_fwd_kernel<0, 0, 1>",
+            "pulpo_ncc_fwd": "ncc_tma_kernel<9, 1>", "pulpo_ncc_bwd": "ncc_tma_kernel<9, 0>"}
+    try:
+        import glob
+        for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
+            tj = json.load(open(path))
+            if kmap.get(dname) in tj:
+                traffic, traffic_src = tj[kmap[dname]]["dram_bytes_per_launch"], os.path.relpath(path, ROOT)
+    except Exception:
+        pass
     roofline = {"kernel": dname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "bytes_per_launch": dbytes, "us_per_launch": d_ms * 1e3, "launches_timed": dg["n"],
                 "share_of_step": dg["ms"] / sum(v["ms"] for v in agg.values()),
                 "note": "launch shape with the largest share of the step; algorithmic bytes (SURVEY.md 8d) / mean CUDA-event duration"}
@@ -399,6 +443,14 @@ def run_ours(args):
         }
         if cb is not None:
             line["cpu_baseline"] = cb
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                ms_t = torch_cuda_baseline(dev, (x_h, y_h, d_h, m_h, s_h), total)
+                line["torch_cuda_baseline"] = {"value": B * nvox / (ms_t * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_t,
+                                               "what": "reference restatement (oracle/torch_ref.py) on stock PyTorch %s CUDA "
+                                                       "kernels on this GPU, fp32, TF32 off; context only" % torch.__version__}
+            except Exception as e:  # pragma: no cover
+                line["torch_cuda_baseline"] = {"value": None, "what": "failed: %r" % (e,)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -266,6 +266,13 @@ __device__ __forceinline__ float4 ld_stream4(const float *p)
     return r;
 }
 
+__device__ __forceinline__ float ld_stream(const float *p)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
 // sm_90+ vector reduction: one 16-byte red instead of four scalar atomics
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
 {

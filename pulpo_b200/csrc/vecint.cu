@@ -30,7 +30,12 @@ namespace cg = cooperative_groups;
 
 namespace pulpo {
 
-constexpr int VI_PX = 8, VI_PY = 4;   // lanes of a warp: 8 along x, 4 along y
+#ifndef PULPO_VI_PX
+#define PULPO_VI_PX 8
+#endif
+constexpr int VI_PX = PULPO_VI_PX, VI_PY = 32 / VI_PX;   // lanes of a warp: VI_PX along x, VI_PY along y
+constexpr int VI_PX_LOG2 = VI_PX == 8 ? 3 : VI_PX == 16 ? 4 : 5;
+static_assert(VI_PX == 8 || VI_PX == 16 || VI_PX == 32, "patch width");
 // One CTA per SM: a CTA that reaches grid.sync() early polls the barrier with acquire loads,
 // and every poll invalidates that SM's L1 (CCTL.IVALL) -- with several CTAs per SM this slowed
 // the CTAs still working next to it.  With one CTA per SM nobody is left to disturb.
@@ -106,7 +111,7 @@ __device__ __forceinline__ Item decode_item(unsigned int it, const VGeom &g, int
     t.z0 = (int)zr * g.zrun;
     t.z1 = min(g.D0, t.z0 + g.zrun);
     t.x = (int)px * VI_PX + (lane & (VI_PX - 1));
-    t.y = (int)py * VI_PY + (lane >> 3);
+    t.y = (int)py * VI_PY + (lane >> VI_PX_LOG2);
     t.valid = (t.x < g.D2) && (t.y < g.D1);
     return t;
 }
@@ -273,6 +278,18 @@ vecint_fwd_kernel(const VMulti m, int nsteps, int save, float scale)
     }
 }
 
+#ifdef PULPO_VI_TRACE
+// tuning builds only: per-CTA (step start, work done) timestamps of the backward, read back by
+// pulpo_debug_vi_trace() to look at load balance across SMs
+__device__ unsigned long long g_vi_trace[148 * 64];
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 struct F3 {
     float x, y, z;
 };
@@ -305,7 +322,7 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
 {
     cg::grid_group grid = cg::this_grid();
     const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31, lx = lane & (VI_PX - 1), ly = lane >> 3;
+    const int lane = threadIdx.x & 31, lx = lane & (VI_PX - 1), ly = lane >> VI_PX_LOG2;
     const unsigned int warp = tid >> 5, nwarps = nthr >> 5;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     constexpr int NOADDR = NOBASE;
@@ -326,6 +343,9 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
     int flip = 0;   // which (P, Y) pair holds the incoming gradient of the current step
     for (int k = nsteps - 1; k >= 0; --k, flip ^= 1) {
         grid.sync();
+#ifdef PULPO_VI_TRACE
+        if (threadIdx.x == 0 && blockIdx.x < 148 && k < 32) g_vi_trace[blockIdx.x * 64 + 2 * k] = gtime();
+#endif
         for (unsigned int it = warp; it < m.items; it += nwarps) {   // warp-uniform loop: all lanes shuffle
             int lv = 0;
 #pragma unroll
@@ -481,6 +501,10 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
                 red3(q, up[0]); red3(q + 1, up[1]); red3(q + sy, up[2]); red3(q + sy + 1, up[3]);
             }
         }
+#ifdef PULPO_VI_TRACE
+        __syncthreads();
+        if (threadIdx.x == 0 && blockIdx.x < 148 && k < 32) g_vi_trace[blockIdx.x * 64 + 2 * k + 1] = gtime();
+#endif
     }
     grid.sync();
     for (int lv = 0; lv < m.n; ++lv) {
@@ -583,6 +607,13 @@ static int fill_levels(VMulti &m, const pulpo_vecint_level *levels, int nlevels,
 }  // namespace pulpo
 
 using namespace pulpo;
+
+#ifdef PULPO_VI_TRACE
+extern "C" int pulpo_debug_vi_trace(unsigned long long *host_out)
+{
+    return cudaMemcpyFromSymbol(host_out, g_vi_trace, sizeof(unsigned long long) * 148 * 64) == cudaSuccess ? 0 : -5;
+}
+#endif
 
 extern "C" size_t pulpo_vecint_ws_bytes(int nsteps, int save_steps, int B, int D0, int D1, int D2)
 {

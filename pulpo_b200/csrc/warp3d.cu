@@ -22,7 +22,16 @@ namespace pulpo {
 // gather over 4 lines: 2.3 pipe cycles per voxel against 1.0 now).  WR rows per thread keep
 // several independent gathers in flight and let the fused regulariser take its y neighbours from
 // registers and its x neighbours from warp shuffles.
-constexpr int WR = 4;
+#ifndef PULPO_WARP_WR
+#define PULPO_WARP_WR 4
+#endif
+#ifndef PULPO_WARP_FWD_CTAS
+#define PULPO_WARP_FWD_CTAS 3
+#endif
+#ifndef PULPO_WARP_BWD_CTAS
+#define PULPO_WARP_BWD_CTAS 2
+#endif
+constexpr int WR = PULPO_WARP_WR;
 
 struct WarpGeom {
     int B, C, D0, D1, D2, S;
@@ -116,11 +125,14 @@ __device__ __forceinline__ WItem decode_witem(unsigned int w, int lane, const Wa
     return t;
 }
 
-// the WR values of one field channel this thread owns (0 outside the volume)
+// the WR values of one field channel this thread owns (0 outside the volume).  STREAM: read-once data
+// (field without the fused regulariser, upstream gradient) bypasses L1 so that it does not evict the
+// image lines the corner gathers live on.
+template <bool STREAM>
 __device__ __forceinline__ void load_rows(const float *f, int sy, const bool (&ok)[WR], float (&v)[WR])
 {
 #pragma unroll
-    for (int j = 0; j < WR; ++j) v[j] = ok[j] ? __ldg(f + j * sy) : 0.0f;
+    for (int j = 0; j < WR; ++j) v[j] = ok[j] ? (STREAM ? ld_stream(f + j * sy) : __ldg(f + j * sy)) : 0.0f;
 }
 
 // L2_reg of one field channel at the WR voxels this thread owns (forward differences on the
@@ -164,7 +176,7 @@ __device__ __forceinline__ float l2_fwd_terms(const float *f, const float (&c)[W
 }
 
 template <int MODE, bool IDX, bool REG>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, PULPO_WARP_FWD_CTAS)
 warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, float *__restrict__ out,
                   int32_t *__restrict__ idx, float *reg_out, ReduceWs *ws, double reg_scale, const WarpGeom g)
 {
@@ -182,9 +194,9 @@ warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, f
         for (int j = 0; j < WR; ++j) ok[j] = t.xok && (t.y0 + j < g.D1);
         const float *f = df + (i64)t.b * 3 * S + v0;
         float dz[WR], dy[WR], dx[WR];
-        load_rows(f, sy, ok, dz);
-        load_rows(f + S, sy, ok, dy);
-        load_rows(f + 2 * S, sy, ok, dx);
+        load_rows<!REG>(f, sy, ok, dz);
+        load_rows<!REG>(f + S, sy, ok, dy);
+        load_rows<!REG>(f + 2 * S, sy, ok, dx);
         if (REG) {
             const bool inner = t.z > 0 && t.y0 > 0 && t.y0 + WR <= g.D1 && __all_sync(0xffffffffu, t.xok);
             reg_acc += l2_fwd_terms(f, dz, ok, t, lane, sy, sz, inner) + l2_fwd_terms(f + S, dy, ok, t, lane, sy, sz, inner) +
@@ -272,7 +284,7 @@ __device__ __forceinline__ void l2_bwd_terms(const float *f, const float (&c)[WR
 // Backward: gather half (gdf) always, scatter half (gimg) only when requested.  REG adds the
 // gradient of the fused L2_reg term to gdf.
 template <int MODE, bool SCATTER, bool REG>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, PULPO_WARP_BWD_CTAS)
 warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ df,
                   float *__restrict__ gimg, float *__restrict__ gdf, const float *__restrict__ reg_gloss,
                   float reg_k, const WarpGeom g)
@@ -289,9 +301,9 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
     for (int j = 0; j < WR; ++j) ok[j] = t.xok && (t.y0 + j < g.D1);
     const float *f = df + (i64)t.b * 3 * S + v0;
     float dz[WR], dy[WR], dx[WR];
-    load_rows(f, sy, ok, dz);
-    load_rows(f + S, sy, ok, dy);
-    load_rows(f + 2 * S, sy, ok, dx);
+    load_rows<!REG>(f, sy, ok, dz);
+    load_rows<!REG>(f + S, sy, ok, dy);
+    load_rows<!REG>(f + 2 * S, sy, ok, dx);
     const float zf = (float)t.z, xf = (float)t.x;
     // autograd chain of 2*(loc/(S-1)-0.5) after the sampler's S/2:  (m*g*2)/(S-1)
     const float kz = 2.0f * g.a0.rcp, ky = 2.0f * g.a1.rcp, kx = 2.0f * g.a2.rcp;
@@ -311,7 +323,7 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
     for (int c = 0; c < g.C; ++c) {
         const i64 off = ((i64)t.b * g.C + c) * S;
         float go[WR];
-        load_rows(gout + off + v0, sy, ok, go);
+        load_rows<true>(gout + off + v0, sy, ok, go);
 #pragma unroll
         for (int j = 0; j < WR; ++j) {
             if (!ok[j]) continue;
@@ -392,7 +404,7 @@ static int launch_fwd(const float *img, const float *df, float *out, int32_t *id
     WarpGeom g;
     int rc = make_geom(g, B, C, D0, D1, D2);
     if (rc != PULPO_OK) return rc;
-    const unsigned int grid = persistent_grid(g.items, 3);
+    const unsigned int grid = persistent_grid(g.items, PULPO_WARP_FWD_CTAS);
     if (idx)
         warp3d_fwd_kernel<MODE, true, false><<<grid, 256, 0, st>>>(img, df, out, idx, nullptr, nullptr, 0.0, g);
     else if (reg_out)
@@ -410,7 +422,7 @@ static int launch_bwd(const float *gout, const float *img, const float *df, floa
     WarpGeom g;
     int rc = make_geom(g, B, C, D0, D1, D2);
     if (rc != PULPO_OK) return rc;
-    const unsigned int grid = persistent_grid(g.items, 2);
+    const unsigned int grid = persistent_grid(g.items, PULPO_WARP_BWD_CTAS);
     if (gimg && reg)
         warp3d_bwd_kernel<MODE, true, true><<<grid, 256, 0, st>>>(gout, img, df, gimg, gdf, reg_gloss, reg_k, g);
     else if (gimg)

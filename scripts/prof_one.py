@@ -30,7 +30,7 @@ def main():
             o = PF.vecint(v, nsteps, mode)
         elif op == "warp":
             v = f.clone().requires_grad_(True)
-            o = PF.warp(v, x)
+            o = PF.warp(v, x, mode & 1)
         elif op == "ncc":
             v = x.clone().requires_grad_(True)
             o = PF.ncc_loss(v, y, win, 0.05)
