@@ -569,3 +569,67 @@ def test_pipeline_matches_plan_across_slots(PF):
             assert_loss_close(got[k][1 + j], ref[k][1][j], "pipeline part %d/%d" % (k, j))
     with pytest.raises(RuntimeError):
         pipe.result(tickets[0])       # slot long reused
+
+
+# ----------------------------------------------------------------------------- BASELINE full sizes (configs 2, 4, 5)
+@pytest.mark.parametrize("shape", [(160, 192, 224)])
+def test_vecint_full_resolution_equals_iterated_warp_config4(PF, shape):
+    """Config 4 (7-step scaling-and-squaring at full 160x192x224): the cooperative VecInt kernel against
+    seven launches of the independent warp kernel (v <- v + warp(v, v), network_blocks.py:173-177).  Both
+    follow the CPU sampler op by op, so the forward must agree bit for bit; the backward (VecInt's
+    own/scatter ping-pong vs autograd through 7 warp backward launches with their atomics) within the
+    gradient tolerance."""
+    from pulpo_b200 import synthetic as syn
+    v = syn.make_field(shape, 21, max_abs=3.0).cuda()
+    g = syn.make_field(shape, 22, max_abs=1.0).cuda()
+    a = v.clone().requires_grad_(True)
+    out = PF.vecint(a, 7, PF.CPU_EXACT)
+    out.backward(g)
+    b = v.clone().requires_grad_(True)
+    w = b * (1.0 / 128.0)
+    for _ in range(7):
+        w = w + PF.warp(w, w, PF.CPU_EXACT)
+    assert torch.equal(out.detach(), w.detach()), "max-abs %.3e" % float((out.detach() - w.detach()).abs().max())
+    w.backward(g)
+    assert_grad_close(a.grad.cpu().numpy(), b.grad.cpu().numpy(), "vecint full-res gvec")
+
+
+def test_warp_full_size_properties_config2(PF):
+    """Config-2 size: identity up to the reference's S/(S-1) - 0.5 convention is hard to state, so use
+    exact properties: a constant image is reproduced exactly for any field (weights sum to 1 only up to
+    rounding -> tolerance), integer sampling indices stay inside the volume, and warping a 3-channel image
+    equals warping its channels one by one (bitwise)."""
+    from pulpo_b200 import synthetic as syn
+    shape = (160, 192, 224)
+    df = (syn.make_field(shape, 31, max_abs=40.0)).cuda()
+    const = torch.full((1, 1) + shape, 0.625, device="cuda")
+    out, idx = PF.warp_indices(df, const)
+    assert float((out - 0.625).abs().max()) <= 1e-6
+    for a, s in enumerate(shape):
+        assert int(idx[:, a].min()) >= 0 and int(idx[:, a].max()) <= s - 1
+    img3 = torch.rand((1, 3) + shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    w3 = PF.warp(df, img3)
+    for c in range(3):
+        assert torch.equal(w3[:, c:c + 1], PF.warp(df, img3[:, c:c + 1].contiguous()))
+
+
+def test_plan_batch_equals_per_pair_means_config5(PF):
+    """Config 5 shards a batch over ranks; every loss term is a batch mean (losses.py:64,134,222), so a
+    B=3 step must equal the mean of three B=1 steps, and each pair's gradients are 1/3 of its own."""
+    from pulpo_b200 import synthetic as syn
+    size, total, latent, B = [32, 32, 32], 4, 3, 3
+    x, y, dfs, mus, sgs = syn.make_hot_path_inputs(size, total, latent, seed=4, batch=B)
+    cu = lambda t: t.cuda()
+    big = _run_plan((cu(x), cu(y), {l: cu(dfs[l]) for l in dfs}, {l: cu(mus[l]) for l in dfs}, {l: cu(sgs[l]) for l in dfs}),
+                    total, latent, size, B, True, False)
+    tot, gd = 0.0, {l: [] for l in dfs}
+    for b in range(B):
+        sl = lambda t: t[b:b + 1].contiguous().cuda()
+        one = _run_plan((sl(x), sl(y), {l: sl(dfs[l]) for l in dfs}, {l: sl(mus[l]) for l in dfs},
+                         {l: sl(sgs[l]) for l in dfs}), total, latent, size, 1, True, False)
+        tot += one.total.item() / B
+        for l in dfs:
+            gd[l].append(one.gdf[l].clone() / B)
+    assert_loss_close(big.total.item(), tot, "batch total")
+    for l in dfs:
+        assert_grad_close(big.gdf[l].cpu().numpy(), torch.cat(gd[l]).cpu().numpy(), "batch gdf %d" % l)
