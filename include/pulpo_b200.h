@@ -158,6 +158,24 @@ int pulpo_l2reg_fwd(const float *f, float lamb, float *out, void *ws, size_t ws_
 int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, float *gf, int accumulate,
                     int B, int C, int D0, int D1, int D2, pulpo_stream_t stream);
 
+/* ---- f-2: jacobian_det(deformation_field, normalize) / JDetStd   src/losses.py:147-204 (3-D branch) ----
+ * det: [B,D0,D1,D2] (the reference returns jacobian[:,0,0]-shaped maps).  Replication-padded central
+ * differences of the channel-flipped field scaled as the reference scales it (see csrc/jacdet.cu). */
+int pulpo_jacdet_fwd(const float *df, float *det, int normalize, int B, int D0, int D1, int D2,
+                     pulpo_stream_t stream);
+/* gdf = (d det / d df)^T gdet; ws: 9 upstream-weighted cofactor planes. */
+size_t pulpo_jacdet_bwd_ws_bytes(int B, int D0, int D1, int D2);
+int pulpo_jacdet_bwd(const float *gdet, const float *df, float *gdf, void *ws, size_t ws_bytes,
+                     int normalize, int B, int D0, int D1, int D2, pulpo_stream_t stream);
+/* out = lamb * x.std() (unbiased, over all n elements; JDetStd, src/losses.py:202-204).  ws
+ * (pulpo_std_ws_bytes, zeroed once by the caller) keeps mean and std for the backward:
+ * gx = gloss * lamb * (x - mean) / ((n-1) * std);  gloss: device scalar, nullable = 1. */
+size_t pulpo_std_ws_bytes(void);
+int pulpo_std_fwd(const float *x, float lamb, float *out, void *ws, size_t ws_bytes, long long n,
+                  pulpo_stream_t stream);
+int pulpo_std_bwd(const float *gloss, const float *x, const void *ws, float lamb, float *gx,
+                  long long n, pulpo_stream_t stream);
+
 /* ---- f-3: per-voxel MC moments   evaluate.py:243-251 (std over samples) -------------------
  * Streaming Welford update of (mean, M2) with one new sample x (count = samples so far,
  * including this one), Chan merge of two partial states, and the unbiased std. */

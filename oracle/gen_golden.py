@@ -200,5 +200,29 @@ def main():
     _save("combine_dfs", input_size=np.asarray(input_size), **arrs)
 
 
+def gen_jacdet():
+    """jacobian_det / JDetStd (src/losses.py:147-204): determinant maps with and without normalisation,
+    the std regulariser and its autograd gradient; a large-displacement case folds (det <= 0 somewhere)."""
+    torch.set_num_threads(1)
+    nb, ls, cp, md = ref_import.load()
+    arrs = {}
+    for tag, shape, B, amp in [("a", (9, 11, 13), 2, 3.0), ("b", (6, 7, 5), 1, 9.0)]:
+        df = syn.make_field(shape, 40 + len(tag) + B, batch=B, max_abs=amp)
+        d = df.clone().requires_grad_(True)
+        det = ls.jacobian_det(d, normalize=True)
+        loss = ls.JDetStd(d, lamb=0.7, normalize=True)
+        loss.backward()
+        gout = _randn(det.shape, 8)
+        d2 = df.clone().requires_grad_(True)
+        ls.jacobian_det(d2, normalize=False).backward(gout)
+        arrs.update({"df_" + tag: df, "det_" + tag: det, "det_nonorm_" + tag: ls.jacobian_det(df, normalize=False),
+                     "jdetstd_" + tag: loss, "gdf_std_" + tag: d.grad, "gout_" + tag: gout, "gdf_nonorm_" + tag: d2.grad})
+    _save("jacdet", **arrs)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "jacdet":
+        gen_jacdet()
+    else:
+        main()
+        gen_jacdet()

@@ -51,6 +51,12 @@ SIGNATURES = {
     "pulpo_kl_diag_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _ll, _vp]),
     "pulpo_l2reg_fwd": (_i, [_vp, _f, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "pulpo_l2reg_bwd": (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_jacdet_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_jacdet_bwd_ws_bytes": (_sz, [_i, _i, _i, _i]),
+    "pulpo_jacdet_bwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_std_ws_bytes": (_sz, []),
+    "pulpo_std_fwd": (_i, [_vp, _f, _vp, _vp, _sz, _ll, _vp]),
+    "pulpo_std_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _ll, _vp]),
     "pulpo_moments_update": (_i, [_vp, _vp, _vp, _i, _ll, _vp]),
     "pulpo_moments_merge": (_i, [_vp, _vp, _i, _vp, _vp, _i, _ll, _vp]),
     "pulpo_moments_std": (_i, [_vp, _vp, _i, _ll, _vp]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libpulpo_b200.so")
-SOURCES = ["warp3d.cu", "vecint.cu", "resize.cu", "ncc.cu", "ncc_tma.cu", "losses.cu"]
+SOURCES = ["warp3d.cu", "vecint.cu", "resize.cu", "ncc.cu", "ncc_tma.cu", "losses.cu", "jacdet.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--use_fast_math=false",

@@ -328,6 +328,67 @@ def l2_reg(deformation_field, lamb=0.0):
     return _L2Reg.apply(deformation_field, lamb)
 
 
+# ----------------------------------------------------------------------------- Jacobian determinant (f-2)
+class _JacDet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, df, normalize):
+        df = _prep(df, "deformation_field")
+        B, C, D0, D1, D2 = _dims5(df, "deformation_field")
+        if C != 3:
+            raise RuntimeError("pulpo_b200: jacobian_det expects a 3-channel field, got C=%d" % C)
+        det = torch.empty((B, D0, D1, D2), dtype=torch.float32, device=df.device)
+        check(_lib.lib().pulpo_jacdet_fwd(_ptr(df), _ptr(det), int(bool(normalize)), B, D0, D1, D2, _stream()),
+              "jacdet_fwd")
+        ctx.normalize = int(bool(normalize))
+        ctx.save_for_backward(df)
+        return det
+
+    @staticmethod
+    def backward(ctx, gdet):
+        (df,) = ctx.saved_tensors
+        gdet = _prep(gdet, "grad_output")
+        B, C, D0, D1, D2 = df.shape
+        L = _lib.lib()
+        nbytes = L.pulpo_jacdet_bwd_ws_bytes(B, D0, D1, D2)
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=df.device)
+        gdf = torch.empty_like(df)
+        check(L.pulpo_jacdet_bwd(_ptr(gdet), _ptr(df), _ptr(gdf), _ptr(ws), nbytes, ctx.normalize, B, D0, D1, D2,
+                                 _stream()), "jacdet_bwd")
+        return gdf, None
+
+
+def jacobian_det(deformation_field, normalize=True):
+    """jacobian_det (src/losses.py:147-199), 3-D branch: [B,3,D,H,W] -> [B,D,H,W]."""
+    return _JacDet.apply(deformation_field, normalize)
+
+
+class _Std(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, lamb):
+        x = _prep(x, "x")
+        L = _lib.lib()
+        ws = torch.zeros(L.pulpo_std_ws_bytes(), dtype=torch.uint8, device=x.device)   # holds mean/std for backward
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        check(L.pulpo_std_fwd(_ptr(x), float(lamb), _ptr(out), _ptr(ws), ws.numel(), x.numel(), _stream()), "std_fwd")
+        ctx.lamb = float(lamb)
+        ctx.save_for_backward(x, ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, gloss):
+        x, ws = ctx.saved_tensors
+        gloss = gloss.to(torch.float32).contiguous()
+        gx = torch.empty_like(x)
+        check(_lib.lib().pulpo_std_bwd(_ptr(gloss), _ptr(x), _ptr(ws), ctx.lamb, _ptr(gx), x.numel(), _stream()),
+              "std_bwd")
+        return gx, None
+
+
+def jdet_std(deformation_field, lamb=0.0, normalize=True):
+    """JDetStd (src/losses.py:202-204): lamb * jacobian_det(field).std() (unbiased, all elements)."""
+    return _Std.apply(jacobian_det(deformation_field, normalize), lamb)
+
+
 # ----------------------------------------------------------------------------- MC moments (f-3)
 def moments_update(x, mean, m2, count):
     """Welford update of per-voxel (mean, M2) with sample x; count includes x."""

@@ -6,10 +6,11 @@
     HierarchicalKLLoss              <- src/losses.py:225-276
     HierarchicalReconstructionLoss  <- src/losses.py:279-325
     HierarchicalRegularization      <- src/losses.py:327-355
+    jacobian_det / JDetStd          <- src/losses.py:147-204
 
 Same names, arguments, return types ((total, {level: loss}) tuples) and quirks (the KL
 argument-order swap at :271-273, weight_dict mutated in place by similarity_pyramid, division
-by len(recon_loss)).  "mse" / "dice" / KL_nondiagonal / JDetStd are outside this path
+by len(recon_loss)).  "mse" / "dice" / KL_nondiagonal are outside this path
  and raise NotImplementedError.
 """
 from __future__ import annotations
@@ -39,6 +40,20 @@ def L2_reg(deformation_field: torch.Tensor, lamb=0) -> torch.Tensor:
     if deformation_field.dim() != 5:
         raise NotImplementedError("pulpo_b200.L2_reg: only 3-D fields are implemented")
     return PF.l2_reg(deformation_field, lamb)
+
+
+def jacobian_det(deformation_field: torch.Tensor, lamb=None, normalize=True) -> torch.Tensor:
+    """Jacobian determinant map of a displacement field, [B,3,D,H,W] -> [B,D,H,W] (reference :147-199)."""
+    if deformation_field.dim() != 5:
+        raise NotImplementedError("pulpo_b200.jacobian_det: only 3-D fields are implemented")
+    return PF.jacobian_det(deformation_field, normalize)
+
+
+def JDetStd(deformation_field: torch.Tensor, lamb=0, normalize=True) -> torch.Tensor:
+    """The standard deviation of the Jacobian determinant as a regularization loss (reference :202-204)."""
+    if deformation_field.dim() != 5:
+        raise NotImplementedError("pulpo_b200.JDetStd: only 3-D fields are implemented")
+    return PF.jdet_std(deformation_field, lamb, normalize)
 
 
 class HierarchicalKLLoss(nn.Module):

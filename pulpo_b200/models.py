@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from . import functional as PF
 from .components.pulpo import PULPoPrior, SVFDecoder, moving_pyramid
-from .losses import (HierarchicalKLLoss, HierarchicalReconstructionLoss, HierarchicalRegularization,
+from .losses import (HierarchicalKLLoss, HierarchicalReconstructionLoss, HierarchicalRegularization, JDetStd,
                      KL_two_gauss_with_diag_cov, L2_reg)
 from .synthetic import level_sizes
 
@@ -74,7 +74,7 @@ class RegistrationHotPath(nn.Module):
     VelocityField conv output, ``mus`` / ``sigmas`` for the encoder's posterior."""
 
     def __init__(self, input_size, total_levels, latent_levels, beta=0.1, gamma=0.05, lamb=0.025,
-                 df_resolution="level_res", similarity_pyramid=False, with_reg=True):
+                 df_resolution="level_res", similarity_pyramid=False, with_reg=True, regularizer="l2"):
         super().__init__()
         self.input_size = [int(s) for s in input_size]
         self.total_levels, self.latent_levels = total_levels, latent_levels
@@ -92,7 +92,10 @@ class RegistrationHotPath(nn.Module):
         self.prior = PULPoPrior()
         self.hierarchical_kl_loss = HierarchicalKLLoss(KL_two_gauss_with_diag_cov, kl_w, similarity_pyramid)
         self.hierarchical_recon_loss = HierarchicalReconstructionLoss(["ncc"], rec_w, similarity_pyramid, 3, win)
-        self.hierarchical_regularization = HierarchicalRegularization(L2_reg, reg_w, similarity_pyramid)
+        if regularizer not in ("l2", "jdet"):      # PULPo.__init__, src/models.py:94-99
+            raise ValueError("regularizer must be 'l2' or 'jdet', got %r" % (regularizer,))
+        self.hierarchical_regularization = HierarchicalRegularization(L2_reg if regularizer == "l2" else JDetStd, reg_w,
+                                                                      similarity_pyramid)
 
     def decode(self, x, velocity_fields):
         level_x = moving_pyramid(x, self.latent_levels, self.lk_offset, self.df_resolution)

@@ -113,3 +113,14 @@ def test_live_reference_when_present():
     assert np.array_equal(cport.vecint_fwd(df.numpy(), 7)[-1], ref_v.numpy())
     x, y = syn.make_pair((14, 15, 16), 44)
     assert_loss_close(cport.ncc(x.numpy(), y.numpy(), 5, 0.05), ls.NCC_loss(x, y, win_size=5).item(), "ncc live")
+
+
+def test_numpy_oracle_jacobian_det_matches_reference_fixture():
+    """f-2: jacobian_det / JDetStd restatement (oracle/jacdet_ref.py) against outputs of the live reference."""
+    from oracle import jacdet_ref as J
+    g = load_golden("jacdet")
+    for t in "ab":
+        assert np.array_equal(J.jacobian_det(g["df_" + t]), g["det_" + t])
+        assert np.array_equal(J.jacobian_det(g["df_" + t], normalize=False), g["det_nonorm_" + t])
+        assert abs(J.jdet_std(g["df_" + t], 0.7) - float(g["jdetstd_" + t])) <= 1e-6 * abs(float(g["jdetstd_" + t]))
+    assert (g["det_nonorm_b"] <= 0).any(), "fixture should contain folded voxels"
