@@ -252,6 +252,130 @@ up2_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gx, float sca
     *reinterpret_cast<float4 *>(o) = res;
 }
 
+// ---- x2 adjoint, z-marching version (the default for factor 2).
+// The 4x4x10 gather above reads every gradient row through L1 four times (two y and two z neighbours
+// need it) and is bound by the L1 pipe (81 % in ncu).  Here a warp owns 64 consecutive inputs along x
+// (two per lane) times two rows, and walks a run of input planes: every gradient plane is turned ONCE
+// into its x/y-adjoint T(oz) (six rows, one 128-bit load + two shuffles per row), and an input plane
+// is the z-adjoint of four consecutive T's, two of which are carried in registers from the previous
+// plane.  Gradient rows are read 1.5x instead of 4x, all loads are full cache lines.
+constexpr int UB_RY = 2;       // input rows per thread
+struct Up2MGeom {
+    int BC, d0, d1, d2;
+    int nxb, nyb, zrun, nzrun;
+    unsigned int items;
+    FastDiv dnxb, dnyb, dnz;
+};
+
+struct T4 {
+    float v[UB_RY][2];   // [row][x]
+};
+
+// the six gradient rows one plane contributes to this thread's 2 rows x 2 columns
+struct PlaneRaw {
+    float4 c[UB_RY + 4];              // gradients 2*x0 .. 2*x0+3 of rows 2*y0-1 .. 2*y0+4
+    float el[UB_RY + 4], er[UB_RY + 4];   // gradients 2*x0-1 / 2*x0+4 for the warp's edge lanes
+};
+
+// All loads of a plane are issued back to back (six independent 128-bit loads + the edge lanes'
+// scalars); the shuffles and the arithmetic come later (a load placed after a shuffle waits for it:
+// that version ran at 0.8 TB/s with one load in flight per warp).
+__device__ __forceinline__ void up2_plane_load(PlaneRaw &p, const float *__restrict__ plane, int o1, int o2, int y0, int x0,
+                                               bool xok, int lane)
+{
+    const bool need_l = (lane == 0) && xok && x0 > 0, need_r = (lane == 31) && xok && (2 * x0 + 4 < o2);
+#pragma unroll
+    for (int b = 0; b < UB_RY + 4; ++b) {
+        int oy = 2 * y0 - 1 + b;
+        oy = oy < 0 ? 0 : (oy > o1 - 1 ? o1 - 1 : oy);   // out-of-range rows carry weight 0
+        const float *row = plane + (i64)oy * o2;
+        p.c[b] = xok ? ld_stream4(row + 2 * x0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        p.el[b] = need_l ? __ldg(row + 2 * x0 - 1) : 0.0f;
+        p.er[b] = need_r ? __ldg(row + 2 * x0 + 4) : 0.0f;
+    }
+}
+
+// x/y adjoint of one gradient plane for this thread's 2 rows x 2 columns
+__device__ __forceinline__ T4 up2_plane_adjoint(const PlaneRaw &p, int lane, const float (&wx)[2][4],
+                                                const float (&wy)[UB_RY][4])
+{
+    float tx[UB_RY + 4][2];
+#pragma unroll
+    for (int b = 0; b < UB_RY + 4; ++b) {
+        float left = __shfl_up_sync(0xffffffffu, p.c[b].w, 1), right = __shfl_down_sync(0xffffffffu, p.c[b].x, 1);
+        if (lane == 0) left = p.el[b];
+        if (lane == 31) right = p.er[b];
+        tx[b][0] = wx[0][0] * left + wx[0][1] * p.c[b].x + wx[0][2] * p.c[b].y + wx[0][3] * p.c[b].z;
+        tx[b][1] = wx[1][0] * p.c[b].y + wx[1][1] * p.c[b].z + wx[1][2] * p.c[b].w + wx[1][3] * right;
+    }
+    T4 t;
+#pragma unroll
+    for (int r = 0; r < UB_RY; ++r)
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            t.v[r][q] = wy[r][0] * tx[2 * r][q] + wy[r][1] * tx[2 * r + 1][q] + wy[r][2] * tx[2 * r + 2][q] +
+                        wy[r][3] * tx[2 * r + 3][q];
+    return t;
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(256, 2)
+up2_bwd_march_kernel(const float *__restrict__ gout, float *__restrict__ gx, float scale, const Up2MGeom g)
+{
+    const unsigned int nwarps = gridDim.x * 8u;
+    const int lane = threadIdx.x & 31;
+    const int d0 = g.d0, d1 = g.d1, d2 = g.d2, o0 = 2 * d0, o1 = 2 * d1, o2 = 2 * d2;
+    const T4 zero = {{{0.f, 0.f}, {0.f, 0.f}}};
+    for (unsigned int w = (blockIdx.x * 256u + threadIdx.x) >> 5; w < g.items; w += nwarps) {
+        unsigned int r, xb, r2, yb, bc, zr;
+        fast_divmod(w, g.dnxb, r, xb);
+        fast_divmod(r, g.dnyb, r2, yb);
+        fast_divmod(r2, g.dnz, bc, zr);
+        const int x0 = ((int)xb * 32 + lane) * 2, y0 = (int)yb * UB_RY;
+        const bool xok = x0 < d2;                       // d2 is even: x0 + 1 < d2 as well
+        const int z0 = (int)zr * g.zrun, z1 = min(d0, z0 + g.zrun);
+        float wx[2][4], wy[UB_RY][4];
+        adj4(x0, d2, wx[0]);
+        adj4(x0 + 1, d2, wx[1]);
+#pragma unroll
+        for (int rr = 0; rr < UB_RY; ++rr) {
+            adj4(y0 + rr, d1, wy[rr]);
+            if (y0 + rr >= d1) wy[rr][0] = wy[rr][1] = wy[rr][2] = wy[rr][3] = 0.0f;
+        }
+        const float *gb = gout + (i64)bc * o0 * o1 * o2;
+        const i64 plane = (i64)o1 * o2;
+        // T(2z-1), T(2z) carried; T(2z+1), T(2z+2) computed per plane (both planes' loads in flight together)
+        PlaneRaw ra, rb;
+        if (z0 > 0) up2_plane_load(ra, gb + (i64)(2 * z0 - 1) * plane, o1, o2, y0, x0, xok, lane);
+        up2_plane_load(rb, gb + (i64)(2 * z0) * plane, o1, o2, y0, x0, xok, lane);
+        T4 ta = (z0 > 0) ? up2_plane_adjoint(ra, lane, wx, wy) : zero;
+        T4 tb = up2_plane_adjoint(rb, lane, wx, wy);
+        for (int z = z0; z < z1; ++z) {
+            up2_plane_load(ra, gb + (i64)(2 * z + 1) * plane, o1, o2, y0, x0, xok, lane);
+            if (z + 1 < d0) up2_plane_load(rb, gb + (i64)(2 * z + 2) * plane, o1, o2, y0, x0, xok, lane);
+            const T4 tc = up2_plane_adjoint(ra, lane, wx, wy);
+            const T4 td = (z + 1 < d0) ? up2_plane_adjoint(rb, lane, wx, wy) : zero;
+            float wz[4];
+            adj4(z, d0, wz);
+#pragma unroll
+            for (int rr = 0; rr < UB_RY; ++rr) {
+                if (!xok || y0 + rr >= d1) continue;
+                float2 res;
+                res.x = scale * (wz[0] * ta.v[rr][0] + wz[1] * tb.v[rr][0] + wz[2] * tc.v[rr][0] + wz[3] * td.v[rr][0]);
+                res.y = scale * (wz[0] * ta.v[rr][1] + wz[1] * tb.v[rr][1] + wz[2] * tc.v[rr][1] + wz[3] * td.v[rr][1]);
+                float2 *o = reinterpret_cast<float2 *>(gx + (((i64)bc * d0 + z) * d1 + y0 + rr) * d2 + x0);
+                if (ACC) {
+                    const float2 old = *o;
+                    res.x += old.x; res.y += old.y;
+                }
+                *o = res;
+            }
+            ta = tc;
+            tb = td;
+        }
+    }
+}
+
 // avg_pool3d(kernel 2, stride 2, pad 0, ceil_mode=True): clipped windows, divide by clipped count
 __global__ void __launch_bounds__(256)
 avgpool2_kernel(const float *__restrict__ in, float *__restrict__ out, int BC, int D0, int D1, int D2)
@@ -311,6 +435,32 @@ extern "C" int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, flo
     PULPO_REQUIRE(gout && gx, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && d0 > 0 && d1 > 0 && d2 > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(factor >= 2 && factor <= 64, PULPO_ERR_UNSUPPORTED);
+    if (factor == 2 && (d2 % 2 == 0) && aligned16(gout) && aligned16(gx) && d0 >= 2 &&
+        (i64)B * C * d0 * d1 * d2 * 8 < (1ll << 31) && !getenv("PULPO_UP2_BWD_OLD")) {
+        Up2MGeom g;
+        g.BC = B * C; g.d0 = d0; g.d1 = d1; g.d2 = d2;
+        g.nxb = (d2 / 2 + 31) / 32;
+        g.nyb = (d1 + UB_RY - 1) / UB_RY;
+        int dev = 0, sms = kSMs;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const i64 columns = (i64)g.BC * g.nyb * g.nxb;
+        i64 grid = (columns * d0 + 7) / 8;                 // CTAs if every warp took one plane
+        if (grid > (i64)sms * 2) grid = (i64)sms * 2;
+        if (grid < 1) grid = 1;
+        i64 per_col = (2 * grid * 8 + columns - 1) / columns;   // ~2 runs per resident warp
+        if (per_col < 1) per_col = 1;
+        if (per_col > d0) per_col = d0;
+        g.zrun = (int)((d0 + per_col - 1) / per_col);
+        g.nzrun = (d0 + g.zrun - 1) / g.zrun;
+        g.items = (unsigned int)(columns * g.nzrun);
+        g.dnxb = make_fastdiv(g.nxb); g.dnyb = make_fastdiv(g.nyb); g.dnz = make_fastdiv(g.nzrun);
+        if (accumulate)
+            up2_bwd_march_kernel<true><<<(unsigned int)grid, 256, 0, (cudaStream_t)stream>>>(gout, gx, scale, g);
+        else
+            up2_bwd_march_kernel<false><<<(unsigned int)grid, 256, 0, (cudaStream_t)stream>>>(gout, gx, scale, g);
+        return launch_status();
+    }
     if (factor == 2 && (d2 % 4 == 0) && aligned16(gout) && aligned16(gx) && (i64)B * C * d0 * d1 * d2 < (1ll << 31)) {
         Up2BGeom g;
         g.BC = B * C; g.d0 = d0; g.d1 = d1; g.d2 = d2; g.XQ = d2 / 4;
