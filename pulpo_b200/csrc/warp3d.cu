@@ -83,11 +83,25 @@ struct C8 {
     float c000, c001, c010, c011, c100, c101, c110, c111;
 };
 
-__device__ __forceinline__ C8 gather8(const float *p, int sy, int sz)
+// strides as 64-bit BYTE offsets computed once per thread: each corner address is then one 64-bit add
+// (the int-stride version spent ~35 integer instructions per voxel on sign extensions and carries)
+struct GStride {
+    i64 y, z, zy;
+};
+__device__ __forceinline__ GStride make_gstride(int sy, int sz)
 {
-    const float *py = p + sy, *pz = p + sz, *pzy = pz + sy;
+    GStride s;
+    s.y = (i64)sy * 4; s.z = (i64)sz * 4; s.zy = s.y + s.z;
+    return s;
+}
+
+__device__ __forceinline__ C8 gather8(const float *im, int base, const GStride &st)
+{
+    const char *p = reinterpret_cast<const char *>(im) + (i64)base * 4;
+    const float *p0 = reinterpret_cast<const float *>(p), *py = reinterpret_cast<const float *>(p + st.y);
+    const float *pz = reinterpret_cast<const float *>(p + st.z), *pzy = reinterpret_cast<const float *>(p + st.zy);
     C8 k;
-    k.c000 = __ldg(p); k.c001 = __ldg(p + 1); k.c010 = __ldg(py); k.c011 = __ldg(py + 1);
+    k.c000 = __ldg(p0); k.c001 = __ldg(p0 + 1); k.c010 = __ldg(py); k.c011 = __ldg(py + 1);
     k.c100 = __ldg(pz); k.c101 = __ldg(pz + 1); k.c110 = __ldg(pzy); k.c111 = __ldg(pzy + 1);
     return k;
 }
@@ -184,6 +198,7 @@ warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, f
     const unsigned int nwarps = gridDim.x * 8u;
     const int lane = threadIdx.x & 31;
     const int S = g.S, sy = g.D2, sz = g.D1 * g.D2;
+    const GStride gst = make_gstride(sy, sz);
     float reg_acc = 0.0f;
     // persistent: whole waves of resident CTAs stride over the work items (one warp-item at a time)
     for (unsigned int w = (blockIdx.x * 256u + threadIdx.x) >> 5; w < g.items; w += nwarps) {
@@ -217,12 +232,17 @@ warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, f
         for (int c = 0; c < g.C; ++c) {
             const float *im = img + ((i64)t.b * g.C + c) * S;
             float *o = out + ((i64)t.b * g.C + c) * S + v0;
-            float res[WR];
+            // all 8*WR corner gathers are issued before the first interpolation (no branch in between: the
+            // footprint of a lane outside the volume is clamped in-bounds, so its loads are legal and just
+            // unused) -- the kernel is bound by load latency, not by the L1 pipe
+            C8 q[WR];
 #pragma unroll
-            for (int j = 0; j < WR; ++j) res[j] = ok[j] ? interp8(gather8(im + ft[j].base, sy, sz), ft[j]) : 0.0f;
+            for (int j = 0; j < WR; ++j) q[j] = gather8(im, ft[j].base, gst);
 #pragma unroll
-            for (int j = 0; j < WR; ++j)
-                if (ok[j]) o[j * sy] = res[j];
+            for (int j = 0; j < WR; ++j) {
+                const float res = interp8(q[j], ft[j]);
+                if (ok[j]) o[j * sy] = res;
+            }
         }
     }
     if (REG) {
@@ -292,6 +312,7 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
     const unsigned int nwarps = gridDim.x * 8u;
     const int lane = threadIdx.x & 31;
     const int S = g.S, sy = g.D2, sz = g.D1 * g.D2;
+    const GStride gst = make_gstride(sy, sz);
     const float reg_scale_k = REG ? (reg_gloss ? __ldg(reg_gloss) : 1.0f) * reg_k : 0.0f;
     for (unsigned int w = (blockIdx.x * 256u + threadIdx.x) >> 5; w < g.items; w += nwarps) {   // persistent, warp-uniform
     const WItem t = decode_witem(w, lane, g);
@@ -324,11 +345,13 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
         const i64 off = ((i64)t.b * g.C + c) * S;
         float go[WR];
         load_rows<true>(gout + off + v0, sy, ok, go);
+        C8 qq[WR];   // all gathers first (see the forward)
+#pragma unroll
+        for (int j = 0; j < WR; ++j) qq[j] = gather8(img + off, ft[j].base, gst);
 #pragma unroll
         for (int j = 0; j < WR; ++j) {
-            if (!ok[j]) continue;
             const Foot &k = ft[j];
-            const C8 q = gather8(img + off + k.base, sy, sz);
+            const C8 &q = qq[j];
             // d/dx: difference along x, interpolated along y and z; likewise for y and z
             const float sx = ((q.c001 - q.c000) * k.wy0 + (q.c011 - q.c010) * k.wy1) * k.wz0 +
                              ((q.c101 - q.c100) * k.wy0 + (q.c111 - q.c110) * k.wy1) * k.wz1;
@@ -339,7 +362,7 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
             rx[j] += sx * go[j];
             ry[j] += sy_ * go[j];
             rz[j] += sz_ * go[j];
-            if (SCATTER) {
+            if (SCATTER && ok[j]) {
                 float *o = gimg + off + k.base;
                 const float w00 = k.wx0 * k.wy0, w01 = k.wx1 * k.wy0, w10 = k.wx0 * k.wy1, w11 = k.wx1 * k.wy1;
                 const float g0 = go[j] * k.wz0, g1 = go[j] * k.wz1;
