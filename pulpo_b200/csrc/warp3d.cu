@@ -158,13 +158,17 @@ __device__ __forceinline__ float l2_fwd_terms(const float *f, const float (&c)[W
 {
     float acc = 0.0f;
     if (inner) {
+        // interior block: every neighbour address is inside the allocation (z > 0, y0 > 0), so the x
+        // neighbour is simply the cached load one element to the left (the value read by lane 0 at x == 0
+        // is masked) -- no shuffles, no predicated edge loads
         const float xin = t.x > 0 ? 1.0f : 0.0f;
-        float py = __ldg(f - sy);
+        const char *row = reinterpret_cast<const char *>(f);
+        const i64 sy8 = (i64)sy * 4, sz8 = (i64)sz * 4;
+        float py = __ldg(reinterpret_cast<const float *>(row - sy8));
 #pragma unroll
-        for (int j = 0; j < WR; ++j) {
-            float left = __shfl_up_sync(0xffffffffu, c[j], 1);
-            if (lane == 0 && t.x > 0) left = __ldg(f + j * sy - 1);
-            const float dzz = c[j] - __ldg(f + j * sy - sz), dyy = c[j] - py, dxx = c[j] - left;
+        for (int j = 0; j < WR; ++j, row += sy8) {
+            const float left = __ldg(reinterpret_cast<const float *>(row) - 1);
+            const float dzz = c[j] - __ldg(reinterpret_cast<const float *>(row - sz8)), dyy = c[j] - py, dxx = c[j] - left;
             acc += xin * (dzz * dzz + dyy * dyy + dxx * dxx);
             py = c[j];
         }
@@ -261,17 +265,21 @@ __device__ __forceinline__ void l2_bwd_terms(const float *f, const float (&c)[WR
 {
     const bool xin = t.x > 0, xn = t.x + 1 < g.D2;
     if (inner) {
+        // interior block (all z / y neighbours and the rows around exist): x neighbours are cached loads at
+        // +-1 element (masked at the two x faces), no shuffles, no predicated edge loads
         const float mi = xin ? 1.0f : 0.0f, mn = xn ? 1.0f : 0.0f;
-        float py = __ldg(f - sy);
-        const float down = __ldg(f + WR * sy);
+        const char *row = reinterpret_cast<const char *>(f);
+        const i64 sy8 = (i64)sy * 4, sz8 = (i64)sz * 4;
+        float py = __ldg(reinterpret_cast<const float *>(row - sy8));
+        const float down = __ldg(reinterpret_cast<const float *>(row + WR * sy8));
 #pragma unroll
-        for (int j = 0; j < WR; ++j) {
-            float left = __shfl_up_sync(0xffffffffu, c[j], 1), right = __shfl_down_sync(0xffffffffu, c[j], 1);
-            if (lane == 0 && xin) left = __ldg(f + j * sy - 1);
-            if (lane == 31 && xn) right = __ldg(f + j * sy + 1);
+        for (int j = 0; j < WR; ++j, row += sy8) {
+            const float *rp = reinterpret_cast<const float *>(row);
+            const float left = __ldg(rp - 1), right = __ldg(rp + 1);
             const float cc = c[j];
             const float ny = j + 1 < WR ? c[j + 1 < WR ? j + 1 : 0] : down;
-            const float nb = (__ldg(f + j * sy - sz) + __ldg(f + j * sy + sz)) + (py + ny);
+            const float nb = (__ldg(reinterpret_cast<const float *>(row - sz8)) + __ldg(reinterpret_cast<const float *>(row + sz8))) +
+                             (py + ny);
             r[j] = mi * ((5.0f * cc - left) - nb) - mn * (right - cc);
             py = cc;
         }
