@@ -135,21 +135,32 @@ __device__ __forceinline__ float4 ld4v(const float4 *p)
 // Walking a z run, the upper four corners of one plane are the lower four of the next whenever the
 // footprint moved by exactly one plane (the usual case for a smooth field): those are kept in
 // registers, so a plane costs four 128-bit gathers instead of eight.
-__device__ __forceinline__ void gather8(const float4 *p, int sy, int sz, bool reuse_lower, Corners &k)
+// Strides are 64-bit BYTE offsets computed once per work item, so each corner address is one 64-bit add.
+struct VStride {
+    i64 y, z, zy;
+};
+__device__ __forceinline__ VStride make_vstride(int sy, int sz)
 {
-    const float4 *py = p + sy, *pz = p + sz, *pzy = pz + sy;
+    VStride s;
+    s.y = (i64)sy * 16; s.z = (i64)sz * 16; s.zy = s.y + s.z;
+    return s;
+}
+
+__device__ __forceinline__ void gather8(const float4 *vol, int base, const VStride &st, bool reuse_lower, Corners &k)
+{
+    const char *p = reinterpret_cast<const char *>(vol) + (i64)base * 16;
     if (reuse_lower) {
         k.c[0] = k.c[4]; k.c[1] = k.c[5]; k.c[2] = k.c[6]; k.c[3] = k.c[7];
     } else {
-        k.c[0] = ld4v(p);
-        k.c[1] = ld4v(p + 1);
-        k.c[2] = ld4v(py);
-        k.c[3] = ld4v(py + 1);
+        k.c[0] = ld4v(reinterpret_cast<const float4 *>(p));
+        k.c[1] = ld4v(reinterpret_cast<const float4 *>(p) + 1);
+        k.c[2] = ld4v(reinterpret_cast<const float4 *>(p + st.y));
+        k.c[3] = ld4v(reinterpret_cast<const float4 *>(p + st.y) + 1);
     }
-    k.c[4] = ld4v(pz);
-    k.c[5] = ld4v(pz + 1);
-    k.c[6] = ld4v(pzy);
-    k.c[7] = ld4v(pzy + 1);
+    k.c[4] = ld4v(reinterpret_cast<const float4 *>(p + st.z));
+    k.c[5] = ld4v(reinterpret_cast<const float4 *>(p + st.z) + 1);
+    k.c[6] = ld4v(reinterpret_cast<const float4 *>(p + st.zy));
+    k.c[7] = ld4v(reinterpret_cast<const float4 *>(p + st.zy) + 1);
 }
 
 // same corner order / op order as the CPU grid sampler (tnw, tne, tsw, tse, bnw, ...)
@@ -234,6 +245,7 @@ vecint_fwd_kernel(const VMulti m, int nsteps, int save, float scale)
             const VGeom &g = L.g;
             const unsigned int N = g.N, S = g.S;
             const int sy = g.D2, sz = g.D1 * g.D2;
+            const VStride vst = make_vstride(sy, sz);
             const float4 *src = save ? L.ws + (i64)k * N : L.ws + (i64)(k & 1) * N;
             float4 *dst = save ? L.ws + (i64)(k + 1) * N : L.ws + (i64)((k + 1) & 1) * N;
             const Item t = decode_item(it - L.item0, g, lane);
@@ -248,7 +260,7 @@ vecint_fwd_kernel(const VMulti m, int nsteps, int save, float scale)
                 float4 vn = v;
                 if (z + 1 < t.z1) vn = ld4v(vol + off + sz);   // the next plane's own value, ahead of this plane's gathers
                 const VFoot f = make_vfoot<MODE>((float)z, yf, xf, v, g);
-                gather8(vol + f.base, sy, sz, f.base == prev_base + sz, kc);
+                gather8(vol, f.base, vst, f.base == prev_base + sz, kc);
                 prev_base = f.base;
                 const float r0 = interp8<MODE>(kc.c[0].x, kc.c[1].x, kc.c[2].x, kc.c[3].x, kc.c[4].x, kc.c[5].x, kc.c[6].x, kc.c[7].x, f.w, v.x);
                 const float r1 = interp8<MODE>(kc.c[0].y, kc.c[1].y, kc.c[2].y, kc.c[3].y, kc.c[4].y, kc.c[5].y, kc.c[6].y, kc.c[7].y, f.w, v.y);
@@ -354,6 +366,7 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
             const VGeom &g = L.g;
             const unsigned int N = g.N, S = g.S;
             const int sy = g.D2, sz = g.D1 * g.D2;
+            const VStride vst = make_vstride(sy, sz);
             float4 *Pa = L.scr + (flip ? 2 : 0) * (i64)N, *Ya = Pa + N;
             float4 *Pb = L.scr + (flip ? 0 : 2) * (i64)N, *Yb = Pb + N;
             // autograd chain of the sample position: (S/2) * 2/(S-1) per axis where the clamp is inactive
@@ -394,7 +407,7 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
                 const VFoot f = make_vfoot<MODE>((float)z, yf, xf, v, g, &uz, &uy, &ux);
                 const int A = t.valid ? f.base : NOADDR;
                 if (t.valid) {
-                    gather8(vol + f.base, sy, sz, f.base == prev_base + sz, kc);
+                    gather8(vol, f.base, vst, f.base == prev_base + sz, kc);
                     prev_base = f.base;
                     // q[d] = <corner_d, G> over the 3 channels
                     float q[8];
