@@ -3,6 +3,7 @@
     SVFDecoder   <- src/components/pulpo.py:265-319  (forward :301-319)
     PULPoPrior   <- src/components/pulpo.py:323-341
     moving_pyramid (function) <- Autoencoder.forward :168-179
+    feedback_resample (function) <- Autoencoder.forward :195-206
 
 ``SVFDecoder`` keeps the attributes callers reach into (``spatial_transform``, ``integrate``,
 ``resizer_level``, ``resizer_output``, ``velocity_field``; reference models.py:330,387 and
@@ -93,6 +94,14 @@ class PULPoPrior(nn.Module):
             prior_sigmas[l] = torch.ones((), dtype=torch.float32, device=s.device).expand(s.shape)
             prior_mus[l]._pulpo_const, prior_sigmas[l]._pulpo_const = 0.0, 1.0   # host-side tag
         return prior_mus, prior_sigmas
+
+
+def feedback_resample(feedback_items, down_size):
+    """``torch.cat([F.interpolate(item, size=down_size, mode='trilinear', align_corners=False) ...], dim=1)`` of
+    Autoencoder.forward (src/components/pulpo.py:195-206): the coarser level's samples / velocity fields /
+    displacement fields / warped image, resampled straight into one concatenated tensor that feeds
+    ``up_blocks[k]`` (PyTorch convolutions)."""
+    return PF.resample_cat(list(feedback_items), down_size)
 
 
 def moving_pyramid(x, latent_levels, lk_offset, df_resolution="level_res"):

@@ -198,6 +198,71 @@ def avgpool2(x):
     return out
 
 
+# ----------------------------------------------------------------------------- encoder feedback (f-4)
+class _ResampleCat(torch.autograd.Function):
+    """cat([F.interpolate(t, size, trilinear, align_corners=False) for t in items], dim=1) without the
+    per-item temporaries and the concat pass: every item is resampled straight into its channel slice of
+    the output (one launch per item and batch element); the backward is the exact adjoint in gather form."""
+
+    @staticmethod
+    def forward(ctx, size, *items):
+        items = [_prep(t, "feedback item") for t in items]
+        B = int(items[0].shape[0])
+        o0, o1, o2 = (int(v) for v in size)
+        So = o0 * o1 * o2
+        ctot = sum(int(t.shape[1]) for t in items)
+        out = torch.empty((B, ctot, o0, o1, o2), dtype=torch.float32, device=items[0].device)
+        L, st = _lib.lib(), _stream()
+        c0, meta = 0, []
+        for t in items:
+            Bt, C, i0, i1, i2 = _dims5(t, "feedback item")
+            if Bt != B:
+                raise RuntimeError("pulpo_b200: feedback items differ in batch size")
+            for b in range(B):
+                dst = _vp(out.data_ptr() + 4 * ((b * ctot + c0) * So))
+                src = _vp(t.data_ptr() + 4 * b * C * i0 * i1 * i2)
+                if (i0, i1, i2) == (o0, o1, o2):
+                    out[b, c0:c0 + C].copy_(t[b])
+                else:
+                    check(L.pulpo_interp_size_fwd(src, dst, 1, C, i0, i1, i2, o0, o1, o2, st), "interp_size_fwd")
+            meta.append((c0, C, i0, i1, i2))
+            c0 += C
+        ctx.meta, ctx.osize, ctx.ctot, ctx.B = meta, (o0, o1, o2), ctot, B
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        gout = _prep(gout, "grad_output")
+        o0, o1, o2 = ctx.osize
+        So, B, ctot = o0 * o1 * o2, ctx.B, ctx.ctot
+        L, st = _lib.lib(), _stream()
+        grads = []
+        for k, (c0, C, i0, i1, i2) in enumerate(ctx.meta):
+            if not ctx.needs_input_grad[1 + k]:
+                grads.append(None)
+                continue
+            if (i0, i1, i2) == (o0, o1, o2):
+                grads.append(gout[:, c0:c0 + C].contiguous())
+                continue
+            f = o0 // i0
+            if f < 2 or (f * i0, f * i1, f * i2) != (o0, o1, o2):
+                raise NotImplementedError("pulpo_b200: feedback resampling backward needs an integer size ratio "
+                                          "(got %s -> %s)" % ((i0, i1, i2), (o0, o1, o2)))
+            g = torch.empty((B, C, i0, i1, i2), dtype=torch.float32, device=gout.device)
+            for b in range(B):
+                src = _vp(gout.data_ptr() + 4 * ((b * ctot + c0) * So))
+                dst = _vp(g.data_ptr() + 4 * b * C * i0 * i1 * i2)
+                check(L.pulpo_resize_up_bwd(src, dst, f, 1.0, 0, 1, C, i0, i1, i2, st), "resize_up_bwd")
+            grads.append(g)
+        return (None, *grads)
+
+
+def resample_cat(items, size):
+    """The encoder's feedback tensor (src/components/pulpo.py:195-206): every item of the coarser level
+    trilinearly resized to ``size`` and concatenated along channels."""
+    return _ResampleCat.apply(tuple(int(v) for v in size), *items)
+
+
 # ----------------------------------------------------------------------------- NCC (a9)
 class _NCC(torch.autograd.Function):
     @staticmethod

@@ -668,3 +668,26 @@ def test_jacobian_det_full_size_vs_oracle_slices(PF):
         assert_close(det[:, z0:z0 + 10], ref_full[:, z0:z0 + 10], 1e-5, "jacdet slab %d" % z0)
     s = F.jdet_std(df.cuda(), 1.0).item()
     assert_loss_close(s, float(ref_full.astype(np.float64).std(ddof=1)), "full-size JDetStd")
+
+
+# ----------------------------------------------------------------------------- encoder feedback resampling (f-4)
+@pytest.mark.parametrize("B", [1, 2])
+def test_feedback_resample_cat_matches_torch(PF, B):
+    """src/components/pulpo.py:195-206: six coarser-level tensors resized x2 and concatenated; forward and the
+    gradients to every item against F.interpolate + torch.cat on the CPU (the reference's own ops)."""
+    import torch.nn.functional as F
+    from pulpo_b200.components.pulpo import feedback_resample
+    g = torch.Generator().manual_seed(3)
+    lo, hi = (5, 6, 7), (10, 12, 14)
+    chans = [4, 3, 3, 3, 3, 1]      # samples(zdim), velocity_fields, individual, combined, final dfs, transformed
+    items = [torch.randn(B, c, *lo, generator=g) for c in chans]
+    ref_in = [t.clone().requires_grad_(True) for t in items]
+    ref = torch.cat([F.interpolate(t, size=hi, mode="trilinear", align_corners=False) for t in ref_in], dim=1)
+    gout = torch.randn(ref.shape, generator=g)
+    ref.backward(gout)
+    ours_in = [t.cuda().requires_grad_(True) for t in items]
+    out = feedback_resample(ours_in, hi)
+    assert_close(out.detach().cpu().numpy(), ref.detach().numpy(), 1e-5, "feedback cat")
+    out.backward(gout.cuda())
+    for a, b in zip(ours_in, ref_in):
+        assert_grad_close(a.grad.cpu().numpy(), b.grad.numpy(), "feedback grad")
