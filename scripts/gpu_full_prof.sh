@@ -14,6 +14,6 @@ ncu --set full --clock-control none --import-source on -k regex:'ncc_tma_kernel'
 echo "ncu ncc rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:'warp3d_' -s 6 -c 2 -f -o $out/full_${tag}_warp $cmd >> $out/ncu_full_$tag.log 2>&1
 echo "ncu warp rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'up2_(fwd|bwd)_kernel' -s 3 -c 2 -f -o $out/full_${tag}_up2 $cmd >> $out/ncu_full_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'up2_' -s 3 -c 2 -f -o $out/full_${tag}_up2 $cmd >> $out/ncu_full_$tag.log 2>&1
 echo "ncu up2 rc=$?"
 tail -3 $out/ncu_full_$tag.log
