@@ -82,8 +82,8 @@ size_t pulpo_vecint_ws_bytes(int nsteps, int save_steps, int B, int D0, int D1, 
 int pulpo_vecint_fwd(const float *vec, float *out, void *ws, size_t ws_bytes, int nsteps,
                      int save_steps, int B, int D0, int D1, int D2, int coord_mode,
                      pulpo_stream_t stream);
-/* gvec = d loss/d vec.  `saved` = the ws of a save_steps=1 forward; scratch: 4 states
- * (two (own, scatter) gradient pairs that ping-pong between steps). */
+/* gvec = d loss/d vec.  `saved` = the ws of a save_steps=1 forward; scratch: 3 rotating
+ * gradient states (pulpo_vecint_bwd_scratch_bytes). */
 size_t pulpo_vecint_bwd_scratch_bytes(int B, int D0, int D1, int D2);
 int pulpo_vecint_bwd(const float *gout, const void *saved, float *gvec, void *scratch,
                      size_t scratch_bytes, int nsteps, int B, int D0, int D1, int D2,

@@ -42,6 +42,9 @@ static_assert(VI_PX == 8 || VI_PX == 16 || VI_PX == 32, "patch width");
 // Thread counts from a sweep on B200 (config-2 levels, bench kernel table): fewer, longer z runs win
 // (more corner reuse / scatter carry per run, no spills): forward 1024 -> 768: 126 -> 118 us,
 // backward 768 / 640 / 512 / 448 / 384: 343 / 347 / 322 / 356 / 414 us.
+#ifndef PULPO_VI_BWD_PY
+#define PULPO_VI_BWD_XYZ 1   // three rotating gradient states (default); -DPULPO_VI_BWD_PY: two (own, scatter) pairs
+#endif
 #ifndef PULPO_VI_FWD_THREADS
 #define PULPO_VI_FWD_THREADS 768
 #endif
@@ -321,13 +324,14 @@ __device__ __forceinline__ void red3(float4 *addr, const F3 &a)
 }
 
 // Backward of one step  v' = v + W(v) v :   g = g' + W(v)^T g' + (dW/dv : v)^T g'
-//   own    : g' + gather-form gradient through the sample position -> plain 128-bit store into P
-//   scatter: w_d * g' onto the 8 corners -> red.global.add.v4.f32 into Y, combined across lanes
-//            and planes first (COMBINE)
-// The incoming gradient of a step is P + Y.  Two (P, Y) pairs ping-pong: a step reads pair A and
-// zeroes A's Y behind itself (each voxel is read by exactly one thread), writes own parts to
-// B's P and scatters into B's Y (zeroed one step earlier), so no pass over memory is spent on
-// clearing and no ordering hazard exists between the plain stores and the reductions.
+//   own    : g' + gather-form gradient through the sample position
+//   scatter: w_d * g' onto the 8 corners -> red.global.add.v4.f32, the four upper-corner contributions
+//            carried in registers to the next plane of the z run (COMBINE == 2, default)
+// Gradient states (float4 per voxel).  Default: three states rotate -- X is read, Y (zero at step start)
+// receives both parts through vector reductions, Z is cleared for the next step by the thread that owns the
+// voxel; 48 B/voxel of scratch keeps more of the working set in L2 than the alternative
+// (-DPULPO_VI_BWD_PY: two (own P, scatter Y) pairs, the own part a plain store; 64 B/voxel; measured
+// 324 vs 312 us at config 2, 979 vs 904 us at two pairs per GPU).
 template <int MODE, int COMBINE>
 __global__ void __launch_bounds__(VI_BWD_THREADS, 1)
 vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
@@ -343,7 +347,11 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
     for (int lv = 0; lv < m.n; ++lv) {
         const VLevel &L = m.l[lv];
         const unsigned int N = L.g.N, S = L.g.S;
+#ifdef PULPO_VI_BWD_XYZ
+        float4 *Pa = L.scr, *Ya = L.scr + N, *Yb = L.scr + N;      // X = gout, Y = 0
+#else
         float4 *Pa = L.scr, *Ya = L.scr + N, *Yb = L.scr + 3 * (i64)N;
+#endif
         for (unsigned int i = tid; i < N; i += nthr) {
             unsigned int b = i / S, v = i - b * S;
             const float *f = L.in + (i64)b * 3 * S + v;
@@ -367,8 +375,16 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
             const unsigned int N = g.N, S = g.S;
             const int sy = g.D2, sz = g.D1 * g.D2;
             const VStride vst = make_vstride(sy, sz);
+#ifdef PULPO_VI_BWD_XYZ
+            // three rotating states: X (incoming gradient), Y (accumulates own + scatter parts, zero at step start),
+            // Z (being zeroed for the next step); Pa = X, Yb = Y, Ya = Z in the names below
+            const int rot = (nsteps - 1 - k) % 3;
+            float4 *Pa = L.scr + (i64)rot * N, *Yb = L.scr + (i64)((rot + 1) % 3) * N, *Ya = L.scr + (i64)((rot + 2) % 3) * N;
+            float4 *Pb = Yb;
+#else
             float4 *Pa = L.scr + (flip ? 2 : 0) * (i64)N, *Ya = Pa + N;
             float4 *Pb = L.scr + (flip ? 0 : 2) * (i64)N, *Yb = Pb + N;
+#endif
             // autograd chain of the sample position: (S/2) * 2/(S-1) per axis where the clamp is inactive
             const float kz = (MODE == PULPO_COORD_FAST) ? g.a0.kf : g.a0.gmul * (2.0f * g.a0.rcp);
             const float ky = (MODE == PULPO_COORD_FAST) ? g.a1.kf : g.a1.gmul * (2.0f * g.a1.rcp);
@@ -387,8 +403,12 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
             int carry_addr = NOADDR;
             float4 Gn = zero4, vn = zero4;
             if (t.valid) {
+#ifdef PULPO_VI_BWD_XYZ
+                Gn = ld4v(Pa + vb + off);
+#else
                 const float4 p = ld4v(Pa + vb + off), y = ld4v(Ya + vb + off);
                 Gn = make_float4(p.x + y.x, p.y + y.y, p.z + y.z, 0.0f);
+#endif
                 vn = ld4v(vol + off);
             }
             Corners kc;
@@ -398,8 +418,12 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
                 if (t.valid) {
                     Ya[vb + off] = zero4;   // read above (or one iteration ago): clear it for the step after next
                     if (z + 1 < t.z1) {     // next plane's own values, requested ahead of this plane's gathers
+#ifdef PULPO_VI_BWD_XYZ
+                        Gn = ld4v(Pa + vb + off + sz);
+#else
                         const float4 p = ld4v(Pa + vb + off + sz), y = ld4v(Ya + vb + off + sz);
                         Gn = make_float4(p.x + y.x, p.y + y.y, p.z + y.z, 0.0f);
+#endif
                         vn = ld4v(vol + off + sz);
                     }
                 }
@@ -422,7 +446,11 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
                     const float mz = (uz > 0.0f && uz < g.a0.Sm1) ? kz : 0.0f;
                     const float my = (uy > 0.0f && uy < g.a1.Sm1) ? ky : 0.0f;
                     const float mx = (ux > 0.0f && ux < g.a2.Sm1) ? kx : 0.0f;
+#ifdef PULPO_VI_BWD_XYZ
+                    red_add_v4(reinterpret_cast<float *>(Pb + vb + off), G.x + mz * sz_, G.y + my * sy_, G.z + mx * sx, 0.0f);
+#else
                     Pb[vb + off] = make_float4(G.x + mz * sz_, G.y + my * sy_, G.z + mx * sx, 0.0f);
+#endif
                 }
                 // ---- scatter half.  c[d] = w_d * G for the 8 corners (all in-bounds; border corners carry weight 0)
                 F3 c[8];
@@ -523,7 +551,11 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
     for (int lv = 0; lv < m.n; ++lv) {
         const VLevel &L = m.l[lv];
         const unsigned int N = L.g.N, S = L.g.S;
+#ifdef PULPO_VI_BWD_XYZ
+        const float4 *Pa = L.scr + (i64)(nsteps % 3) * N, *Ya = L.scr + (i64)((nsteps + 1) % 3) * N;   // X; the last step's Z is all zero
+#else
         const float4 *Pa = L.scr + (flip ? 2 : 0) * (i64)N, *Ya = Pa + N;
+#endif
         for (unsigned int i = tid; i < N; i += nthr) {
             unsigned int b = i / S, v = i - b * S;
             const float4 p = Pa[i], y = Ya[i];
@@ -637,7 +669,11 @@ extern "C" size_t pulpo_vecint_ws_bytes(int nsteps, int save_steps, int B, int D
 
 extern "C" size_t pulpo_vecint_bwd_scratch_bytes(int B, int D0, int D1, int D2)
 {
+#ifdef PULPO_VI_BWD_XYZ
+    return (size_t)B * D0 * D1 * D2 * sizeof(float4) * 3;   // three rotating gradient states
+#else
     return (size_t)B * D0 * D1 * D2 * sizeof(float4) * 4;   // two (P, Y) pairs
+#endif
 }
 
 extern "C" int pulpo_vecint_multi_fwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int save_steps, int B,

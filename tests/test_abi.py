@@ -62,7 +62,7 @@ def test_version_and_errors(lib):
 def test_workspace_arithmetic(lib):
     assert lib.pulpo_vecint_ws_bytes(7, 1, 1, 80, 96, 112) == 7 * 80 * 96 * 112 * 16
     assert lib.pulpo_vecint_ws_bytes(7, 0, 2, 8, 8, 8) == 2 * 2 * 512 * 16
-    assert lib.pulpo_vecint_bwd_scratch_bytes(1, 8, 8, 8) == 4 * 512 * 16
+    assert lib.pulpo_vecint_bwd_scratch_bytes(1, 8, 8, 8) == 3 * 512 * 16
     assert lib.pulpo_ncc_ws_bytes(1, 1, 160, 192, 224) >= 16 + 8 * 7 * 12
     assert lib.pulpo_reduce_ws_bytes() >= 16 + 8 * 592
 
