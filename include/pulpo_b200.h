@@ -151,6 +151,20 @@ int pulpo_kl_diag_bwd(const float *gloss, const float *mu0, const float *sigma0,
                       const float *sigma1, float eps, float weight, float *gmu0, float *gsigma0,
                       int B, long long n, pulpo_stream_t stream);
 
+/* All levels of HierarchicalKLLoss (src/losses.py:262-276) with the N(0,1) prior, value AND gradients, in
+ * one launch: out = weight * KL(N(mu, sigma) || N(0,1)) per level (batch mean), gmu/gsigma = its gradient.
+ * `levels` is a HOST array (at most 6); ws: pulpo_kl_multi_ws_bytes(), zeroed once by the caller. */
+typedef struct pulpo_kl_level {
+    const float *mu, *sigma;   /* [B, n] */
+    float *gmu, *gsigma;       /* [B, n] */
+    float *out;                /* device scalar */
+    long long n;
+    float weight;              /* level weight * beta */
+} pulpo_kl_level;
+size_t pulpo_kl_multi_ws_bytes(void);
+int pulpo_kl_n01_multi(const pulpo_kl_level *levels, int nlevels, float eps, int B, void *ws,
+                       size_t ws_bytes, pulpo_stream_t stream);
+
 /* ---- f-1: L2_reg(deformation_field, lamb)   src/losses.py:208-222 (3-D branch) ------------- */
 int pulpo_l2reg_fwd(const float *f, float lamb, float *out, void *ws, size_t ws_bytes,
                     int B, int C, int D0, int D1, int D2, pulpo_stream_t stream);

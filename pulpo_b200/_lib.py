@@ -25,6 +25,11 @@ class VecIntLevel(ctypes.Structure):
                 ("D0", _i), ("D1", _i), ("D2", _i)]
 
 
+class KlLevel(ctypes.Structure):
+    """pulpo_kl_level (include/pulpo_b200.h)."""
+    _fields_ = [("mu", _vp), ("sigma", _vp), ("gmu", _vp), ("gsigma", _vp), ("out", _vp), ("n", _ll), ("weight", _f)]
+
+
 # name -> (restype, argtypes); mirrors include/pulpo_b200.h one to one
 SIGNATURES = {
     "pulpo_version": (_i, []),
@@ -49,6 +54,8 @@ SIGNATURES = {
     "pulpo_reduce_ws_bytes": (_sz, []),
     "pulpo_kl_diag_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _sz, _i, _ll, _vp]),
     "pulpo_kl_diag_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _ll, _vp]),
+    "pulpo_kl_multi_ws_bytes": (_sz, []),
+    "pulpo_kl_n01_multi": (_i, [ctypes.POINTER(KlLevel), _i, _f, _i, _vp, _sz, _vp]),
     "pulpo_l2reg_fwd": (_i, [_vp, _f, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "pulpo_l2reg_bwd": (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_jacdet_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -62,6 +62,63 @@ kl_bwd_kernel(const float *__restrict__ gloss, const float *__restrict__ mu0, co
     }
 }
 
+// ---- all pyramid levels, value and gradients, in ONE launch (HotPathPlan: the KL terms have no data
+// dependence on anything else in the step, so eight tiny launches become one streaming pass that reads
+// mu / sigma once).  N(0,1) prior only (src/components/pulpo.py:337-339).
+constexpr int KL_MAXL = 6;
+struct KlLevel {
+    const float *mu, *sg;
+    float *gmu, *gsg, *out;
+    i64 total;      // B * n
+    float k;        // weight / B : scale of the gradients
+    double scale;   // 0.5 * weight / B : scale of the value
+};
+struct KlMulti {
+    int n;
+    KlLevel l[KL_MAXL];
+};
+struct KlMultiWs {
+    unsigned int ticket, pad;
+    double partial[1];   // [KL_MAXL][ctas]
+};
+
+__global__ void __launch_bounds__(256)
+kl_multi_kernel(const KlMulti m, float eps, KlMultiWs *ws)
+{
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    const i64 tid = blockIdx.x * (i64)blockDim.x + threadIdx.x, nthr = (i64)gridDim.x * blockDim.x;
+    const float den = 1.0f + eps;
+    for (int lv = 0; lv < m.n; ++lv) {
+        const KlLevel &L = m.l[lv];
+        float acc = 0.0f;
+        for (i64 i = tid; i < L.total; i += nthr) {
+            const float mu = __ldg(L.mu + i), s = __ldg(L.sg + i);
+            acc += kl_term(mu, s, 0.0f, 1.0f, eps);
+            L.gmu[i] = L.k * mu / den;
+            L.gsg[i] = L.k * (s / den - s / (s * s + eps));
+        }
+        const double bt = block_sum((double)acc, red);
+        if (threadIdx.x == 0) ws->partial[(i64)lv * gridDim.x + blockIdx.x] = bt;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = (atomicAdd(&ws->ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int lv = 0; lv < m.n; ++lv) {
+            double sum = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x)
+                sum += ((volatile double *)ws->partial)[(i64)lv * gridDim.x + i];
+            sum = block_sum(sum, red);
+            if (threadIdx.x == 0) *m.l[lv].out = (float)(sum * m.l[lv].scale);
+        }
+        if (threadIdx.x == 0) ws->ticket = 0;
+    }
+}
+
 // L2_reg: forward differences on the [1:,1:,1:] crop
 __global__ void __launch_bounds__(256)
 l2reg_fwd_kernel(const float *__restrict__ f, float *out, ReduceWs *ws, double scale, int BC, int D0, int D1, int D2)
@@ -251,6 +308,33 @@ extern "C" int pulpo_kl_diag_fwd(const float *mu0, const float *sigma0, const fl
     int grid = grid_for((total + 3) / 4, 256, 4);
     kl_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mu0, sigma0, mu1, sigma1, eps, out, (ReduceWs *)ws,
                                                         0.5 * (double)weight / (double)B, total, (al && (total & 3) == 0) ? 1 : 0);
+    return launch_status();
+}
+
+extern "C" size_t pulpo_kl_multi_ws_bytes(void) { return 16 + sizeof(double) * KL_MAXL * 592; }
+
+extern "C" int pulpo_kl_n01_multi(const pulpo_kl_level *levels, int nlevels, float eps, int B, void *ws, size_t ws_bytes,
+                                  pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(levels && ws, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(nlevels >= 1 && nlevels <= KL_MAXL && B > 0, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(ws_bytes >= pulpo_kl_multi_ws_bytes(), PULPO_ERR_WORKSPACE);
+    KlMulti m;
+    m.n = nlevels;
+    i64 most = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        const pulpo_kl_level &v = levels[l];
+        PULPO_REQUIRE(v.mu && v.sigma && v.gmu && v.gsigma && v.out, PULPO_ERR_NULL_POINTER);
+        PULPO_REQUIRE(v.n > 0, PULPO_ERR_INVALID_SHAPE);
+        m.l[l].mu = v.mu; m.l[l].sg = v.sigma; m.l[l].gmu = v.gmu; m.l[l].gsg = v.gsigma; m.l[l].out = v.out;
+        m.l[l].total = (i64)B * v.n;
+        m.l[l].k = v.weight / (float)B;
+        m.l[l].scale = 0.5 * (double)v.weight / (double)B;
+        if (m.l[l].total > most) most = m.l[l].total;
+    }
+    int grid = grid_for(most, 256, 4);
+    if (grid > 592) grid = 592;
+    kl_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m, eps, (KlMultiWs *)ws);
     return launch_status();
 }
 

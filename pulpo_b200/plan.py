@@ -96,7 +96,7 @@ class HotPathPlan:
         self.total = torch.zeros((), dtype=torch.float32, device=dev)
         # reduction workspaces (ticket counters must start at zero; kernels reset them)
         rbytes = lib.pulpo_reduce_ws_bytes()
-        self.ws_kl = [torch.zeros(rbytes, dtype=torch.uint8, device=dev) for _ in range(L)]
+        self.ws_klm = torch.zeros(lib.pulpo_kl_multi_ws_bytes(), dtype=torch.uint8, device=dev)
         self.ws_l2 = [torch.zeros(rbytes, dtype=torch.uint8, device=dev) for _ in range(L)]
         self.ws_ncc = [torch.zeros(lib.pulpo_ncc_ws_bytes(B, 1, *self.outsz[l]), dtype=torch.uint8, device=dev)
                        for l in range(L)]
@@ -154,6 +154,18 @@ class HotPathPlan:
             ev_comb[l] = torch.cuda.Event()
             ev_comb[l].record(cur)
 
+        # ---- KL of every level, value and gradients, in one launch on the aux stream (losses.py:47-76 with the
+        #      N(0,1) prior; weight = level weight * beta).  Independent of everything else in the step.
+        kl_arr = (_lib.KlLevel * L)()
+        for l in range(L):
+            nlat = 3 * self.insz[l][0] * self.insz[l][1] * self.insz[l][2]
+            kl_arr[l] = _lib.KlLevel(mus[l].data_ptr(), sigmas[l].data_ptr(), self.gmu[l].data_ptr(),
+                                     self.gsigma[l].data_ptr(), self.losses.data_ptr() + 4 * (0 * L + l), nlat,
+                                     self.kl_weight[l])
+        call(lib.pulpo_kl_n01_multi, kl_arr, L, 1e-10, B, _p(self.ws_klm), self.ws_klm.numel(), H(aux))
+        ev_kl = torch.cuda.Event()
+        ev_kl.record(aux)
+
         # ---- integrate every level in ONE cooperative launch (a cooperative kernel owns all SMs, so
         #      per-level launches would serialise; pulpo.py:311 for each decoder)
         lv_arr = (_lib.VecIntLevel * L)()
@@ -172,13 +184,7 @@ class HotPathPlan:
             if ms:
                 s.wait_event(start)
             din, dout = self.insz[l], self.outsz[l]
-            nlat = 3 * din[0] * din[1] * din[2]
             hs = H(s)
-            # KL (losses.py:47-76 with the N(0,1) prior; weight = level weight * beta)
-            call(lib.pulpo_kl_diag_fwd, _p(mus[l]), _p(sigmas[l]), None, None, 1e-10, self.kl_weight[l],
-                 self._loss_ptr(0, l), _p(self.ws_kl[l]), self.ws_kl[l].numel(), B, nlat, hs)
-            call(lib.pulpo_kl_diag_bwd, None, _p(mus[l]), _p(sigmas[l]), None, None, 1e-10, self.kl_weight[l],
-                 _p(self.gmu[l]), _p(self.gsigma[l]), B, nlat, hs)
             if ms:
                 s.wait_event(ev_int)
             # resize the integrated field to the output size
@@ -221,6 +227,7 @@ class HotPathPlan:
 
         # ---- backward of the integration, again one launch for all levels
         if ms:
+            cur.wait_event(ev_kl)
             for l in range(L):
                 cur.wait_event(ev_done[l])
         for l in range(L):

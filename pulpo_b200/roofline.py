@@ -52,6 +52,8 @@ def algo_bytes(name, args):
         return a[9] * a[10] * 4 * (2 + (1 if a[2] else 0) + (1 if a[3] else 0))
     if name == "pulpo_kl_diag_bwd":         # gloss, mu0, s0, mu1, s1, eps, weight, gmu, gsg, B, n
         return a[9] * a[10] * 4 * (4 + (1 if a[3] else 0) + (1 if a[4] else 0))
+    if name == "pulpo_kl_n01_multi":        # levels*, nlevels, eps, B, ws, bytes
+        return sum(a[3] * lv.n * 16 for lv in args[0][:a[1]])     # mu, sigma read once; gmu, gsigma written
     if name == "pulpo_l2reg_fwd":           # f, lamb, out, ws, bytes, B, C, D0..
         return a[5] * a[6] * a[7] * a[8] * a[9] * 4
     if name == "pulpo_l2reg_bwd":           # gloss, f, lamb, gf, accumulate, B, C, D0..
