@@ -86,6 +86,7 @@ struct NccTmaParams {
     float Wf, rcpW;
     int BC, D0, D1, D2, xt, yt;
     long long total_planes;        // BC * yt * xt * D0
+    int zchunks;                   // > 0: aligned (column, z chunk) grid with this many chunks per column
 };
 
 

@@ -127,7 +127,17 @@ ncc_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     // this CTA's share of the linearised (column, z) space
     const long long T = p.total_planes;
     long long q = (T * blockIdx.x) / gridDim.x;
-    const long long q_end = (T * (blockIdx.x + 1)) / gridDim.x;
+    long long q_end = (T * (blockIdx.x + 1)) / gridDim.x;
+    if (p.zchunks > 0) {
+        // aligned mode: CTA = (column, z chunk) with the same chunk boundaries in every column and neighbouring
+        // columns on neighbouring CTAs, so the CTAs that share halo rows read them at about the same time (L2 hits)
+        const int ncols = (int)(T / D0);
+        const int colx = blockIdx.x % ncols, ch = blockIdx.x / ncols;
+        const int zc = (D0 + p.zchunks - 1) / p.zchunks;
+        const int za = ch * zc, zb = min(D0, za + zc);
+        q = (long long)colx * D0 + za;
+        q_end = (long long)colx * D0 + (zb > za ? zb : za);
+    }
 
     float cc_acc = 0.0f;
     const float gk = FWD ? 0.0f : ((p.gloss ? __ldg(p.gloss) : 1.0f) * p.k);
@@ -394,7 +404,24 @@ int ncc_tma_grid(int BC, int D0, int D1, int D2, int win)
     // at least ~2*win planes per CTA so the z halo stays a fraction of the work
     const long long want = planes / (2 * win);
     const long long cap = (long long)sms * NT_CTAS_PER_SM;
+    const long long ncols = planes / D0;
+    if (!getenv("PULPO_NCC_LINEAR") && ncols <= cap && want >= cap) {   // aligned (column, z chunk) grid
+        const long long k = cap / ncols;
+        if (k * ncols * 10 >= cap * 8) return (int)(k * ncols);          // keeps >= 80 % of the CTA slots busy
+    }
     return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+// z chunks per column of the aligned grid (0: linearised split)
+static int ncc_tma_zchunks(int BC, int D0, int D1, int D2, int grid)
+{
+    const long long ncols = (long long)BC * ((D2 + NT_TX - 1) / NT_TX) * ((D1 + NT_TY - 1) / NT_TY);
+    if (getenv("PULPO_NCC_LINEAR") || grid % ncols != 0) return 0;
+    int dev = 0, sms = kSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long cap = (long long)sms * NT_CTAS_PER_SM;
+    return (grid / ncols == cap / ncols && ncols <= cap) ? (int)(grid / ncols) : 0;
 }
 
 // in2 == nullptr selects the forward (inputs: target, pred), else the backward (a, b, c)
@@ -413,6 +440,7 @@ int ncc_tma_launch(const float *in0, const float *in1, const float *in2, NccTmaP
     p.yt = (p.D1 + NT_TY - 1) / NT_TY;
     p.total_planes = (long long)p.BC * p.xt * p.yt * p.D0;
     const int grid = ncc_tma_grid(p.BC, p.D0, p.D1, p.D2, win);
+    p.zchunks = ncc_tma_zchunks(p.BC, p.D0, p.D1, p.D2, grid);
 #define PULPO_NCC_TMA_CASE(WW)                                                   \
     case WW:                                                                     \
         return fwd ? ncc_tma_launch_w<WW, true>(t0, t1, t2, p, grid, st)         \
