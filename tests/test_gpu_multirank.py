@@ -1,0 +1,66 @@
+"""Two-GPU NCCL run of the MC-sample sharding (config 3) with the real kernels: the merged per-voxel
+moments of 2 ranks x 4 samples equal the single-rank run over the same 8 samples (same per-sample
+Philox seeds).  Skipped on boxes with fewer than 2 GPUs."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+SIZE, TOTAL, LATENT, N = [32, 32, 32], 4, 3, 8
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _sample_fn_factory(dev):
+    from pulpo_b200 import synthetic as syn
+    from pulpo_b200.models import combine_dfs
+    from pulpo_b200.network_blocks import SpatialTransformer, gauss_sampler
+    x, y, dfs, mus, sgs = syn.make_hot_path_inputs(SIZE, TOTAL, LATENT, seed=3)
+    xc = x.to(dev)
+    mu = {l: dfs[l].to(dev) for l in dfs}
+    sg = {l: (0.3 * sgs[l]).to(dev) for l in dfs}
+    st = SpatialTransformer(SIZE)
+
+    def sample_fn(i, gen):
+        v = {l: gauss_sampler(mu[l], sg[l], generator=gen) for l in mu}
+        _, final = combine_dfs(v, SIZE)
+        return {"final0": final[0][0], "moved0": st(final[0], xc)[0]}
+    return sample_fn
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from pulpo_b200 import mc
+        res = mc.mc_uncertainty(_sample_fn_factory(dev), N, seed0=11, device=dev, dst=0)
+        if rank == 0:
+            torch.save({"count": res["final0"].count, "std": res["final0"].std().cpu(), "var": res["moved0"].variance_map().cpu()},
+                       os.path.join(out_dir, "r0.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_mc_uncertainty_two_gpus_nccl(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from pulpo_b200 import mc
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "r0.pt"))
+    dev = torch.device("cuda", 0)
+    one = mc.mc_uncertainty(_sample_fn_factory(dev), N, seed0=11, device=dev)
+    assert got["count"] == N
+    torch.testing.assert_close(got["std"], one["final0"].std().cpu(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(got["var"], one["moved0"].variance_map().cpu(), rtol=1e-4, atol=1e-7)
