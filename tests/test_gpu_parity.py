@@ -691,3 +691,46 @@ def test_feedback_resample_cat_matches_torch(PF, B):
     out.backward(gout.cuda())
     for a, b in zip(ours_in, ref_in):
         assert_grad_close(a.grad.cpu().numpy(), b.grad.numpy(), "feedback grad")
+
+
+# ----------------------------------------------------------------------------- autograd contract
+def test_modules_under_no_grad_and_anomaly_mode(PF):
+    """The drop-ins must work under torch.no_grad() (inference: no saved states / coefficient volumes) and
+    under torch.autograd.set_detect_anomaly(True) (the reference trains with it on, src/train.py)."""
+    from pulpo_b200 import synthetic as syn
+    from pulpo_b200.models import RegistrationHotPath
+    size, total, latent = [32, 32, 32], 4, 3
+    x, y, dfs, mus, sgs = syn.make_hot_path_inputs(size, total, latent, seed=6)
+    hp = RegistrationHotPath(size, total, latent).cuda()
+    cu = lambda d: {l: d[l].cuda() for l in d}
+    with torch.no_grad():
+        l0, _, outs0 = hp(x.cuda(), y.cuda(), cu(dfs), cu(mus), cu(sgs))
+    assert not l0.requires_grad
+    with torch.autograd.set_detect_anomaly(True):
+        d = {l: dfs[l].cuda().requires_grad_(True) for l in dfs}
+        m = {l: mus[l].cuda().requires_grad_(True) for l in dfs}
+        s = {l: sgs[l].cuda().requires_grad_(True) for l in dfs}
+        l1, _, outs1 = hp(x.cuda(), y.cuda(), d, m, s)
+        l1.backward()
+    assert_loss_close(l0.item(), l1.item(), "no_grad vs grad loss")
+    for l in range(latent):
+        assert torch.equal(outs0["moved"][l], outs1["moved"][l].detach())
+        assert torch.isfinite(d[l].grad).all() and torch.isfinite(m[l].grad).all() and torch.isfinite(s[l].grad).all()
+
+
+def test_transform_segmentation_many_channels_and_image_gradient(PF):
+    """PULPo.transform_segmentation warps 36-channel one-hot maps (models.py:370-388): multi-channel warp,
+    and the gradient into the moving image (scatter half) against the C oracle."""
+    from oracle import cport
+    from pulpo_b200 import synthetic as syn
+    shape, C = (12, 14, 16), 36
+    df = syn.make_field(shape, 61, max_abs=4.0)
+    seg = (torch.rand((1, C) + shape, generator=torch.Generator().manual_seed(2)) > 0.7).float()
+    ref, _ = cport.warp3d_fwd(df.numpy(), seg.numpy(), want_idx=True)
+    img = seg.cuda().requires_grad_(True)
+    out = PF.warp(df.cuda(), img)
+    assert np.array_equal(out.detach().cpu().numpy(), ref)
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    out.backward(gout.cuda())
+    gimg_ref, gdf_ref = cport.warp3d_bwd(gout.numpy(), df.numpy(), seg.numpy())
+    assert_grad_close(img.grad.cpu().numpy(), gimg_ref, "segmentation gimg")
