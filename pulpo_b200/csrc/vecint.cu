@@ -217,6 +217,46 @@ __device__ __forceinline__ VFoot make_vfoot(float zf, float yf, float xf, const 
     return f;
 }
 
+// One forward work item.  L0 = true: the item belongs to level 0 (the bulk of the work), whose geometry is then
+// addressed at constant offsets of the kernel parameter (constant-bank operands) instead of through a run-time
+// level index (one LDC per use).
+template <int MODE, bool L0>
+__device__ __forceinline__ void vi_fwd_item(const VMulti &m, int lv, unsigned int it, int lane, int k, int save, bool last)
+{
+            const VLevel &L = L0 ? m.l[0] : m.l[lv];
+            const VGeom &g = L.g;
+            const unsigned int N = g.N, S = g.S;
+            const int sy = g.D2, sz = g.D1 * g.D2;
+            const VStride vst = make_vstride(sy, sz);
+            const float4 *src = save ? L.ws + (i64)k * N : L.ws + (i64)(k & 1) * N;
+            float4 *dst = save ? L.ws + (i64)(k + 1) * N : L.ws + (i64)((k + 1) & 1) * N;
+            const Item t = decode_item(it - L.item0, g, lane);
+            if (!t.valid) return;
+            const float yf = (float)t.y, xf = (float)t.x;
+            const float4 *vol = src + (i64)t.b * S;
+            int off = (t.z0 * g.D1 + t.y) * g.D2 + t.x;
+            float4 v = ld4v(vol + off);
+            Corners kc;
+            int prev_base = NOBASE;
+            for (int z = t.z0; z < t.z1; ++z, off += sz) {
+                float4 vn = v;
+                if (z + 1 < t.z1) vn = ld4v(vol + off + sz);   // the next plane's own value, ahead of this plane's gathers
+                const VFoot f = make_vfoot<MODE>((float)z, yf, xf, v, g);
+                gather8(vol, f.base, vst, f.base == prev_base + sz, kc);
+                prev_base = f.base;
+                const float r0 = interp8<MODE>(kc.c[0].x, kc.c[1].x, kc.c[2].x, kc.c[3].x, kc.c[4].x, kc.c[5].x, kc.c[6].x, kc.c[7].x, f.w, v.x);
+                const float r1 = interp8<MODE>(kc.c[0].y, kc.c[1].y, kc.c[2].y, kc.c[3].y, kc.c[4].y, kc.c[5].y, kc.c[6].y, kc.c[7].y, f.w, v.y);
+                const float r2 = interp8<MODE>(kc.c[0].z, kc.c[1].z, kc.c[2].z, kc.c[3].z, kc.c[4].z, kc.c[5].z, kc.c[6].z, kc.c[7].z, f.w, v.z);
+                if (last) {
+                    float *o = L.out + (i64)t.b * 3 * S + off;
+                    o[0] = r0; o[S] = r1; o[2 * S] = r2;
+                } else {
+                    dst[(i64)t.b * S + off] = make_float4(r0, r1, r2, 0.0f);
+                }
+                v = vn;
+            }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(VI_FWD_THREADS, 1)
 vecint_fwd_kernel(const VMulti m, int nsteps, int save, float scale)
@@ -244,38 +284,10 @@ vecint_fwd_kernel(const VMulti m, int nsteps, int save, float scale)
             int lv = 0;
 #pragma unroll
             for (int j = 1; j < VI_MAXL; ++j) lv += (j < m.n && it >= m.l[j].item0) ? 1 : 0;
-            const VLevel &L = m.l[lv];
-            const VGeom &g = L.g;
-            const unsigned int N = g.N, S = g.S;
-            const int sy = g.D2, sz = g.D1 * g.D2;
-            const VStride vst = make_vstride(sy, sz);
-            const float4 *src = save ? L.ws + (i64)k * N : L.ws + (i64)(k & 1) * N;
-            float4 *dst = save ? L.ws + (i64)(k + 1) * N : L.ws + (i64)((k + 1) & 1) * N;
-            const Item t = decode_item(it - L.item0, g, lane);
-            if (!t.valid) continue;
-            const float yf = (float)t.y, xf = (float)t.x;
-            const float4 *vol = src + (i64)t.b * S;
-            int off = (t.z0 * g.D1 + t.y) * g.D2 + t.x;
-            float4 v = ld4v(vol + off);
-            Corners kc;
-            int prev_base = NOBASE;
-            for (int z = t.z0; z < t.z1; ++z, off += sz) {
-                float4 vn = v;
-                if (z + 1 < t.z1) vn = ld4v(vol + off + sz);   // the next plane's own value, ahead of this plane's gathers
-                const VFoot f = make_vfoot<MODE>((float)z, yf, xf, v, g);
-                gather8(vol, f.base, vst, f.base == prev_base + sz, kc);
-                prev_base = f.base;
-                const float r0 = interp8<MODE>(kc.c[0].x, kc.c[1].x, kc.c[2].x, kc.c[3].x, kc.c[4].x, kc.c[5].x, kc.c[6].x, kc.c[7].x, f.w, v.x);
-                const float r1 = interp8<MODE>(kc.c[0].y, kc.c[1].y, kc.c[2].y, kc.c[3].y, kc.c[4].y, kc.c[5].y, kc.c[6].y, kc.c[7].y, f.w, v.y);
-                const float r2 = interp8<MODE>(kc.c[0].z, kc.c[1].z, kc.c[2].z, kc.c[3].z, kc.c[4].z, kc.c[5].z, kc.c[6].z, kc.c[7].z, f.w, v.z);
-                if (last) {
-                    float *o = L.out + (i64)t.b * 3 * S + off;
-                    o[0] = r0; o[S] = r1; o[2 * S] = r2;
-                } else {
-                    dst[(i64)t.b * S + off] = make_float4(r0, r1, r2, 0.0f);
-                }
-                v = vn;
-            }
+            if (lv == 0)
+                vi_fwd_item<MODE, true>(m, 0, it, lane, k, save, last);
+            else
+                vi_fwd_item<MODE, false>(m, lv, it, lane, k, save, last);
         }
     }
     if (nsteps == 0) {
