@@ -82,7 +82,9 @@ size_t pulpo_vecint_ws_bytes(int nsteps, int save_steps, int B, int D0, int D1, 
 int pulpo_vecint_fwd(const float *vec, float *out, void *ws, size_t ws_bytes, int nsteps,
                      int save_steps, int B, int D0, int D1, int D2, int coord_mode,
                      pulpo_stream_t stream);
-/* gvec = d loss/d vec.  `saved` = the ws of a save_steps=1 forward; scratch: 3 rotating
+/* gvec = d loss/d vec.  Bits 8-9 of coord_mode select the scatter strategy (tuning; same result up to
+ * summation order): 0 = z-carried (default), 0x100 = one reduction per corner, 0x200 = lane + plane combining.
+ * `saved` = the ws of a save_steps=1 forward; scratch: 3 rotating
  * gradient states (pulpo_vecint_bwd_scratch_bytes). */
 size_t pulpo_vecint_bwd_scratch_bytes(int B, int D0, int D1, int D2);
 int pulpo_vecint_bwd(const float *gout, const void *saved, float *gvec, void *scratch,

@@ -47,7 +47,6 @@ __global__ void __launch_bounds__(NCC_THREADS, 2)
 ncc_box_kernel(const NccParams p)
 {
     constexpr int R = W / 2;
-    constexpr int NIN = FWD ? 2 : 3;
     constexpr int ROWS = NCC_TY + 2 * R;
     constexpr int SEGS = NCC_TX / NCC_XS;
     constexpr int NV = NCC_XS + 2 * R;  // inputs per item

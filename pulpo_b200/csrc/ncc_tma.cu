@@ -405,7 +405,7 @@ int ncc_tma_grid(int BC, int D0, int D1, int D2, int win)
     const long long want = planes / (2 * win);
     const long long cap = (long long)sms * NT_CTAS_PER_SM;
     const long long ncols = planes / D0;
-    if (!getenv("PULPO_NCC_LINEAR") && ncols <= cap && want >= cap) {   // aligned (column, z chunk) grid
+    if (ncols <= cap && want >= cap) {   // aligned (column, z chunk) grid
         const long long k = cap / ncols;
         if (k * ncols * 10 >= cap * 8) return (int)(k * ncols);          // keeps >= 80 % of the CTA slots busy
     }
@@ -416,7 +416,7 @@ int ncc_tma_grid(int BC, int D0, int D1, int D2, int win)
 static int ncc_tma_zchunks(int BC, int D0, int D1, int D2, int grid)
 {
     const long long ncols = (long long)BC * ((D2 + NT_TX - 1) / NT_TX) * ((D1 + NT_TY - 1) / NT_TY);
-    if (getenv("PULPO_NCC_LINEAR") || grid % ncols != 0) return 0;
+    if (grid % ncols != 0) return 0;
     int dev = 0, sms = kSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -501,7 +501,7 @@ extern "C" int pulpo_resize_up_fwd(const float *x, const float *addend, float *o
     PULPO_REQUIRE(B > 0 && C > 0 && d0 > 0 && d1 > 0 && d2 > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(factor >= 2 && factor <= 64, PULPO_ERR_UNSUPPORTED);
     if (factor == 2 && (d2 % 2 == 0) && aligned16(out) && (!addend || aligned16(addend)) &&
-        (i64)B * C * d0 * d1 * d2 < (1ll << 28) && !getenv("PULPO_UP2_FWD_OLD")) {
+        (i64)B * C * d0 * d1 * d2 < (1ll << 28)) {
         Up2FGeom g;
         g.BC = B * C; g.d0 = d0; g.d1 = d1; g.d2 = d2; g.XQ = d2 / 2;
         int dev = 0, sms = kSMs;
@@ -549,7 +549,7 @@ extern "C" int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, flo
     PULPO_REQUIRE(B > 0 && C > 0 && d0 > 0 && d1 > 0 && d2 > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(factor >= 2 && factor <= 64, PULPO_ERR_UNSUPPORTED);
     if (factor == 2 && (d2 % 2 == 0) && aligned16(gout) && aligned16(gx) && d0 >= 2 &&
-        (i64)B * C * d0 * d1 * d2 * 8 < (1ll << 31) && !getenv("PULPO_UP2_BWD_OLD")) {
+        (i64)B * C * d0 * d1 * d2 * 8 < (1ll << 31)) {
         Up2MGeom g;
         g.BC = B * C; g.d0 = d0; g.d1 = d1; g.d2 = d2;
         g.nxb = (d2 / 2 + 31) / 32;

@@ -478,16 +478,6 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
                     }
                     continue;
                 }
-                if (COMBINE == 3) continue;   // timing experiment only: no scatter at all
-                if (COMBINE == 4) {           // timing experiment only: plain stores instead of reductions
-                    if (t.valid) {
-                        float4 *q = acc + A;
-#pragma unroll
-                        for (int d = 0; d < 8; ++d)
-                            q[(d & 1) + ((d >> 1) & 1) * sy + (d >> 2) * sz] = make_float4(c[d].x, c[d].y, c[d].z, 0.f);
-                    }
-                    continue;
-                }
                 if (COMBINE == 2) {
                     // z-carry only: the four upper corners of the previous plane are this plane's lower corners
                     // whenever the footprint moved by exactly one plane -> 4 reductions per voxel, no shuffles
@@ -718,15 +708,15 @@ extern "C" int pulpo_vecint_multi_bwd(const pulpo_vecint_level *levels, int nlev
     float scale = 1.0f / (float)(1u << nsteps);
     void *args[] = {&m, &nsteps, &scale};
     cudaStream_t st = (cudaStream_t)stream;
-    // scatter strategy: default z-carry (2); 0x100 -> per-corner (0), 0x200 -> lane+plane combining (1);
-    // 0x300 / 0x400 -> timing experiments (no scatter / plain stores; wrong results)
-    const int comb = variant == 0 ? 2 : variant == 1 ? 0 : variant == 2 ? 1 : variant;
+    // scatter strategy (same result up to summation order): default z-carry (2); 0x100 -> one reduction per corner
+    // (0), 0x200 -> lane + plane combining (1)
+    PULPO_REQUIRE(variant <= 2, PULPO_ERR_UNSUPPORTED);
+    const int comb = variant == 0 ? 2 : variant == 1 ? 0 : 1;
 #define PULPO_VI_BWD_CASE(M, C) \
     if (coord_mode == M && comb == C) return launch_coop(vecint_bwd_kernel<M, C>, VI_BWD_THREADS, m, args, st);
     PULPO_VI_BWD_CASE(0, 2) PULPO_VI_BWD_CASE(1, 2) PULPO_VI_BWD_CASE(2, 2)
     PULPO_VI_BWD_CASE(0, 0) PULPO_VI_BWD_CASE(2, 0)
     PULPO_VI_BWD_CASE(0, 1) PULPO_VI_BWD_CASE(2, 1)
-    PULPO_VI_BWD_CASE(2, 3) PULPO_VI_BWD_CASE(2, 4)
 #undef PULPO_VI_BWD_CASE
     return PULPO_ERR_UNSUPPORTED;
 }
