@@ -43,15 +43,42 @@ UNIT = "Gvoxel/s"
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  The region is ~20 ms long (20 steps of
+    ~1 ms), far below nvidia-smi's 100 ms polling grain, so NVML is polled directly from a thread (~1 ms
+    period; the main thread sits in a CUDA synchronize and has released the GIL).  Falls back to
+    `nvidia-smi -lms` when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx, self.proc, self.lines = gpu_index, None, []
+        self.nvml, self.handle, self.samples, self.stop_flag, self.thread = None, None, [], False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append((n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM),
+                                     n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)))
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -65,6 +92,22 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            n = self.nvml
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = sorted(c for c, _ in self.samples)
+            mask = 0
+            for _, r in self.samples:
+                mask |= int(r)
+            names = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap))
+            try:
+                smax = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+            except Exception:
+                smax = None
+            return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": smax,
+                    "reasons": [k for k, bit in names if mask & bit], "samples": len(sm), "source": "nvml, 1 ms polling"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -85,7 +128,7 @@ class ClockSampler:
         busy = [v for v in sm if v > 0.5 * (max(sm) if sm else 1)]
         med = busy[len(busy) // 2] if busy else (sm[len(sm) // 2] if sm else None)
         return {"sm_mhz": med, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------ reference arm
