@@ -53,10 +53,13 @@ def make_pair(shape, seed=0, batch=1):
     return torch.stack(xs)[:, None].contiguous(), torch.stack(ys)[:, None].contiguous()
 
 
-def make_field(shape, seed=0, batch=1, max_abs=3.0, channels=3):
-    """Smooth random field [batch,channels,*shape], scaled so max|v| == max_abs voxels."""
+def make_field(shape, seed=0, batch=1, max_abs=3.0, channels=3, sigma_vox=None):
+    """Smooth random field [batch,channels,*shape], scaled so max|v| == max_abs voxels.  Default smoothing:
+    sigma = 8 * min(shape) / 160 voxels (>= 1), i.e. the same PHYSICAL length scale at every pyramid level;
+    ``sigma_vox`` fixes it in this grid's own voxels instead (coarser levels then carry smoother components,
+    as the levels of a real Laplacian pyramid do)."""
     gen = torch.Generator().manual_seed(1000 + seed)
-    sig = max(1.0, 8.0 * min(shape) / 160.0)
+    sig = float(sigma_vox) if sigma_vox is not None else max(1.0, 8.0 * min(shape) / 160.0)
     f = torch.stack([torch.stack([_smooth_noise(shape, sig, gen) for _ in range(channels)])
                      for _ in range(batch)])
     return (f * (max_abs / f.abs().max().clamp_min(1e-12))).contiguous()
@@ -70,7 +73,7 @@ def level_sizes(input_size, total_levels):
     return sizes
 
 
-def make_hot_path_inputs(input_size, total_levels, latent_levels, seed=0, batch=1, max_abs=3.0):
+def make_hot_path_inputs(input_size, total_levels, latent_levels, seed=0, batch=1, max_abs=3.0, field_sigma_vox=None):
     """Everything the hot path consumes for one step: x, y, and per latent level the
     velocity field (stand-in for the VelocityField conv output), mu and sigma."""
     x, y = make_pair(tuple(input_size), seed, batch)
@@ -79,7 +82,7 @@ def make_hot_path_inputs(input_size, total_levels, latent_levels, seed=0, batch=
     dfs, mus, sigmas = {}, {}, {}
     for l in range(latent_levels):
         s = tuple(sizes[l + lk])
-        dfs[l] = make_field(s, seed * 17 + l, batch, max_abs=max_abs)
+        dfs[l] = make_field(s, seed * 17 + l, batch, max_abs=max_abs, sigma_vox=field_sigma_vox)
         mus[l] = make_field(s, seed * 17 + 100 + l, batch, max_abs=1.5)
         g = torch.Generator().manual_seed(7000 + seed * 17 + l)
         sigmas[l] = (0.2 + 0.8 * torch.rand(batch, 3, *s, generator=g)).contiguous()

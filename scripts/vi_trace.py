@@ -14,7 +14,8 @@ shapes, B, n = [(80, 96, 112), (40, 48, 56), (20, 24, 28), (10, 12, 14)], 1, 7
 if len(sys.argv) > 1:
     shapes = shapes[:int(sys.argv[1])]
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-v = [syn.make_field(sh, 3 + i, max_abs=3.0).cuda() for i, sh in enumerate(shapes)]
+amps = [45.0, 21.0, 9.0, 3.0]   # magnitudes of the combined fields in the bench workload (3 voxels per level, summed coarse to fine)
+v = [syn.make_field(sh, 3 + i, max_abs=amps[i]).cuda() for i, sh in enumerate(shapes)]
 g = [syn.make_field(sh, 9 + i, max_abs=1.0).cuda() for i, sh in enumerate(shapes)]
 ws = [torch.empty(L.pulpo_vecint_ws_bytes(n, 1, B, *sh) // 4, device="cuda") for sh in shapes]
 scr = [torch.empty(L.pulpo_vecint_bwd_scratch_bytes(B, *sh) // 4, device="cuda") for sh in shapes]
