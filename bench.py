@@ -265,7 +265,7 @@ def run_ours(args):
     nvox = size[0] * size[1] * size[2]
     B = args.batch
     x_h, y_h, d_h, m_h, s_h = syn.make_hot_path_inputs(size, total, latent, seed=rank, batch=B,
-                                                       field_sigma_vox=args.field_sigma_vox)
+                                                       field_sigma_vox=args.field_sigma_vox, max_abs=args.field_max_abs)
     host = [x_h, y_h] + [d_h[l] for l in range(latent)] + [m_h[l] for l in range(latent)] + [s_h[l] for l in range(latent)]
     host = [t.pin_memory() for t in host]
     h2d_bytes = sum(t.numel() * 4 for t in host)
@@ -505,7 +505,7 @@ def run_ours(args):
                        "levels": "%d total / %d latent, level_res, 7 integration steps" % (total, latent),
                        "launch": launch_mode, "engine": args.engine, "parallelism": "pairs sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "per-step working set ~1.5 GB >> 126 MB L2; no explicit flush",
-                       "velocity_fields": "smooth N(0,1), max |v| = 3 voxels per level, sigma = %s" % (
+                       "velocity_fields": "smooth N(0,1), max |v| = %g voxels per level, sigma = %s" % (args.field_max_abs,
                            "%g voxels of each level's grid" % args.field_sigma_vox if args.field_sigma_vox is not None
                            else "8 full-res voxels at every level")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
@@ -548,6 +548,9 @@ def main():
     ap.add_argument("--field-sigma-vox", type=float, default=None,
                     help="smoothing of the synthetic velocity fields in each level's own voxels (default: the same physical "
                          "length scale at every level, 8 full-resolution voxels, which makes the combined field fold)")
+    ap.add_argument("--field-max-abs", type=float, default=3.0,
+                    help="max |v| of every level's synthetic velocity field in that level's voxels (SURVEY 8d: 3; the "
+                         "coarse-to-fine sum then reaches ~45 level-0 voxels)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
