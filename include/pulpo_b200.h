@@ -167,6 +167,21 @@ size_t pulpo_kl_multi_ws_bytes(void);
 int pulpo_kl_n01_multi(const pulpo_kl_level *levels, int nlevels, float eps, int B, void *ws,
                        size_t ws_bytes, pulpo_stream_t stream);
 
+/* ---- f-4: gauss_sampler (src/network_blocks.py:7-8) fused with the level's KL term (src/losses.py:47-76):
+ * z = mu + sigma * (var * noise) and out = weight * KL[N(mu, sigma) || N(mu1, sigma1)] (batch mean; mu1 / sigma1
+ * nullable = N(0,1)) from one read of mu and sigma.  `noise` is the caller's N(0,1) draw (torch.randn), so the
+ * samples are the reference's for the same generator state.  ws: pulpo_reduce_ws_bytes(), zeroed once. */
+int pulpo_gauss_sample_kl_fwd(const float *mu, const float *sigma, const float *noise, const float *mu1,
+                              const float *sigma1, float var, float eps, float weight, float *z,
+                              float *out, void *ws, size_t ws_bytes, int B, long long n,
+                              pulpo_stream_t stream);
+/* gmu = gz + gloss * dKL/dmu, gsigma = gz * var * noise + gloss * dKL/dsigma.  gz nullable (= 0);
+ * gloss: device scalar, nullable = 1; have_kl == 0 drops the KL part (the loss was not used). */
+int pulpo_gauss_sample_kl_bwd(const float *gz, const float *gloss, int have_kl, const float *mu,
+                              const float *sigma, const float *noise, const float *mu1,
+                              const float *sigma1, float var, float eps, float weight, float *gmu,
+                              float *gsigma, int B, long long n, pulpo_stream_t stream);
+
 /* ---- f-1: L2_reg(deformation_field, lamb)   src/losses.py:208-222 (3-D branch) ------------- */
 int pulpo_l2reg_fwd(const float *f, float lamb, float *out, void *ws, size_t ws_bytes,
                     int B, int C, int D0, int D1, int D2, pulpo_stream_t stream);

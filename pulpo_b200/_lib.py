@@ -54,6 +54,8 @@ SIGNATURES = {
     "pulpo_reduce_ws_bytes": (_sz, []),
     "pulpo_kl_diag_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _sz, _i, _ll, _vp]),
     "pulpo_kl_diag_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _ll, _vp]),
+    "pulpo_gauss_sample_kl_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _sz, _i, _ll, _vp]),
+    "pulpo_gauss_sample_kl_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _i, _ll, _vp]),
     "pulpo_kl_multi_ws_bytes": (_sz, []),
     "pulpo_kl_n01_multi": (_i, [ctypes.POINTER(KlLevel), _i, _f, _i, _vp, _sz, _vp]),
     "pulpo_l2reg_fwd": (_i, [_vp, _f, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),

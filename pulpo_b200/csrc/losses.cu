@@ -62,6 +62,65 @@ kl_bwd_kernel(const float *__restrict__ gloss, const float *__restrict__ mu0, co
     }
 }
 
+// ---- f-4: gauss_sampler (src/network_blocks.py:7-8) fused with the level's KL term (src/losses.py:47-76,
+// call order :271-273): z = mu + sigma * (var * noise) and KL[N(mu, sigma) || p1] from ONE read of mu, sigma.
+// The noise is an input (torch's Philox stream stays the source of randomness, so the samples are the
+// reference's for the same generator state).
+__global__ void __launch_bounds__(256)
+gauss_kl_fwd_kernel(const float *__restrict__ mu, const float *__restrict__ sg, const float *__restrict__ noise,
+                    const float *__restrict__ mu1, const float *__restrict__ sg1, float var, float eps,
+                    float *__restrict__ z, float *out, ReduceWs *ws, double scale, i64 total, int vec)
+{
+    __shared__ double red[32];
+    float acc = 0.0f;
+    const i64 tid = blockIdx.x * (i64)blockDim.x + threadIdx.x, nthr = (i64)gridDim.x * blockDim.x;
+    if (vec) {
+        for (i64 i = tid * 4; i < total; i += nthr * 4) {
+            const float4 m = ld_stream4(mu + i), s = ld_stream4(sg + i), e = ld_stream4(noise + i);
+            const float4 m1 = mu1 ? ld_stream4(mu1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 s1 = sg1 ? ld_stream4(sg1 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+            float4 o;
+            o.x = __fadd_rn(m.x, __fmul_rn(s.x, __fmul_rn(var, e.x)));
+            o.y = __fadd_rn(m.y, __fmul_rn(s.y, __fmul_rn(var, e.y)));
+            o.z = __fadd_rn(m.z, __fmul_rn(s.z, __fmul_rn(var, e.z)));
+            o.w = __fadd_rn(m.w, __fmul_rn(s.w, __fmul_rn(var, e.w)));
+            *reinterpret_cast<float4 *>(z + i) = o;
+            float t = kl_term(m.x, s.x, m1.x, s1.x, eps);
+            t += kl_term(m.y, s.y, m1.y, s1.y, eps);
+            t += kl_term(m.z, s.z, m1.z, s1.z, eps);
+            t += kl_term(m.w, s.w, m1.w, s1.w, eps);
+            acc += t;
+        }
+    } else {
+        for (i64 i = tid; i < total; i += nthr) {
+            const float m = mu[i], s = sg[i];
+            z[i] = __fadd_rn(m, __fmul_rn(s, __fmul_rn(var, noise[i])));
+            acc += kl_term(m, s, mu1 ? mu1[i] : 0.0f, sg1 ? sg1[i] : 1.0f, eps);
+        }
+    }
+    double bt = block_sum((double)acc, red);
+    grid_reduce_finish(bt, ws, out, scale, red);
+}
+
+// gmu = gz + gloss * dKL/dmu,  gsigma = gz * var * noise + gloss * dKL/dsigma   (gz, gloss nullable)
+__global__ void __launch_bounds__(256)
+gauss_kl_bwd_kernel(const float *__restrict__ gz, const float *__restrict__ gloss, const float *__restrict__ mu,
+                    const float *__restrict__ sg, const float *__restrict__ noise, const float *__restrict__ mu1,
+                    const float *__restrict__ sg1, float var, float eps, float *__restrict__ gmu,
+                    float *__restrict__ gsg, float k0, int have_kl, i64 total)
+{
+    const float k = have_kl ? (gloss ? __ldg(gloss) : 1.0f) * k0 : 0.0f;
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+        const float s = sg[i];
+        const float s1 = sg1 ? sg1[i] : 1.0f;
+        const float m1 = mu1 ? mu1[i] : 0.0f;
+        const float den = s1 * s1 + eps;
+        const float g = gz ? gz[i] : 0.0f;
+        gmu[i] = g + k * (mu[i] - m1) / den;
+        gsg[i] = g * (var * noise[i]) + k * (s / den - s / (s * s + eps));
+    }
+}
+
 // ---- all pyramid levels, value and gradients, in ONE launch (HotPathPlan: the KL terms have no data
 // dependence on anything else in the step, so eight tiny launches become one streaming pass that reads
 // mu / sigma once).  N(0,1) prior only (src/components/pulpo.py:337-339).
@@ -308,6 +367,36 @@ extern "C" int pulpo_kl_diag_fwd(const float *mu0, const float *sigma0, const fl
     int grid = grid_for((total + 3) / 4, 256, 4);
     kl_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mu0, sigma0, mu1, sigma1, eps, out, (ReduceWs *)ws,
                                                         0.5 * (double)weight / (double)B, total, (al && (total & 3) == 0) ? 1 : 0);
+    return launch_status();
+}
+
+extern "C" int pulpo_gauss_sample_kl_fwd(const float *mu, const float *sigma, const float *noise, const float *mu1,
+                                        const float *sigma1, float var, float eps, float weight, float *z, float *out,
+                                        void *ws, size_t ws_bytes, int B, long long n, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(mu && sigma && noise && z && out && ws, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && n > 0, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(ws_bytes >= kReduceWsBytes, PULPO_ERR_WORKSPACE);
+    const i64 total = (i64)B * n;
+    bool al = aligned16(mu) && aligned16(sigma) && aligned16(noise) && aligned16(z) && (!mu1 || aligned16(mu1)) &&
+              (!sigma1 || aligned16(sigma1));
+    int grid = grid_for((total + 3) / 4, 256, 4);
+    gauss_kl_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mu, sigma, noise, mu1, sigma1, var, eps, z, out,
+                                                              (ReduceWs *)ws, 0.5 * (double)weight / (double)B, total,
+                                                              (al && (total & 3) == 0) ? 1 : 0);
+    return launch_status();
+}
+
+extern "C" int pulpo_gauss_sample_kl_bwd(const float *gz, const float *gloss, int have_kl, const float *mu,
+                                        const float *sigma, const float *noise, const float *mu1, const float *sigma1,
+                                        float var, float eps, float weight, float *gmu, float *gsigma, int B,
+                                        long long n, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(mu && sigma && noise && gmu && gsigma, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && n > 0, PULPO_ERR_INVALID_SHAPE);
+    const i64 total = (i64)B * n;
+    gauss_kl_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        gz, gloss, mu, sigma, noise, mu1, sigma1, var, eps, gmu, gsigma, weight / (float)B, have_kl, total);
     return launch_status();
 }
 

@@ -362,6 +362,61 @@ def kl_diag(mu0, sigma0, mu1, sigma1, eps=1e-10):
     return _KL.apply(mu0, sigma0, mu1, sigma1, eps)
 
 
+class _GaussSampleKL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, sigma, noise, mu1, sigma1, var, eps):
+        mu, sigma, noise = _prep(mu, "mu"), _prep(sigma, "sigma"), _prep(noise, "noise")
+        if sigma.shape != mu.shape or noise.shape != mu.shape:
+            raise RuntimeError("pulpo_b200.gauss_sample_kl: mu, sigma and noise must have one shape")
+        mu1 = None if mu1 is None else _prep(mu1, "mu1")
+        sigma1 = None if sigma1 is None else _prep(sigma1, "sigma1")
+        B = int(mu.shape[0])
+        n = mu.numel() // B
+        L = _lib.lib()
+        ws = _workspace(L.pulpo_reduce_ws_bytes(), mu.device)
+        z = torch.empty_like(mu)
+        out = torch.empty((), dtype=torch.float32, device=mu.device)
+        check(L.pulpo_gauss_sample_kl_fwd(_ptr(mu), _ptr(sigma), _ptr(noise), _ptr(mu1), _ptr(sigma1), float(var),
+                                          float(eps), 1.0, _ptr(z), _ptr(out), _ptr(ws), ws.numel(), B, n, _stream()),
+              "gauss_sample_kl_fwd")
+        ctx.var, ctx.eps, ctx.B, ctx.n = float(var), float(eps), B, n
+        ctx.have1 = (mu1 is not None, sigma1 is not None)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(mu, sigma, noise, *[t for t in (mu1, sigma1) if t is not None])
+        return z, out
+
+    @staticmethod
+    def backward(ctx, gz, gloss):
+        saved = list(ctx.saved_tensors)
+        mu, sigma, noise = saved[:3]
+        rest = saved[3:]
+        mu1 = rest.pop(0) if ctx.have1[0] else None
+        sigma1 = rest.pop(0) if ctx.have1[1] else None
+        gz = None if gz is None else gz.to(torch.float32).contiguous()
+        have_kl = gloss is not None
+        gloss = None if gloss is None else gloss.to(torch.float32).contiguous()
+        gmu, gsg = torch.empty_like(mu), torch.empty_like(sigma)
+        check(_lib.lib().pulpo_gauss_sample_kl_bwd(_ptr(gz), _ptr(gloss), int(have_kl), _ptr(mu), _ptr(sigma),
+                                                   _ptr(noise), _ptr(mu1), _ptr(sigma1), ctx.var, ctx.eps, 1.0,
+                                                   _ptr(gmu), _ptr(gsg), ctx.B, ctx.n, _stream()),
+              "gauss_sample_kl_bwd")
+        return gmu, gsg, None, None, None, None, None
+
+
+def gauss_sample_kl(mu, sigma, noise, mu1=None, sigma1=None, var=1, eps=1e-10):
+    """gauss_sampler (src/network_blocks.py:7-8) and KL_two_gauss_with_diag_cov(mu, sigma, mu1, sigma1)
+    (src/losses.py:47-76) in one pass over mu and sigma (SURVEY f-4).  Returns (z, kl); both are
+    differentiable w.r.t. mu and sigma, and one fused backward serves whichever of them is used."""
+    for t in (mu1, sigma1):
+        if t is not None and t.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("pulpo_b200: KL gradient w.r.t. the second distribution is not implemented")
+    if _const_value(mu1) == 0.0:
+        mu1 = None
+    if _const_value(sigma1) == 1.0:
+        sigma1 = None
+    return _GaussSampleKL.apply(mu, sigma, noise, mu1, sigma1, var, eps)
+
+
 # ----------------------------------------------------------------------------- L2 reg (f-1)
 class _L2Reg(torch.autograd.Function):
     @staticmethod

@@ -8,7 +8,7 @@ INTEGRATION.md), but every forward/backward runs in libpulpo_b200's sm_100a kern
     ResizeTransform     <- src/network_blocks.py:124-150
     DFAdder             <- src/network_blocks.py:152-158
     VecInt              <- src/network_blocks.py:160-177
-    gauss_sampler       <- src/network_blocks.py:7-8
+    gauss_sampler       <- src/network_blocks.py:7-8   (gauss_sampler_kl: fused with the level's KL, f-4)
 
 Only ndims == 3 and CUDA fp32 tensors are implemented; anything else raises (no fallback).
 """
@@ -29,6 +29,17 @@ def gauss_sampler(mu: torch.Tensor, sigma: torch.Tensor, var: Optional[int] = 1,
     reproducible: sample i always uses seed0 + i whichever rank draws it."""
     noise = torch.randn(sigma.shape, dtype=torch.float32, device=sigma.device, generator=generator)
     return mu + sigma * (var * noise)
+
+
+def gauss_sampler_kl(mu: torch.Tensor, sigma: torch.Tensor, var: Optional[int] = 1,
+                     generator: Optional[torch.Generator] = None, prior_mu: Optional[torch.Tensor] = None,
+                     prior_sigma: Optional[torch.Tensor] = None, eps: float = 1e-10):
+    """``gauss_sampler`` plus the level's KL[N(mu, sigma) || prior] (prior None = N(0,1), the reference's
+    PULPoPrior) from one read of mu and sigma (SURVEY f-4).  Draws the same noise as ``gauss_sampler`` for
+    the same generator state.  Returns ``(z, kl)``; ``kl`` is what
+    ``KL_two_gauss_with_diag_cov(mu, sigma, prior_mu, prior_sigma)`` returns."""
+    noise = torch.randn(sigma.shape, dtype=torch.float32, device=sigma.device, generator=generator)
+    return PF.gauss_sample_kl(mu, sigma, noise, prior_mu, prior_sigma, var, eps)
 
 
 def _drop_grid_key(module, state_dict, prefix, *args):

@@ -310,6 +310,50 @@ def test_kl_golden(PF):
     assert_loss_close(PF.kl_diag(mu, sg, pm[0], ps[0]).item(), g["kl_std"], "kl fast path")
 
 
+def test_gauss_sample_kl_fused(PF):
+    """f-4: gauss_sampler fused with the level's KL == the two separate reference expressions
+    (src/network_blocks.py:7-8, src/losses.py:47-76) on the golden KL inputs: z bitwise for the same
+    noise, KL and the joint gradient within the loss / gradient tolerances; ragged and aligned sizes."""
+    from pulpo_b200 import network_blocks as NB
+    g = load_golden("kl_diag")
+    for tag, m1, s1 in [("std", None, None), ("gen", g["mu1"], g["sigma1"])]:
+        mu, sg = dev(g["mu0"], True), dev(g["sigma0"], True)
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        noise = torch.randn(sg.shape, dtype=torch.float32, device="cuda", generator=gen)
+        gen.manual_seed(5)
+        z, kl = NB.gauss_sampler_kl(mu, sg, var=1, generator=gen, prior_mu=None if m1 is None else dev(m1),
+                                    prior_sigma=None if s1 is None else dev(s1))
+        z_ref = mu.detach() + sg.detach() * (1 * noise)
+        assert torch.equal(z, z_ref), "fused sample differs from mu + sigma * (var * noise)"
+        assert_loss_close(kl.item(), g["kl_" + tag], "fused kl " + tag)
+        w = torch.randn(z.shape, device="cuda", generator=gen)
+        ((z * w).sum() + kl).backward()
+        assert_grad_close(mu.grad.cpu().numpy(), g["gmu0_" + tag] + w.cpu().numpy(), "fused gmu " + tag)
+        assert_grad_close(sg.grad.cpu().numpy(), g["gsigma0_" + tag] + (w * noise).cpu().numpy(), "fused gsigma " + tag)
+    # only one of the two outputs used; ragged length (scalar path); var != 1
+    for shape in [(2, 3, 5, 7, 9), (1, 3, 8, 8, 8)]:
+        gen = torch.Generator(device="cuda").manual_seed(1)
+        mu0 = torch.randn(shape, device="cuda", generator=gen)
+        sg0 = torch.rand(shape, device="cuda", generator=gen) + 0.1
+        noise = torch.randn(shape, device="cuda", generator=gen)
+        mu, sg = mu0.clone().requires_grad_(True), sg0.clone().requires_grad_(True)
+        z, kl = PF.gauss_sample_kl(mu, sg, noise, var=2)
+        assert torch.equal(z, mu0 + sg0 * (2 * noise))
+        kl_sep = PF.kl_diag(mu0, sg0, None, None)
+        assert_loss_close(kl.item(), kl_sep.item(), "fused kl vs separate")
+        z.sum().backward()
+        assert torch.equal(mu.grad, torch.ones_like(mu0)) and torch.equal(sg.grad, 2 * noise)
+        mu2, sg2 = mu0.clone().requires_grad_(True), sg0.clone().requires_grad_(True)
+        mu3, sg3 = mu0.clone().requires_grad_(True), sg0.clone().requires_grad_(True)
+        PF.gauss_sample_kl(mu2, sg2, noise)[1].backward()
+        PF.kl_diag(mu3, sg3, None, None).backward()
+        torch.testing.assert_close(mu2.grad, mu3.grad, rtol=1e-6, atol=0)
+        torch.testing.assert_close(sg2.grad, sg3.grad, rtol=1e-6, atol=1e-7)
+    with torch.no_grad():
+        z, kl = PF.gauss_sample_kl(mu0, sg0, noise)
+        assert not z.requires_grad and torch.isfinite(kl)
+
+
 def test_l2reg_golden(PF):
     g = load_golden("l2reg")
     f = dev(g["f"], True)
