@@ -511,6 +511,33 @@ def test_plan_golden(PF, multi_stream, graph, fuse_reg):
         assert_grad_close(plan.gsigma[l].cpu().numpy(), g["gsigma%d" % l], "gsigma %d" % l)
 
 
+def test_plan_full_size_config2_vs_torch_oracle(PF):
+    """The benchmarked configuration itself (BASELINE config 2: 160x192x224 pair, 5 total / 4 latent levels,
+    bench.py's synthetic inputs, fused regulariser, CUDA graph) against the torch-CPU restatement at FULL size:
+    losses, moved images, final fields and every input gradient (a few seconds of CPU time)."""
+    from oracle import torch_ref as T
+    from pulpo_b200 import synthetic as syn
+    size, total, latent = [160, 192, 224], 5, 4
+    x, y, dfs, mus, sgs = syn.make_hot_path_inputs(size, total, latent, seed=0)
+    d_ref = {l: dfs[l].clone().requires_grad_(True) for l in dfs}
+    m_ref = {l: mus[l].clone().requires_grad_(True) for l in dfs}
+    s_ref = {l: sgs[l].clone().requires_grad_(True) for l in dfs}
+    ref_total, ref_parts, ref_out = T.hot_path_losses(x, y, d_ref, m_ref, s_ref, total)
+    ref_total.backward()
+    plan = _run_plan((x.cuda(), y.cuda(), {l: dfs[l].cuda() for l in dfs}, {l: mus[l].cuda() for l in dfs},
+                      {l: sgs[l].cuda() for l in dfs}), total, latent, size, 1, True, True, fuse_reg=True)
+    losses = plan.losses.sum(dim=1).cpu().numpy()
+    for i, k in enumerate(("kl", "recon", "reg")):
+        assert_loss_close(losses[i], ref_parts[k].item(), k)
+    assert_loss_close(plan.total.item(), ref_total.item(), "total")
+    for l in range(latent):
+        assert_close(plan.moved[l].cpu().numpy(), ref_out["moved"][l].detach().numpy(), FIELD_ATOL, "moved %d" % l)
+        assert_close(plan.final[l].cpu().numpy(), ref_out["final"][l].detach().numpy(), FIELD_ATOL, "final %d" % l)
+        assert_grad_close(plan.gdf[l].cpu().numpy(), d_ref[l].grad.numpy(), "gdf %d" % l)
+        assert_grad_close(plan.gmu[l].cpu().numpy(), m_ref[l].grad.numpy(), "gmu %d" % l)
+        assert_grad_close(plan.gsigma[l].cpu().numpy(), s_ref[l].grad.numpy(), "gsigma %d" % l)
+
+
 def test_plan_matches_autograd_modules_config1(PF):
     """The planned multi-stream path and the autograd drop-in modules are the same arithmetic."""
     from pulpo_b200 import synthetic as syn
