@@ -239,7 +239,7 @@ def run_reference(args):
                        "note": "reference PyTorch CPU path on host cores; rank 0 only"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -257,7 +257,11 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- pulpo_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = {"bound": False}
     if world > 1:
+        # one process per GPU: keep this rank's threads and pinned host buffers on its GPU's NUMA node
+        from pulpo_b200.hostmem import bind_to_gpu_numa
+        numa = bind_to_gpu_numa(local)
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()   # fail loudly if the CUDA library is missing
 
@@ -509,7 +513,8 @@ def run_ours(args):
                            "%g voxels of each level's grid" % args.field_sigma_vox if args.field_sigma_vox is not None
                            else "8 full-res voxels at every level")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "api": e2e_api},
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "api": e2e_api,
+                    "host_numa_binding": numa},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "clocks": clk,
@@ -529,9 +534,29 @@ def run_ours(args):
                                                        "kernels on this GPU, fp32, TF32 off; context only" % torch.__version__}
             except Exception as e:  # pragma: no cover
                 line["torch_cuda_baseline"] = {"value": None, "what": "failed: %r" % (e,)}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write banners there too (NCCL prints its version
+    on the first communicator when NCCL_DEBUG is set), so keep the real stdout for the result line and
+    point fd 1 at stderr for everything else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -554,6 +579,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
