@@ -268,6 +268,8 @@ def run_ours(args):
     size, total, latent = WORKLOADS[args.workload]
     nvox = size[0] * size[1] * size[2]
     B = args.batch
+    plan_kw = dict(fuse_reg=bool(args.fuse_reg), fuse_combine=bool(args.fuse_combine), pool_pyramid=bool(args.pool_pyramid),
+                   aux_early=bool(args.aux_early))
     x_h, y_h, d_h, m_h, s_h = syn.make_hot_path_inputs(size, total, latent, seed=rank, batch=B,
                                                        field_sigma_vox=args.field_sigma_vox, max_abs=args.field_max_abs)
     host = [x_h, y_h] + [d_h[l] for l in range(latent)] + [m_h[l] for l in range(latent)] + [s_h[l] for l in range(latent)]
@@ -290,7 +292,7 @@ def run_ours(args):
     plan = None
     if args.engine == "plan":
         from pulpo_b200.plan import HotPathPlan
-        plan = HotPathPlan(size, total, latent, batch=B, device=dev, fuse_reg=bool(args.fuse_reg))
+        plan = HotPathPlan(size, total, latent, batch=B, device=dev, **plan_kw)
         dd = {l: d[l].detach() for l in d}
         mm = {l: m[l].detach() for l in m}
         ss = {l: s[l].detach() for l in s}
@@ -404,7 +406,7 @@ def run_ours(args):
         # HotPathPipeline: one packed pinned buffer per step -> one H2D copy on a copy stream, double-buffered
         # against the graph-replayed compute; the loss scalars are read back (D2H) for every step
         from pulpo_b200.pipeline import HotPathPipeline
-        pipe = HotPathPipeline(size, total, latent, batch=B, device=dev, fuse_reg=bool(args.fuse_reg))
+        pipe = HotPathPipeline(size, total, latent, batch=B, device=dev, **plan_kw)
         hbs = [pipe.host_batch().fill(x_h, y_h, d_h, m_h, s_h) for _ in range(2)]
         h2d_bytes, d2h_bytes = pipe.h2d_bytes, 16
         e2e_api = "pulpo_b200.pipeline.HotPathPipeline.submit/result (packed pinned batch, copy/compute overlap)"
@@ -449,7 +451,7 @@ def run_ours(args):
     prof_step = step
     if plan is not None:
         from pulpo_b200.plan import HotPathPlan
-        plan1 = HotPathPlan(size, total, latent, batch=B, device=dev, multi_stream=False, fuse_reg=bool(args.fuse_reg))
+        plan1 = HotPathPlan(size, total, latent, batch=B, device=dev, multi_stream=False, **plan_kw)
         prof_step = lambda: plan1.run(x, y, dd, mm, ss)
         prof_step()
         torch.cuda.synchronize()
@@ -570,6 +572,9 @@ def main():
     ap.add_argument("--engine", default="plan", choices=["plan", "autograd"],
                     help="plan: pre-planned multi-stream C-ABI sequence; autograd: the drop-in nn.Modules")
     ap.add_argument("--fuse-reg", type=int, default=1, help="plan engine: L2_reg fused into the warp kernels (1) or separate kernels (0)")
+    ap.add_argument("--fuse-combine", type=int, default=0, help="plan engine: pyramid combination inside the integration launches (1) or separate launches (0)")
+    ap.add_argument("--pool-pyramid", type=int, default=1, help="plan engine: moving-image pyramid in one launch (1) or one launch per level (0)")
+    ap.add_argument("--aux-early", type=int, default=0, help="plan engine: pyramid + KL start with the step (1) or after the integration (0)")
     ap.add_argument("--field-sigma-vox", type=float, default=None,
                     help="smoothing of the synthetic velocity fields in each level's own voxels (default: the same physical "
                          "length scale at every level, 8 full-resolution voxels, which makes the combined field fold)")

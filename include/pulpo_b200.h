@@ -110,6 +110,23 @@ int pulpo_vecint_multi_fwd(const pulpo_vecint_level *levels, int nlevels, int ns
 int pulpo_vecint_multi_bwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int B,
                            int coord_mode, pulpo_stream_t stream);
 
+/* a6/a7 + a3 in one launch: the coarse-to-fine combination of the Laplacian pyramid
+ * (SVFDecoder.forward, src/components/pulpo.py:308; PULPo.combine_dfs, src/models.py:356-367)
+ * folded into the integration launch.  levels[] is a x2 pyramid ordered fine to coarse (level l exactly
+ * twice the size of level l+1); indiv: HOST array of nlevels device pointers, the levels' individual fields.
+ * Forward: combined_l = 2 * up2(combined_{l+1}) + indiv[l] is WRITTEN to levels[l].in for l < nlevels-1
+ * (the coarsest combined field is indiv[nlevels-1] itself; its levels[].in is not touched) and integrated
+ * into levels[l].out.  Backward: levels[l].in = gradient w.r.t. the integrated field, levels[l].out =
+ * gradient w.r.t. indiv[l] (= w.r.t. combined_l), including 2 * up2^T of the finer level's.
+ * Six fewer launches per step; at config 2 the separate launches are nevertheless faster (they overlap
+ * with the other streams' work, the in-kernel phases are latency-bound on the cooperative grid), so
+ * HotPathPlan uses this only on request (fuse_combine=True). */
+int pulpo_combine_vecint_multi_fwd(const pulpo_vecint_level *levels, const float *const *indiv,
+                                   int nlevels, int nsteps, int save_steps, int B, int coord_mode,
+                                   pulpo_stream_t stream);
+int pulpo_combine_vecint_multi_bwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int B,
+                                   int coord_mode, pulpo_stream_t stream);
+
 /* ---- a4 + a5: ResizeTransform.forward (factor>1) fused with DFAdder.forward ---------------
  * src/network_blocks.py:138-150, :152-158; used at src/components/pulpo.py:308,314 and
  * src/models.py:356-367.   out = trilinear_up_f(scale * x) (+ addend),  x: [B,C,d0,d1,d2],
@@ -128,6 +145,12 @@ int pulpo_interp_size_fwd(const float *x, float *out, int B, int C, int i0, int 
 /* ---- a8: avg_pool3d(2, 2, ceil_mode=True)  src/components/pulpo.py:171-179 ---------------- */
 int pulpo_avgpool2_fwd(const float *x, float *out, int B, int C, int D0, int D1, int D2,
                        pulpo_stream_t stream);
+/* The whole moving-image pyramid in one launch: outs[i] (HOST array of nlevels <= 4 device pointers) =
+ * avg_pool3d(2,2) applied i+1 times; the input is read once.  Needs D0, D1, D2 divisible by 2^nlevels
+ * (by 4 for nlevels == 1) and a 16-byte aligned x, else PULPO_ERR_UNSUPPORTED: use pulpo_avgpool2_fwd per
+ * level.  Bit-identical to the chain of pulpo_avgpool2_fwd calls. */
+int pulpo_avgpool2_pyramid_fwd(const float *x, float *const *outs, int nlevels, int B, int C, int D0,
+                               int D1, int D2, pulpo_stream_t stream);
 
 /* ---- a9: NCC_loss(y_pred, y_true, win_size, gamma)   src/losses.py:85-135 ------------------
  * loss (device scalar) = -gamma/B * sum cc.  abc (nullable): [3][B,C,S] coefficient volumes

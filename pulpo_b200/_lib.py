@@ -44,10 +44,13 @@ SIGNATURES = {
     "pulpo_vecint_bwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_vecint_multi_fwd": (_i, [ctypes.POINTER(VecIntLevel), _i, _i, _i, _i, _i, _vp]),
     "pulpo_vecint_multi_bwd": (_i, [ctypes.POINTER(VecIntLevel), _i, _i, _i, _i, _vp]),
+    "pulpo_combine_vecint_multi_fwd": (_i, [ctypes.POINTER(VecIntLevel), ctypes.POINTER(ctypes.c_void_p), _i, _i, _i, _i, _i, _vp]),
+    "pulpo_combine_vecint_multi_bwd": (_i, [ctypes.POINTER(VecIntLevel), _i, _i, _i, _i, _vp]),
     "pulpo_resize_up_fwd": (_i, [_vp, _vp, _vp, _i, _f, _i, _i, _i, _i, _i, _vp]),
     "pulpo_resize_up_bwd": (_i, [_vp, _vp, _i, _f, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_interp_size_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_avgpool2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_avgpool2_pyramid_fwd": (_i, [_vp, ctypes.POINTER(ctypes.c_void_p), _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_ncc_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "pulpo_ncc_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _f, _i, _i, _i, _i, _i, _vp]),
     "pulpo_ncc_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _i, _i, _i, _i, _vp]),

@@ -129,6 +129,7 @@ struct KlLevel {
     const float *mu, *sg;
     float *gmu, *gsg, *out;
     i64 total;      // B * n
+    int vec;        // total % 4 == 0 and all four pointers 16-byte aligned
     float k;        // weight / B : scale of the gradients
     double scale;   // 0.5 * weight / B : scale of the value
 };
@@ -151,11 +152,44 @@ kl_multi_kernel(const KlMulti m, float eps, KlMultiWs *ws)
     for (int lv = 0; lv < m.n; ++lv) {
         const KlLevel &L = m.l[lv];
         float acc = 0.0f;
-        for (i64 i = tid; i < L.total; i += nthr) {
-            const float mu = __ldg(L.mu + i), s = __ldg(L.sg + i);
-            acc += kl_term(mu, s, 0.0f, 1.0f, eps);
-            L.gmu[i] = L.k * mu / den;
-            L.gsg[i] = L.k * (s / den - s / (s * s + eps));
+        if (L.vec) {   // 128-bit accesses, two quads in flight per thread (the scalar loop is latency-bound)
+            const i64 nq = L.total >> 2;
+            for (i64 q = tid; q < nq; q += 2 * nthr) {
+                const i64 q1 = q + nthr;
+                const bool two = q1 < nq;
+                const float4 m0 = ld_stream4(L.mu + 4 * q), s0 = ld_stream4(L.sg + 4 * q);
+                const float4 m1 = two ? ld_stream4(L.mu + 4 * q1) : m0, s1 = two ? ld_stream4(L.sg + 4 * q1) : s0;
+                float4 gm, gs;
+                float t = kl_term(m0.x, s0.x, 0.0f, 1.0f, eps);
+                t += kl_term(m0.y, s0.y, 0.0f, 1.0f, eps);
+                t += kl_term(m0.z, s0.z, 0.0f, 1.0f, eps);
+                t += kl_term(m0.w, s0.w, 0.0f, 1.0f, eps);
+                acc += t;
+                gm.x = L.k * m0.x / den; gm.y = L.k * m0.y / den; gm.z = L.k * m0.z / den; gm.w = L.k * m0.w / den;
+                gs.x = L.k * (s0.x / den - s0.x / (s0.x * s0.x + eps)); gs.y = L.k * (s0.y / den - s0.y / (s0.y * s0.y + eps));
+                gs.z = L.k * (s0.z / den - s0.z / (s0.z * s0.z + eps)); gs.w = L.k * (s0.w / den - s0.w / (s0.w * s0.w + eps));
+                *reinterpret_cast<float4 *>(L.gmu + 4 * q) = gm;
+                *reinterpret_cast<float4 *>(L.gsg + 4 * q) = gs;
+                if (two) {
+                    t = kl_term(m1.x, s1.x, 0.0f, 1.0f, eps);
+                    t += kl_term(m1.y, s1.y, 0.0f, 1.0f, eps);
+                    t += kl_term(m1.z, s1.z, 0.0f, 1.0f, eps);
+                    t += kl_term(m1.w, s1.w, 0.0f, 1.0f, eps);
+                    acc += t;
+                    gm.x = L.k * m1.x / den; gm.y = L.k * m1.y / den; gm.z = L.k * m1.z / den; gm.w = L.k * m1.w / den;
+                    gs.x = L.k * (s1.x / den - s1.x / (s1.x * s1.x + eps)); gs.y = L.k * (s1.y / den - s1.y / (s1.y * s1.y + eps));
+                    gs.z = L.k * (s1.z / den - s1.z / (s1.z * s1.z + eps)); gs.w = L.k * (s1.w / den - s1.w / (s1.w * s1.w + eps));
+                    *reinterpret_cast<float4 *>(L.gmu + 4 * q1) = gm;
+                    *reinterpret_cast<float4 *>(L.gsg + 4 * q1) = gs;
+                }
+            }
+        } else {
+            for (i64 i = tid; i < L.total; i += nthr) {
+                const float mu = __ldg(L.mu + i), s = __ldg(L.sg + i);
+                acc += kl_term(mu, s, 0.0f, 1.0f, eps);
+                L.gmu[i] = L.k * mu / den;
+                L.gsg[i] = L.k * (s / den - s / (s * s + eps));
+            }
         }
         const double bt = block_sum((double)acc, red);
         if (threadIdx.x == 0) ws->partial[(i64)lv * gridDim.x + blockIdx.x] = bt;
@@ -417,11 +451,12 @@ extern "C" int pulpo_kl_n01_multi(const pulpo_kl_level *levels, int nlevels, flo
         PULPO_REQUIRE(v.n > 0, PULPO_ERR_INVALID_SHAPE);
         m.l[l].mu = v.mu; m.l[l].sg = v.sigma; m.l[l].gmu = v.gmu; m.l[l].gsg = v.gsigma; m.l[l].out = v.out;
         m.l[l].total = (i64)B * v.n;
+        m.l[l].vec = (m.l[l].total % 4 == 0 && aligned16(v.mu) && aligned16(v.sigma) && aligned16(v.gmu) && aligned16(v.gsigma)) ? 1 : 0;
         m.l[l].k = v.weight / (float)B;
         m.l[l].scale = 0.5 * (double)v.weight / (double)B;
         if (m.l[l].total > most) most = m.l[l].total;
     }
-    int grid = grid_for(most, 256, 4);
+    int grid = grid_for((most + 7) / 8, 256, 4);   // two quads per thread and pass
     if (grid > 592) grid = 592;
     kl_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m, eps, (KlMultiWs *)ws);
     return launch_status();

@@ -490,6 +490,69 @@ avgpool2_kernel(const float *__restrict__ in, float *__restrict__ out, int BC, i
     }
 }
 
+// The whole 2x pooling pyramid in one launch (Autoencoder.forward, src/components/pulpo.py:168-179: NL
+// successive avg_pool3d(2,2)), for volumes whose sizes are multiples of 2^NL (all windows full, count 8).
+// A CTA stages one E^3 block (E = 2^NL <= 16) of the input in shared memory with 128-bit loads and reduces it
+// level by level; every level is written to its own output.  The input is read once (the chain of NL launches
+// re-reads each level and is launch-latency bound below the first).  Same summation order per window as
+// avgpool2_kernel (z, then y, then x) and the same division, so the results are bit-identical.
+constexpr int POOL_MAXL = 4;
+struct PoolPyr {
+    float *out[POOL_MAXL];
+    int nl, E;
+    int BC, D0, D1, D2;
+    int nb0, nb1, nb2;   // blocks per axis
+};
+
+__global__ void __launch_bounds__(256)
+avgpool2_pyramid_kernel(const float *__restrict__ in, const PoolPyr p)
+{
+    __shared__ __align__(16) float sa[16 * 16 * 16];
+    __shared__ __align__(16) float sb[8 * 8 * 8];
+    const int E = p.E;
+    unsigned int blk = blockIdx.x;
+    const int bx = blk % p.nb2; blk /= p.nb2;
+    const int by = blk % p.nb1; blk /= p.nb1;
+    const int bz = blk % p.nb0;
+    const int bc = blk / p.nb0;
+    // stage the block: E*E rows of E floats (E / 4 quads per row)
+    const int qpr = E >> 2, nquads = E * E * qpr;
+    const float *src = in + (((i64)bc * p.D0 + (i64)bz * E) * p.D1 + (i64)by * E) * p.D2 + (i64)bx * E;
+    for (int q = threadIdx.x; q < nquads; q += 256) {
+        const int xq = q % qpr, row = q / qpr, y = row % E, z = row / E;
+        const float4 v = ld_stream4(src + ((i64)z * p.D1 + y) * p.D2 + 4 * xq);
+        *reinterpret_cast<float4 *>(sa + (z * E + y) * E + 4 * xq) = v;
+    }
+    __syncthreads();
+    float *cur = sa, *nxt = sb;
+    int e = E;   // edge of the block held in `cur`
+#pragma unroll
+    for (int l = 0; l < POOL_MAXL; ++l) {   // unrolled: constant indices into the parameter's pointer array
+        if (l >= p.nl) break;
+        const int h = e >> 1;
+        const int d0 = p.D0 >> (l + 1), d1 = p.D1 >> (l + 1), d2 = p.D2 >> (l + 1);
+        float *o = p.out[l] + (((i64)bc * d0 + (i64)bz * h) * d1 + (i64)by * h) * d2 + (i64)bx * h;
+        for (int t = threadIdx.x; t < h * h * h; t += 256) {
+            const int x = t % h, y = (t / h) % h, z = t / (h * h);
+            float s = 0.0f;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const float2 v = *reinterpret_cast<const float2 *>(cur + ((2 * z + a) * e + 2 * y + b) * e + 2 * x);
+                    s += v.x;
+                    s += v.y;
+                }
+            const float r = __fdiv_rn(s, 8.0f);
+            o[((i64)z * d1 + y) * d2 + x] = r;
+            nxt[(z * h + y) * h + x] = r;
+        }
+        __syncthreads();
+        float *tmp = cur; cur = nxt; nxt = tmp;
+        e = h;
+    }
+}
+
 }  // namespace pulpo
 
 using namespace pulpo;
@@ -611,5 +674,27 @@ extern "C" int pulpo_avgpool2_fwd(const float *x, float *out, int B, int C, int 
     PULPO_REQUIRE(B > 0 && C > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
     i64 total = (i64)B * C * ((D0 + 1) / 2) * ((D1 + 1) / 2) * ((D2 + 1) / 2);
     avgpool2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B * C, D0, D1, D2);
+    return launch_status();
+}
+
+extern "C" int pulpo_avgpool2_pyramid_fwd(const float *x, float *const *outs, int nlevels, int B, int C, int D0, int D1,
+                                          int D2, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(x && outs, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && C > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(nlevels >= 1 && nlevels <= POOL_MAXL, PULPO_ERR_INVALID_SHAPE);
+    const int nl = nlevels, E = nl < 2 ? 4 : (1 << nl);   // a single level still stages 4^3 blocks (quads)
+    PULPO_REQUIRE(D0 % E == 0 && D1 % E == 0 && D2 % E == 0 && aligned16(x), PULPO_ERR_UNSUPPORTED);
+    PoolPyr p;
+    p.nl = nl; p.E = E; p.BC = B * C; p.D0 = D0; p.D1 = D1; p.D2 = D2;
+    p.nb0 = D0 / E; p.nb1 = D1 / E; p.nb2 = D2 / E;
+    for (int l = 0; l < POOL_MAXL; ++l) p.out[l] = nullptr;
+    for (int l = 0; l < nl; ++l) {
+        PULPO_REQUIRE(outs[l], PULPO_ERR_NULL_POINTER);
+        p.out[l] = outs[l];
+    }
+    const i64 blocks = (i64)p.BC * p.nb0 * p.nb1 * p.nb2;
+    PULPO_REQUIRE(blocks < (1ll << 31), PULPO_ERR_INVALID_SHAPE);
+    avgpool2_pyramid_kernel<<<(unsigned int)blocks, 256, 0, (cudaStream_t)stream>>>(x, p);
     return launch_status();
 }

@@ -81,8 +81,76 @@ struct VLevel {
 struct VMulti {
     int n;
     unsigned int items;   // total
+    int combine;          // fold the Laplacian-pyramid combination into the launch (see below)
+    const float *indiv[VI_MAXL];   // combine: the levels' individual fields
     VLevel l[VI_MAXL];
 };
+
+// ---- coarse-to-fine combination folded into the integration launch (SVFDecoder.forward, src/components/pulpo.py:308;
+// PULPo.combine_dfs, src/models.py:356-367):  combined_l = 2 * up2(combined_{l+1}) + individual_l, one grid barrier
+// per level instead of one launch (and the adjoint behind the backward).  Optional: measured at config 2 the
+// separate launches win (+27 us forward, +31 us backward here vs 20 + 25 us of small kernels that overlap with
+// other streams): these phases run on the cooperative grid's ~100 k threads and are latency-bound.  Same taps,
+// weights and nesting order (x, y, z) as the x2 kernels of resize.cu: bit-identical combined fields.
+struct Up2Ax {
+    int ia, ib;
+    float wa, wb;
+};
+__device__ __forceinline__ Up2Ax up2_axis(int o, int n)   // output index o, input size n
+{
+    const int j = o >> 1;
+    Up2Ax t;
+    if (o & 1) {
+        t.ia = j; t.ib = min(j + 1, n - 1); t.wa = 0.75f; t.wb = 0.25f;
+    } else {
+        t.ia = j ? j - 1 : j; t.ib = j; t.wa = j ? 0.25f : 1.0f; t.wb = j ? 0.75f : 0.0f;
+    }
+    return t;
+}
+__device__ __forceinline__ float up2_point(const float *__restrict__ p, int d1, int d2, const Up2Ax &tz, const Up2Ax &ty,
+                                           const Up2Ax &tx, float premul)
+{
+    const float *r00 = p + ((i64)tz.ia * d1 + ty.ia) * d2, *r01 = p + ((i64)tz.ia * d1 + ty.ib) * d2;
+    const float *r10 = p + ((i64)tz.ib * d1 + ty.ia) * d2, *r11 = p + ((i64)tz.ib * d1 + ty.ib) * d2;
+    const float a0 = __ldcg(r00 + tx.ia), a1 = __ldcg(r00 + tx.ib), b0 = __ldcg(r01 + tx.ia), b1 = __ldcg(r01 + tx.ib);
+    const float c0 = __ldcg(r10 + tx.ia), c1 = __ldcg(r10 + tx.ib), e0 = __ldcg(r11 + tx.ia), e1 = __ldcg(r11 + tx.ib);
+    const float x00 = (premul * a0) * tx.wa + (premul * a1) * tx.wb, x01 = (premul * b0) * tx.wa + (premul * b1) * tx.wb;
+    const float x10 = (premul * c0) * tx.wa + (premul * c1) * tx.wb, x11 = (premul * e0) * tx.wa + (premul * e1) * tx.wb;
+    const float y0 = x00 * ty.wa + x01 * ty.wb, y1 = x10 * ty.wa + x11 * ty.wb;
+    return y0 * tz.wa + y1 * tz.wb;
+}
+// adjoint weights of input j for outputs 2j-1 .. 2j+2 (resize.cu: adj4)
+__device__ __forceinline__ void up2_adj_w(int j, int n, float (&w)[4])
+{
+    w[0] = j > 0 ? 0.25f : 0.0f;
+    w[1] = j > 0 ? 0.75f : 1.0f;
+    w[2] = j < n - 1 ? 0.75f : 1.0f;
+    w[3] = j < n - 1 ? 0.25f : 0.0f;
+}
+// sum over the 4x4x4 outputs that read input (z, y, x); go: one channel volume at twice the size
+// (not inlined: keeps the rarely-run combination code out of the integration loops' register allocation)
+__device__ __noinline__ float up2_adjoint_point(const float *__restrict__ go, int d0, int d1, int d2, int z, int y, int x)
+{
+    float wz[4], wy[4], wx[4];
+    up2_adj_w(z, d0, wz); up2_adj_w(y, d1, wy); up2_adj_w(x, d2, wx);
+    const int o1 = 2 * d1, o2 = 2 * d2;
+    float acc = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int oz = min(max(2 * z - 1 + a, 0), 2 * d0 - 1);   // clamped taps carry weight 0
+        float accy = 0.0f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int oy = min(max(2 * y - 1 + b, 0), o1 - 1);
+            const float *row = go + ((i64)oz * o1 + oy) * o2;
+            const float g0 = __ldcg(row + max(2 * x - 1, 0)), g1 = __ldcg(row + 2 * x), g2 = __ldcg(row + 2 * x + 1),
+                        g3 = __ldcg(row + min(2 * x + 2, o2 - 1));
+            accy += wy[b] * (wx[0] * g0 + wx[1] * g1 + wx[2] * g2 + wx[3] * g3);
+        }
+        acc += wz[a] * accy;
+    }
+    return acc;
+}
 
 static int make_vgeom(VGeom &g, int B, int D0, int D1, int D2)
 {
@@ -267,14 +335,54 @@ vecint_fwd_kernel(const VMulti m, int nsteps, int save, float scale)
     const unsigned int warp = tid >> 5, nwarps = nthr >> 5;
 
     // v_0 = vec * 2^-nsteps, planar -> interleaved
-    for (int lv = 0; lv < m.n; ++lv) {
-        const VLevel &L = m.l[lv];
-        const unsigned int N = L.g.N, S = L.g.S;
-        for (unsigned int i = tid; i < N; i += nthr) {
-            unsigned int b = i / S, v = i - b * S;
-            const float *f = L.in + (i64)b * 3 * S + v;
-            L.ws[i] = make_float4(__fmul_rn(__ldg(f), scale), __fmul_rn(__ldg(f + S), scale),
-                                  __fmul_rn(__ldg(f + 2 * S), scale), 0.0f);
+    if (m.combine) {
+        // coarse to fine: combined_l = 2 * up2(combined_{l+1}) + individual_l, written to L.in (an output here) and,
+        // scaled, to the first integration state; one grid barrier per level
+        for (int lv = m.n - 1; lv >= 0; --lv) {
+            const VLevel &L = m.l[lv];
+            const unsigned int N = L.g.N, S = L.g.S;
+            const float *ind = m.indiv[lv];
+            if (lv == m.n - 1) {
+                for (unsigned int i = tid; i < N; i += nthr) {
+                    unsigned int b = i / S, v = i - b * S;
+                    const float *f = ind + (i64)b * 3 * S + v;
+                    L.ws[i] = make_float4(__fmul_rn(__ldg(f), scale), __fmul_rn(__ldg(f + S), scale),
+                                          __fmul_rn(__ldg(f + 2 * S), scale), 0.0f);
+                }
+                continue;
+            }
+            grid.sync();
+            const VLevel &C = m.l[lv + 1];
+            const float *lower = (lv + 1 == m.n - 1) ? m.indiv[lv + 1] : C.in;
+            const int c1 = C.g.D1, c2 = C.g.D2;
+            const unsigned int Sc = C.g.S;
+            float *comb = const_cast<float *>(L.in);
+            for (unsigned int i = tid; i < N; i += nthr) {
+                unsigned int b = i / S, v = i - b * S;
+                unsigned int zy = v / (unsigned int)L.g.D2, x = v - zy * (unsigned int)L.g.D2;
+                unsigned int z = zy / (unsigned int)L.g.D1, y = zy - z * (unsigned int)L.g.D1;
+                const Up2Ax tz = up2_axis((int)z, C.g.D0), ty = up2_axis((int)y, c1), tx = up2_axis((int)x, c2);
+                const float *f = ind + (i64)b * 3 * S + v;
+                const float *lo = lower + (i64)b * 3 * Sc;
+                float r0 = up2_point(lo, c1, c2, tz, ty, tx, 2.0f);
+                float r1 = up2_point(lo + Sc, c1, c2, tz, ty, tx, 2.0f);
+                float r2 = up2_point(lo + 2 * (i64)Sc, c1, c2, tz, ty, tx, 2.0f);
+                r0 += __ldg(f); r1 += __ldg(f + S); r2 += __ldg(f + 2 * S);
+                float *o = comb + (i64)b * 3 * S + v;
+                o[0] = r0; o[S] = r1; o[2 * S] = r2;
+                L.ws[i] = make_float4(__fmul_rn(r0, scale), __fmul_rn(r1, scale), __fmul_rn(r2, scale), 0.0f);
+            }
+        }
+    } else {
+        for (int lv = 0; lv < m.n; ++lv) {
+            const VLevel &L = m.l[lv];
+            const unsigned int N = L.g.N, S = L.g.S;
+            for (unsigned int i = tid; i < N; i += nthr) {
+                unsigned int b = i / S, v = i - b * S;
+                const float *f = L.in + (i64)b * 3 * S + v;
+                L.ws[i] = make_float4(__fmul_rn(__ldg(f), scale), __fmul_rn(__ldg(f + S), scale),
+                                      __fmul_rn(__ldg(f + 2 * S), scale), 0.0f);
+            }
         }
     }
     for (int k = 0; k < nsteps; ++k) {
@@ -558,6 +666,26 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
 #else
         const float4 *Pa = L.scr + (flip ? 2 : 0) * (i64)N, *Ya = Pa + N;
 #endif
+        if (m.combine && lv > 0) {
+            // adjoint of the combination: the finer level's (complete) gradient flows into this level through
+            // 2 * up2^T; fine to coarse, one grid barrier per level
+            grid.sync();
+            const VLevel &F = m.l[lv - 1];
+            const unsigned int Sf = F.g.S;
+            const int d0 = L.g.D0, d1 = L.g.D1, d2 = L.g.D2;
+            for (unsigned int i = tid; i < N; i += nthr) {
+                unsigned int b = i / S, v = i - b * S;
+                unsigned int zy = v / (unsigned int)d2, x = v - zy * (unsigned int)d2;
+                unsigned int z = zy / (unsigned int)d1, yy = zy - z * (unsigned int)d1;
+                const float4 p = Pa[i], y = Ya[i];
+                const float *go = F.out + (i64)b * 3 * Sf;
+                float *o = L.out + (i64)b * 3 * S + v;
+                o[0] = (p.x + y.x) * scale + 2.0f * up2_adjoint_point(go, d0, d1, d2, (int)z, (int)yy, (int)x);
+                o[S] = (p.y + y.y) * scale + 2.0f * up2_adjoint_point(go + Sf, d0, d1, d2, (int)z, (int)yy, (int)x);
+                o[2 * S] = (p.z + y.z) * scale + 2.0f * up2_adjoint_point(go + 2 * (i64)Sf, d0, d1, d2, (int)z, (int)yy, (int)x);
+            }
+            continue;
+        }
         for (unsigned int i = tid; i < N; i += nthr) {
             unsigned int b = i / S, v = i - b * S;
             const float4 p = Pa[i], y = Ya[i];
@@ -628,6 +756,8 @@ static int fill_levels(VMulti &m, const pulpo_vecint_level *levels, int nlevels,
 {
     PULPO_REQUIRE(levels && nlevels >= 1 && nlevels <= VI_MAXL, PULPO_ERR_INVALID_SHAPE);
     m.n = nlevels;
+    m.combine = 0;
+    for (int l = 0; l < VI_MAXL; ++l) m.indiv[l] = nullptr;
     i64 total = 0;
     for (int l = 0; l < nlevels; ++l) {
         const pulpo_vecint_level &v = levels[l];
@@ -678,8 +808,18 @@ extern "C" size_t pulpo_vecint_bwd_scratch_bytes(int B, int D0, int D1, int D2)
 #endif
 }
 
-extern "C" int pulpo_vecint_multi_fwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int save_steps, int B,
-                                      int coord_mode, pulpo_stream_t stream)
+// the levels of a combined launch are a x2 pyramid, fine to coarse
+static int check_pyramid(const pulpo_vecint_level *levels, int nlevels)
+{
+    for (int l = 0; l + 1 < nlevels; ++l)
+        PULPO_REQUIRE(levels[l].D0 == 2 * levels[l + 1].D0 && levels[l].D1 == 2 * levels[l + 1].D1 &&
+                          levels[l].D2 == 2 * levels[l + 1].D2,
+                      PULPO_ERR_INVALID_SHAPE);
+    return PULPO_OK;
+}
+
+static int vecint_multi_fwd_impl(const pulpo_vecint_level *levels, const float *const *indiv, int nlevels, int nsteps,
+                                 int save_steps, int B, int coord_mode, pulpo_stream_t stream)
 {
     PULPO_REQUIRE(B > 0 && nsteps >= 0 && nsteps <= 30, PULPO_ERR_INVALID_SHAPE);
     coord_mode &= 0xff;   // high bits: backward tuning switches
@@ -687,6 +827,15 @@ extern "C" int pulpo_vecint_multi_fwd(const pulpo_vecint_level *levels, int nlev
     VMulti m;
     int rc = fill_levels(m, levels, nlevels, B, false, nsteps, save_steps);
     if (rc != PULPO_OK) return rc;
+    if (indiv) {
+        rc = check_pyramid(levels, nlevels);
+        if (rc != PULPO_OK) return rc;
+        for (int l = 0; l < nlevels; ++l) {
+            PULPO_REQUIRE(indiv[l], PULPO_ERR_NULL_POINTER);
+            m.indiv[l] = indiv[l];
+        }
+        m.combine = 1;
+    }
     float scale = 1.0f / (float)(1u << nsteps);
     void *args[] = {&m, &nsteps, &save_steps, &scale};
     cudaStream_t st = (cudaStream_t)stream;
@@ -695,8 +844,21 @@ extern "C" int pulpo_vecint_multi_fwd(const pulpo_vecint_level *levels, int nlev
     return launch_coop(vecint_fwd_kernel<2>, VI_FWD_THREADS, m, args, st);
 }
 
-extern "C" int pulpo_vecint_multi_bwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int B, int coord_mode,
-                                      pulpo_stream_t stream)
+extern "C" int pulpo_vecint_multi_fwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int save_steps, int B,
+                                      int coord_mode, pulpo_stream_t stream)
+{
+    return vecint_multi_fwd_impl(levels, nullptr, nlevels, nsteps, save_steps, B, coord_mode, stream);
+}
+
+extern "C" int pulpo_combine_vecint_multi_fwd(const pulpo_vecint_level *levels, const float *const *indiv, int nlevels,
+                                              int nsteps, int save_steps, int B, int coord_mode, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(indiv, PULPO_ERR_NULL_POINTER);
+    return vecint_multi_fwd_impl(levels, indiv, nlevels, nsteps, save_steps, B, coord_mode, stream);
+}
+
+static int vecint_multi_bwd_impl(const pulpo_vecint_level *levels, int combine, int nlevels, int nsteps, int B,
+                                 int coord_mode, pulpo_stream_t stream)
 {
     PULPO_REQUIRE(B > 0 && nsteps >= 0 && nsteps <= 30, PULPO_ERR_INVALID_SHAPE);
     const int variant = (coord_mode >> 8) & 0xf;   // tuning switch, see below; 0 = default
@@ -705,6 +867,11 @@ extern "C" int pulpo_vecint_multi_bwd(const pulpo_vecint_level *levels, int nlev
     VMulti m;
     int rc = fill_levels(m, levels, nlevels, B, true, nsteps, 1);
     if (rc != PULPO_OK) return rc;
+    if (combine) {
+        rc = check_pyramid(levels, nlevels);
+        if (rc != PULPO_OK) return rc;
+        m.combine = 1;
+    }
     float scale = 1.0f / (float)(1u << nsteps);
     void *args[] = {&m, &nsteps, &scale};
     cudaStream_t st = (cudaStream_t)stream;
@@ -719,6 +886,18 @@ extern "C" int pulpo_vecint_multi_bwd(const pulpo_vecint_level *levels, int nlev
     PULPO_VI_BWD_CASE(0, 1) PULPO_VI_BWD_CASE(2, 1)
 #undef PULPO_VI_BWD_CASE
     return PULPO_ERR_UNSUPPORTED;
+}
+
+extern "C" int pulpo_vecint_multi_bwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int B, int coord_mode,
+                                      pulpo_stream_t stream)
+{
+    return vecint_multi_bwd_impl(levels, 0, nlevels, nsteps, B, coord_mode, stream);
+}
+
+extern "C" int pulpo_combine_vecint_multi_bwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int B,
+                                              int coord_mode, pulpo_stream_t stream)
+{
+    return vecint_multi_bwd_impl(levels, 1, nlevels, nsteps, B, coord_mode, stream);
 }
 
 extern "C" int pulpo_vecint_fwd(const float *vec, float *out, void *ws, size_t ws_bytes, int nsteps, int save_steps,

@@ -14,7 +14,9 @@ but orchestrated B200-first:
     right after its forward -- no scalar graph, no autograd bookkeeping kernels;
   * gradient sums that autograd would do in extra passes are folded into producers:
     L2-reg's gradient accumulates into the warp's field gradient, the Laplacian-pyramid
-    up-sampling adjoint accumulates into the coarser level's gradient.
+    up-sampling adjoint accumulates into the coarser level's gradient (``fuse_combine=True``
+    moves the combination and its adjoint into the integration launches: fewer launches,
+    measured slower).
 
 Reference call structure reproduced: SVFDecoder.forward (src/components/pulpo.py:301-319) per
 level, Autoencoder's moving pyramid (:168-179), HierarchicalReconstructionLoss / KLLoss /
@@ -41,13 +43,17 @@ def _p(t, byte_offset=0):
 class HotPathPlan:
     def __init__(self, input_size, total_levels, latent_levels, batch=1, beta=0.1, gamma=0.05, lamb=0.025,
                  with_reg=True, nsteps=7, coord_mode=CPU_EXACT, device=None, multi_stream=True, fuse_reg=True,
-                 vecint_mode=CPU_EXACT):
+                 vecint_mode=CPU_EXACT, fuse_combine=False, pool_pyramid=True, aux_early=False):
         self.L = L = latent_levels
         self.B = B = batch
         self.lk = lk = total_levels - latent_levels
         self.nsteps, self.mode, self.with_reg = nsteps, coord_mode, with_reg
         self.vi_mode = vecint_mode   # CPU_EXACT: bit-identical fields; FAST is within 1e-4 but buys little (L1-pipe bound)
         self.fuse_reg = bool(fuse_reg and with_reg)   # L2_reg rides in the warp kernels (same field, same step)
+        # pyramid combination (and its adjoint) inside the integration launches: fewer launches (25 instead of 31) but
+        # measured slower (0.936 vs 0.916 ms at config 2): the in-kernel phases run on the cooperative grid's 113 k / 75 k
+        # threads and are latency-bound, while the separate small launches overlap with the aux stream's work
+        self.fuse_combine = bool(fuse_combine)
         self.dev = dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.lib = _lib.lib()
         self.full = tuple(int(s) for s in input_size)
@@ -100,6 +106,10 @@ class HotPathPlan:
         self.ws_l2 = [torch.zeros(rbytes, dtype=torch.uint8, device=dev) for _ in range(L)]
         self.ws_ncc = [torch.zeros(lib.pulpo_ncc_ws_bytes(B, 1, *self.outsz[l]), dtype=torch.uint8, device=dev)
                        for l in range(L)]
+        npool = len(self.pooled)
+        edge = 4 if npool == 1 else (1 << npool)
+        self.pool_pyramid = bool(pool_pyramid) and 1 <= npool <= 4 and all(s % edge == 0 for s in self.full)
+        self.aux_early = bool(aux_early)
         self.multi_stream = multi_stream
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(L + 1)] if multi_stream else None
         self.launches = 0
@@ -128,43 +138,57 @@ class HotPathPlan:
 
         start = torch.cuda.Event()
         start.record(cur)
-        # ---- moving-image pyramid on the aux stream (pulpo.py:168-179)
-        if ms:
-            aux.wait_event(start)
+        # ---- moving-image pyramid (pulpo.py:168-179) and the KL terms on the aux stream.  Both are independent of the
+        #      fields; `aux_early` decides whether they start with the step (next to the combination / integration
+        #      launch, which as a cooperative kernel needs every SM to itself) or right after the integration
+        #      (next to the level-0 resize / warp kernels).
         ev_lx = {}
-        src, shape = x, self.full
-        for i, dst in enumerate(self.pooled):
-            call(lib.pulpo_avgpool2_fwd, _p(src), _p(dst), B, 1, *shape, H(aux))
-            src, shape = dst, tuple(dst.shape[2:])
-            l = i - self.lk + 1
-            if l >= 1:
-                ev_lx[l] = torch.cuda.Event()
-                ev_lx[l].record(aux)
+
+        def aux_work(after):
+            if ms:
+                aux.wait_event(after)
+            if self.pool_pyramid:
+                outs = (ctypes.c_void_p * len(self.pooled))(*[t.data_ptr() for t in self.pooled])
+                call(lib.pulpo_avgpool2_pyramid_fwd, _p(x), outs, len(self.pooled), B, 1, *self.full, H(aux))
+                ev = torch.cuda.Event()
+                ev.record(aux)
+                for l in range(1, L):
+                    ev_lx[l] = ev
+            else:
+                src, shape = x, self.full
+                for i, dst in enumerate(self.pooled):
+                    call(lib.pulpo_avgpool2_fwd, _p(src), _p(dst), B, 1, *shape, H(aux))
+                    src, shape = dst, tuple(dst.shape[2:])
+                    l = i - self.lk + 1
+                    if l >= 1:
+                        ev_lx[l] = torch.cuda.Event()
+                        ev_lx[l].record(aux)
+            # KL of every level, value and gradients, in one launch (losses.py:47-76 with the N(0,1) prior;
+            # weight = level weight * beta)
+            kl_arr = (_lib.KlLevel * L)()
+            for l in range(L):
+                nlat = 3 * self.insz[l][0] * self.insz[l][1] * self.insz[l][2]
+                kl_arr[l] = _lib.KlLevel(mus[l].data_ptr(), sigmas[l].data_ptr(), self.gmu[l].data_ptr(),
+                                         self.gsigma[l].data_ptr(), self.losses.data_ptr() + 4 * (0 * L + l), nlat,
+                                         self.kl_weight[l])
+            call(lib.pulpo_kl_n01_multi, kl_arr, L, 1e-10, B, _p(self.ws_klm), self.ws_klm.numel(), H(aux))
+            ev = torch.cuda.Event()
+            ev.record(aux)
+            return ev
+
+        ev_kl = aux_work(start) if self.aux_early else None
         lx = {0: x}
         for l in range(1, L):
             lx[l] = self.pooled[self.lk + l - 1]
 
-        # ---- coarse-to-fine field combination on the current stream (pulpo.py:308)
+        # ---- coarse-to-fine field combination (pulpo.py:308) on the current stream (or, fuse_combine, inside the
+        #      integration launch)
         comb = {L - 1: dfs[L - 1]}
-        ev_comb = {}
         for l in range(L - 2, -1, -1):
-            d = self.insz[l + 1]
-            call(lib.pulpo_resize_up_fwd, _p(comb[l + 1]), _p(dfs[l]), _p(self.comb[l]), 2, 2.0, B, 3, *d, H(cur))
+            if not self.fuse_combine:
+                d = self.insz[l + 1]
+                call(lib.pulpo_resize_up_fwd, _p(comb[l + 1]), _p(dfs[l]), _p(self.comb[l]), 2, 2.0, B, 3, *d, H(cur))
             comb[l] = self.comb[l]
-            ev_comb[l] = torch.cuda.Event()
-            ev_comb[l].record(cur)
-
-        # ---- KL of every level, value and gradients, in one launch on the aux stream (losses.py:47-76 with the
-        #      N(0,1) prior; weight = level weight * beta).  Independent of everything else in the step.
-        kl_arr = (_lib.KlLevel * L)()
-        for l in range(L):
-            nlat = 3 * self.insz[l][0] * self.insz[l][1] * self.insz[l][2]
-            kl_arr[l] = _lib.KlLevel(mus[l].data_ptr(), sigmas[l].data_ptr(), self.gmu[l].data_ptr(),
-                                     self.gsigma[l].data_ptr(), self.losses.data_ptr() + 4 * (0 * L + l), nlat,
-                                     self.kl_weight[l])
-        call(lib.pulpo_kl_n01_multi, kl_arr, L, 1e-10, B, _p(self.ws_klm), self.ws_klm.numel(), H(aux))
-        ev_kl = torch.cuda.Event()
-        ev_kl.record(aux)
 
         # ---- integrate every level in ONE cooperative launch (a cooperative kernel owns all SMs, so
         #      per-level launches would serialise; pulpo.py:311 for each decoder)
@@ -173,9 +197,15 @@ class HotPathPlan:
             ws, scr = self.vi_ws[l], self.vi_scr[l]
             lv_arr[l] = _lib.VecIntLevel(comb[l].data_ptr(), self.integ[l].data_ptr(), ws.data_ptr(), ws.numel() * 4,
                                          scr.data_ptr(), scr.numel() * 4, *self.insz[l])
-        call(lib.pulpo_vecint_multi_fwd, lv_arr, L, self.nsteps, 1, B, self.vi_mode, H(cur))
+        if self.fuse_combine:
+            indiv = (ctypes.c_void_p * L)(*[dfs[l].data_ptr() for l in range(L)])
+            call(lib.pulpo_combine_vecint_multi_fwd, lv_arr, indiv, L, self.nsteps, 1, B, self.vi_mode, H(cur))
+        else:
+            call(lib.pulpo_vecint_multi_fwd, lv_arr, L, self.nsteps, 1, B, self.vi_mode, H(cur))
         ev_int = torch.cuda.Event()
         ev_int.record(cur)
+        if not self.aux_early:
+            ev_kl = aux_work(ev_int)
 
         # ---- per level: resize, warp, losses and their backward, on the level's stream
         ev_done = {}
@@ -225,6 +255,16 @@ class HotPathPlan:
             ev_done[l] = torch.cuda.Event()
             ev_done[l].record(s)
 
+        # ---- total loss on the aux stream (every term is known once the levels' forward kernels ran), next to
+        #      the integration backward instead of behind it
+        if ms:
+            for l in range(L):
+                aux.wait_event(ev_done[l])
+            with torch.cuda.stream(aux):
+                torch.sum(self.losses, dim=(0, 1), out=self.total)
+            ev_total = torch.cuda.Event()
+            ev_total.record(aux)
+
         # ---- backward of the integration, again one launch for all levels
         if ms:
             cur.wait_event(ev_kl)
@@ -232,12 +272,18 @@ class HotPathPlan:
                 cur.wait_event(ev_done[l])
         for l in range(L):
             lv_arr[l].inp, lv_arr[l].out = self.ginteg[l].data_ptr(), self.gdf[l].data_ptr()
-        call(lib.pulpo_vecint_multi_bwd, lv_arr, L, self.nsteps, B, self.vi_mode, H(cur))
-
-        # ---- fine-to-coarse: the adjoint of the combination accumulates into the coarser gradient
-        for l in range(1, L):
-            call(lib.pulpo_resize_up_bwd, _p(self.gdf[l - 1]), _p(self.gdf[l]), 2, 2.0, 1, B, 3, *self.insz[l], H(cur))
-        torch.sum(self.losses, dim=(0, 1), out=self.total)
+        if self.fuse_combine:
+            # ... and the adjoint of the combination (fine to coarse) inside the same launch
+            call(lib.pulpo_combine_vecint_multi_bwd, lv_arr, L, self.nsteps, B, self.vi_mode, H(cur))
+        else:
+            call(lib.pulpo_vecint_multi_bwd, lv_arr, L, self.nsteps, B, self.vi_mode, H(cur))
+            # ---- fine-to-coarse: the adjoint of the combination accumulates into the coarser gradient
+            for l in range(1, L):
+                call(lib.pulpo_resize_up_bwd, _p(self.gdf[l - 1]), _p(self.gdf[l]), 2, 2.0, 1, B, 3, *self.insz[l], H(cur))
+        if ms:
+            cur.wait_event(ev_total)
+        else:
+            torch.sum(self.losses, dim=(0, 1), out=self.total)
         self.launches = n[0]
         return self.total
 

@@ -33,6 +33,16 @@ def algo_bytes(name, args):
         return sum(a[2] * 24 * a[4] * lv.D0 * lv.D1 * lv.D2 for lv in args[0][:a[1]])
     if name == "pulpo_vecint_multi_bwd":    # levels*, nlevels, nsteps, B, mode
         return sum(a[2] * 36 * a[3] * lv.D0 * lv.D1 * lv.D2 for lv in args[0][:a[1]])
+    if name == "pulpo_combine_vecint_multi_fwd":   # levels*, indiv*, nlevels, nsteps, save, B, mode
+        lv = args[0][:a[2]]
+        n = [v.D0 * v.D1 * v.D2 for v in lv]
+        comb = sum(12 * n[l + 1] + 24 * n[l] for l in range(len(n) - 1))     # combine 12 n_{k+1} + 24 n_k
+        return a[5] * (sum(a[3] * 24 * v for v in n) + comb)
+    if name == "pulpo_combine_vecint_multi_bwd":   # levels*, nlevels, nsteps, B, mode
+        lv = args[0][:a[1]]
+        n = [v.D0 * v.D1 * v.D2 for v in lv]
+        comb = sum(12 * n[l] + 12 * n[l + 1] for l in range(len(n) - 1))     # combine bwd 12 n_k + 12 n_{k+1}
+        return a[3] * (sum(a[2] * 36 * v for v in n) + comb)
     if name == "pulpo_resize_up_fwd":       # x, addend, out, factor, scale, B, C, d0, d1, d2
         f, B, C, n = a[3], a[5], a[6], a[7] * a[8] * a[9]
         return B * C * 4 * (n + n * f ** 3 * (2 if a[1] else 1))
@@ -48,6 +58,9 @@ def algo_bytes(name, args):
         return a[8] * a[9] * a[10] * a[11] * a[12] * 8
     if name == "pulpo_ncc_bwd":             # abc, pred, target, gloss, gpred, win, gamma, B, C, D0..
         return a[7] * a[8] * a[9] * a[10] * a[11] * 12
+    if name == "pulpo_avgpool2_pyramid_fwd":   # x, outs*, nlevels, B, C, D0, D1, D2
+        n = a[5] * a[6] * a[7]
+        return a[3] * a[4] * 4 * (n + sum(n >> (3 * (l + 1)) for l in range(a[2])))
     if name == "pulpo_kl_diag_fwd":         # mu0, s0, mu1, s1, eps, weight, out, ws, bytes, B, n
         return a[9] * a[10] * 4 * (2 + (1 if a[2] else 0) + (1 if a[3] else 0))
     if name == "pulpo_kl_diag_bwd":         # gloss, mu0, s0, mu1, s1, eps, weight, gmu, gsg, B, n

@@ -179,6 +179,65 @@ def test_vecint_multi_level_launch_matches_per_level_calls(PF):
     assert L.pulpo_vecint_multi_fwd(arr, 7, n, 1, B, 0, st) == -2     # more than 6 levels
 
 
+@pytest.mark.parametrize("shapes,B", [([(16, 24, 32), (8, 12, 16), (4, 6, 8)], 2), ([(80, 96, 112), (40, 48, 56), (20, 24, 28), (10, 12, 14)], 1),
+                                      ([(12, 20, 36), (6, 10, 18)], 1)])
+def test_combine_vecint_multi_matches_separate_launches(PF, shapes, B):
+    """pulpo_combine_vecint_multi_fwd/bwd (pyramid combination + its adjoint inside the integration launches)
+    against the separate x2 up-sampling launches around pulpo_vecint_multi_*: combined fields bit-identical
+    (same taps, weights and nesting order), integrated fields bit-identical, gradients within the tolerance."""
+    import ctypes
+    from pulpo_b200 import _lib, synthetic as syn
+    L = _lib.lib()
+    n, nl = 7, len(shapes)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    df = [syn.make_field(sh, 3 + i, batch=B, max_abs=3.0).cuda() for i, sh in enumerate(shapes)]
+    g = [syn.make_field(sh, 9 + i, batch=B, max_abs=1.0).cuda() for i, sh in enumerate(shapes)]
+    ws = [torch.empty(L.pulpo_vecint_ws_bytes(n, 1, B, *sh) // 4, device="cuda") for sh in shapes]
+    scr = [torch.empty(L.pulpo_vecint_bwd_scratch_bytes(B, *sh) // 4, device="cuda") for sh in shapes]
+
+    def run(fused):
+        comb = [torch.full_like(t, float("nan")) for t in df[:-1]] + [df[-1]]
+        out = [torch.empty_like(t) for t in df]
+        gv = [torch.empty_like(t) for t in df]
+        arr = (_lib.VecIntLevel * nl)()
+        for i, sh in enumerate(shapes):
+            arr[i] = _lib.VecIntLevel(comb[i].data_ptr(), out[i].data_ptr(), ws[i].data_ptr(), ws[i].numel() * 4,
+                                      scr[i].data_ptr(), scr[i].numel() * 4, *sh)
+        if fused:
+            indiv = (ctypes.c_void_p * nl)(*[t.data_ptr() for t in df])
+            _lib.check(L.pulpo_combine_vecint_multi_fwd(arr, indiv, nl, n, 1, B, 0, st))
+        else:
+            for l in range(nl - 2, -1, -1):
+                _lib.check(L.pulpo_resize_up_fwd(vp(comb[l + 1]), vp(df[l]), vp(comb[l]), 2, 2.0, B, 3, *shapes[l + 1], st))
+            _lib.check(L.pulpo_vecint_multi_fwd(arr, nl, n, 1, B, 0, st))
+        for i in range(nl):
+            arr[i].inp, arr[i].out = g[i].data_ptr(), gv[i].data_ptr()
+        if fused:
+            _lib.check(L.pulpo_combine_vecint_multi_bwd(arr, nl, n, B, 0, st))
+        else:
+            _lib.check(L.pulpo_vecint_multi_bwd(arr, nl, n, B, 0, st))
+            for l in range(1, nl):
+                _lib.check(L.pulpo_resize_up_bwd(vp(gv[l - 1]), vp(gv[l]), 2, 2.0, 1, B, 3, *shapes[l], st))
+        torch.cuda.synchronize()
+        return comb, out, gv
+
+    c0, o0, g0 = run(False)
+    c1, o1, g1 = run(True)
+    for i in range(nl):
+        assert torch.equal(c1[i], c0[i]), "combined field of level %d differs (max %.3e)" % (i, (c1[i] - c0[i]).abs().max().item())
+        assert torch.equal(o1[i], o0[i]), "integrated field of level %d differs" % i
+        assert_grad_close(g1[i].cpu().numpy(), g0[i].cpu().numpy(), "gradient of level %d" % i)
+    # not a x2 pyramid -> rejected before any launch
+    arr = (_lib.VecIntLevel * 2)()
+    for i, sh in enumerate([shapes[0], (shapes[0][0] // 2, shapes[0][1] // 2, shapes[0][2] // 2 - 1)]):
+        t = torch.empty(B, 3, *sh, device="cuda")
+        arr[i] = _lib.VecIntLevel(t.data_ptr(), t.data_ptr(), ws[0].data_ptr(), ws[0].numel() * 4, scr[0].data_ptr(),
+                                  scr[0].numel() * 4, *sh)
+    indiv = (ctypes.c_void_p * 2)(df[0].data_ptr(), df[1].data_ptr())
+    assert L.pulpo_combine_vecint_multi_fwd(arr, indiv, 2, n, 1, B, 0, st) == -2
+
+
 def test_vecint_zero_steps_and_zero_field(PF):
     v = torch.randn(1, 3, 6, 8, 10, device="cuda")
     assert torch.equal(PF.vecint(v, 0), v)
@@ -223,6 +282,33 @@ def test_target_pyramid_golden(PF):
     for i in range(5):
         out = PF.interp_to_size(y, tuple(int(s) for s in g["size%d" % i]))
         assert_close(out.cpu().numpy(), g["out%d" % i], 1e-6, "target pyramid %d" % i)
+
+
+@pytest.mark.parametrize("shape,nl,B", [((160, 192, 224), 4, 1), ((64, 64, 64), 3, 2), ((16, 32, 48), 4, 1), ((8, 12, 20), 2, 3),
+                                        ((8, 4, 12), 1, 1)])
+def test_avgpool2_pyramid_equals_chain(PF, shape, nl, B):
+    """pulpo_avgpool2_pyramid_fwd (all pooling levels in one launch, input read once) is bit-identical to the
+    chain of pulpo_avgpool2_fwd launches; shapes that are not multiples of 2^levels are refused."""
+    import ctypes
+    from pulpo_b200 import _lib
+    L = _lib.lib()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    x = torch.rand(B, 1, *shape, device="cuda")
+    chain, src, sh = [], x, shape
+    for _ in range(nl):
+        o = torch.empty(B, 1, *[(v + 1) // 2 for v in sh], device="cuda")
+        _lib.check(L.pulpo_avgpool2_fwd(vp(src), vp(o), B, 1, *sh, st))
+        chain.append(o)
+        src, sh = o, tuple(o.shape[2:])
+    outs = [torch.full_like(t, float("nan")) for t in chain]
+    arr = (ctypes.c_void_p * nl)(*[t.data_ptr() for t in outs])
+    _lib.check(L.pulpo_avgpool2_pyramid_fwd(vp(x), arr, nl, B, 1, *shape, st))
+    torch.cuda.synchronize()
+    for a, b in zip(outs, chain):
+        assert torch.equal(a, b)
+    assert torch.equal(outs[0], torch.nn.functional.avg_pool3d(x, 2, 2, ceil_mode=True))
+    assert L.pulpo_avgpool2_pyramid_fwd(vp(x), arr, nl, B, 1, shape[0], shape[1], shape[2] - 2, st) == -3
 
 
 def test_avgpool2_golden(PF):
