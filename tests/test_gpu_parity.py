@@ -574,14 +574,17 @@ def _run_plan(g_or_inputs, total, latent, size, B, multi_stream=True, graph=Fals
     return plan
 
 
-@pytest.mark.parametrize("multi_stream,graph,fuse_reg", [(False, False, True), (True, False, False), (True, True, True)])
-def test_plan_golden(PF, multi_stream, graph, fuse_reg):
+@pytest.mark.parametrize("multi_stream,graph,fuse_reg,kw", [
+    (False, False, True, {}), (True, False, False, {}), (True, True, True, {}),
+    (True, True, True, {"fuse_combine": True, "pool_pyramid": False, "aux_early": True}),
+    (False, False, True, {"fuse_combine": True})])
+def test_plan_golden(PF, multi_stream, graph, fuse_reg, kw):
     g = load_golden("hot_path_3lvl")
     total, latent = int(g["total_levels"]), int(g["latent_levels"])
     size, B = list(g["x"].shape[2:]), g["x"].shape[0]
     inputs = (dev(g["x"]), dev(g["y"]), {l: dev(g["df%d" % l]) for l in range(latent)},
               {l: dev(g["mu%d" % l]) for l in range(latent)}, {l: dev(g["sigma%d" % l]) for l in range(latent)})
-    plan = _run_plan(inputs, total, latent, size, B, multi_stream, graph, fuse_reg=fuse_reg)
+    plan = _run_plan(inputs, total, latent, size, B, multi_stream, graph, fuse_reg=fuse_reg, **kw)
     losses = plan.losses.cpu().numpy()
     assert_loss_close(losses[0].sum(), g["kl"], "kl")
     assert_loss_close(losses[1].sum(), g["recon"], "recon")
