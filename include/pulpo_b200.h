@@ -99,12 +99,14 @@ int pulpo_vecint_bwd(const float *gout, const void *saved, float *gvec, void *sc
 typedef struct pulpo_vecint_level {
     const float *in;      /* fwd: vec [B,3,D0,D1,D2]        bwd: gout */
     float *out;           /* fwd: integrated field          bwd: gvec */
-    void *ws;             /* fwd: states (pulpo_vecint_ws_bytes)   bwd: the saved states of the forward */
+    void *ws;             /* fwd: states (pulpo_vecint_ws_bytes)   bwd: the saved states of the forward (opaque layout) */
     size_t ws_bytes;      /* fwd only */
     void *scratch;        /* bwd only (pulpo_vecint_bwd_scratch_bytes) */
     size_t scratch_bytes; /* bwd only */
     int D0, D1, D2;
 } pulpo_vecint_level;
+/* Batches of large volumes (>= 2^19 voxels per item over all levels) run one item after the other so that one
+ * item's states stay L2-resident; small volumes share one launch. */
 int pulpo_vecint_multi_fwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int save_steps,
                            int B, int coord_mode, pulpo_stream_t stream);
 int pulpo_vecint_multi_bwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int B,

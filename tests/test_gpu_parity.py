@@ -238,6 +238,57 @@ def test_combine_vecint_multi_matches_separate_launches(PF, shapes, B):
     assert L.pulpo_combine_vecint_multi_fwd(arr, indiv, 2, n, 1, B, 0, st) == -2
 
 
+def test_vecint_large_batch_runs_per_item_and_matches_single_items(PF):
+    """Batches of large volumes are integrated item by item (L2-resident states; opaque per-item layout of the
+    saved states): forward bit-identical to B=1 calls, backward within the gradient tolerance -- through the
+    autograd wrapper (single level) and the joint multi-level launch."""
+    import ctypes
+    from pulpo_b200 import _lib, synthetic as syn
+    L = _lib.lib()
+    n, B = 7, 2
+    shapes = [(80, 96, 112), (40, 48, 56)]
+    v = [syn.make_field(sh, 3 + i, batch=B, max_abs=3.0).cuda() for i, sh in enumerate(shapes)]
+    g = [syn.make_field(sh, 9 + i, batch=B, max_abs=1.0).cuda() for i, sh in enumerate(shapes)]
+    # autograd wrapper, level 0 alone (2 x 860160 voxels -> split)
+    vb = v[0].clone().requires_grad_(True)
+    ob = PF.vecint(vb, n)
+    ob.backward(g[0])
+    for b in range(B):
+        v1 = v[0][b:b + 1].clone().requires_grad_(True)
+        o1 = PF.vecint(v1, n)
+        o1.backward(g[0][b:b + 1])
+        assert torch.equal(ob[b:b + 1].detach(), o1.detach()), "item %d forward differs" % b
+        assert_grad_close(vb.grad[b:b + 1].cpu().numpy(), v1.grad.cpu().numpy(), "item %d gradient" % b)
+    with torch.no_grad():
+        assert torch.equal(PF.vecint(v[0], n), ob.detach())       # two-state (no saved steps) path
+    # joint two-level launch
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ws = [torch.empty(L.pulpo_vecint_ws_bytes(n, 1, B, *sh) // 4, device="cuda") for sh in shapes]
+    scr = [torch.empty(L.pulpo_vecint_bwd_scratch_bytes(B, *sh) // 4, device="cuda") for sh in shapes]
+    out = [torch.empty_like(t) for t in v]
+    gv = [torch.empty_like(t) for t in v]
+    arr = (_lib.VecIntLevel * 2)()
+    for i, sh in enumerate(shapes):
+        arr[i] = _lib.VecIntLevel(v[i].data_ptr(), out[i].data_ptr(), ws[i].data_ptr(), ws[i].numel() * 4,
+                                  scr[i].data_ptr(), scr[i].numel() * 4, *sh)
+    _lib.check(L.pulpo_vecint_multi_fwd(arr, 2, n, 1, B, 0, st))
+    for i in range(2):
+        arr[i].inp, arr[i].out = g[i].data_ptr(), gv[i].data_ptr()
+    _lib.check(L.pulpo_vecint_multi_bwd(arr, 2, n, B, 0, st))
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], ob.detach())
+    assert_grad_close(gv[0].cpu().numpy(), vb.grad.cpu().numpy(), "joint launch gradient, level 0")
+    v1 = v[1].clone().requires_grad_(True)
+    o1 = PF.vecint(v1, n)          # level 1 alone is below the split threshold: one joint launch
+    o1.backward(g[1])
+    assert torch.equal(out[1], o1.detach())
+    assert_grad_close(gv[1].cpu().numpy(), v1.grad.cpu().numpy(), "joint launch gradient, level 1")
+    # a workspace sized for one item only is refused
+    arr[0].inp, arr[0].out = v[0].data_ptr(), out[0].data_ptr()
+    arr[0].ws_bytes = ws[0].numel() * 4 // 2
+    assert L.pulpo_vecint_multi_fwd(arr, 1, n, 1, B, 0, st) == -4
+
+
 def test_vecint_zero_steps_and_zero_field(PF):
     v = torch.randn(1, 3, 6, 8, 10, device="cuda")
     assert torch.equal(PF.vecint(v, 0), v)
