@@ -75,6 +75,7 @@ __device__ __forceinline__ NccPoint ncc_point(float sI, float sJ, float sII, flo
     return r;
 }
 
+constexpr int NCC_MAX_CTAS = 320;   // >= 2 CTAs per SM
 struct NccTmaParams {
     const float *I, *J;            // bwd epilogue (target, pred)
     float *o0, *o1, *o2;           // fwd: a, b, c (nullable) ; bwd: o0 = gpred
@@ -87,6 +88,8 @@ struct NccTmaParams {
     int BC, D0, D1, D2, xt, yt;
     long long total_planes;        // BC * yt * xt * D0
     int zchunks;                   // > 0: aligned (column, z chunk) grid with this many chunks per column
+    int nbounds;                   // > 0: cost-balanced split, CTA i owns linear planes [bounds[i], bounds[i+1])
+    int bounds[NCC_MAX_CTAS + 1];
 };
 
 

@@ -128,7 +128,13 @@ ncc_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     const long long T = p.total_planes;
     long long q = (T * blockIdx.x) / gridDim.x;
     long long q_end = (T * (blockIdx.x + 1)) / gridDim.x;
-    if (p.zchunks > 0) {
+    if (p.nbounds > 0) {
+        // cost-balanced mode: every segment a CTA starts costs its 2R halo planes; the host split the linear space so
+        // that planes + halos are even across CTAs (a plain even split leaves the CTAs that cross a column boundary
+        // with two halos, the aligned grid leaves CTA slots empty)
+        q = p.bounds[blockIdx.x];
+        q_end = p.bounds[blockIdx.x + 1];
+    } else if (p.zchunks > 0) {
         // aligned mode: CTA = (column, z chunk) with the same chunk boundaries in every column and neighbouring
         // columns on neighbouring CTAs, so the CTAs that share halo rows read them at about the same time (L2 hits)
         const int ncols = (int)(T / D0);
@@ -424,6 +430,48 @@ static int ncc_tma_zchunks(int BC, int D0, int D1, int D2, int grid)
     return (grid / ncols == cap / ncols && ncols <= cap) ? (int)(grid / ncols) : 0;
 }
 
+// Cost-balanced split of the linearised (column, z) space over `grid` CTAs: a CTA pays H = 2R halo planes for every
+// segment it starts.  Smallest per-CTA budget T for which a greedy walk needs at most `grid` CTAs (binary search);
+// a CTA does not start a segment it could not extend by at least `minseg` planes.
+static bool ncc_balanced_bounds(NccTmaParams &p, int grid, int win)
+{
+    const long long ncols = p.total_planes / p.D0;
+    if (grid > NCC_MAX_CTAS || p.total_planes >= (1ll << 31) || grid < 2) return false;
+    const int H = 2 * (win / 2), D0 = p.D0, minseg = H;
+    auto walk = [&](int T, int *bounds) -> int {
+        int cta = 0, budget = T;
+        long long q = 0;
+        if (bounds) bounds[0] = 0;
+        for (long long c = 0; c < ncols; ++c) {
+            int remaining = D0;
+            while (remaining > 0) {
+                if (budget < H + (remaining < minseg ? remaining : minseg)) {
+                    ++cta;
+                    if (bounds && cta <= NCC_MAX_CTAS) bounds[cta] = (int)q;
+                    budget = T;
+                }
+                int take = budget - H;
+                if (take > remaining) take = remaining;
+                remaining -= take; q += take; budget -= H + take;
+            }
+        }
+        return cta + 1;
+    };
+    int lo = H + 1, hi = D0 + H;
+    if (walk(hi, nullptr) > grid) return false;
+    while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if (walk(mid, nullptr) <= grid) hi = mid; else lo = mid + 1;
+    }
+    const int used = walk(lo, p.bounds);
+    for (int i = used; i <= grid; ++i) p.bounds[i] = (int)p.total_planes;
+    p.nbounds = grid;
+    return true;
+}
+
+static int ncc_tma_dispatch(const CUtensorMap &t0, const CUtensorMap &t1, const CUtensorMap &t2, const NccTmaParams &p, int grid,
+                            int win, bool fwd, cudaStream_t st);
+
 // in2 == nullptr selects the forward (inputs: target, pred), else the backward (a, b, c)
 int ncc_tma_launch(const float *in0, const float *in1, const float *in2, NccTmaParams p, int win, cudaStream_t st)
 {
@@ -441,6 +489,25 @@ int ncc_tma_launch(const float *in0, const float *in1, const float *in2, NccTmaP
     p.total_planes = (long long)p.BC * p.xt * p.yt * p.D0;
     const int grid = ncc_tma_grid(p.BC, p.D0, p.D1, p.D2, win);
     p.zchunks = ncc_tma_zchunks(p.BC, p.D0, p.D1, p.D2, grid);
+    p.nbounds = 0;
+#ifdef PULPO_NCC_BALANCED
+    {
+        int dev = 0, sms = kSMs;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int cap = sms * NT_CTAS_PER_SM;
+        if (p.total_planes / (2 * win) >= cap && ncc_balanced_bounds(p, cap, win)) {
+            p.zchunks = 0;
+            return ncc_tma_dispatch(t0, t1, t2, p, cap, win, fwd, st);
+        }
+    }
+#endif
+    return ncc_tma_dispatch(t0, t1, t2, p, grid, win, fwd, st);
+}
+
+static int ncc_tma_dispatch(const CUtensorMap &t0, const CUtensorMap &t1, const CUtensorMap &t2, const NccTmaParams &p, int grid,
+                            int win, bool fwd, cudaStream_t st)
+{
 #define PULPO_NCC_TMA_CASE(WW)                                                   \
     case WW:                                                                     \
         return fwd ? ncc_tma_launch_w<WW, true>(t0, t1, t2, p, grid, st)         \
