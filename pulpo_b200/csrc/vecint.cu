@@ -202,6 +202,27 @@ __device__ __forceinline__ float4 ld4v(const float4 *p)
     return r;
 }
 
+// Asynchronous 16-byte global -> shared copies (LDGSTS): the voxel's own values of the next planes travel to a
+// per-lane shared-memory slot without holding registers, so several planes can be in flight per warp.  The
+// integration kernels are bound by memory-level parallelism (a warp walks its z run serially and 16-24 warps
+// per SM with one plane each in flight cover ~1/4 of the bytes HBM latency needs): timing experiments without
+// gathers and with one reduction still took 216 of 311 us.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+#ifndef PULPO_VI_RING
+#define PULPO_VI_RING 4
+#endif
+constexpr int VI_RING = PULPO_VI_RING;   // planes of own values staged per warp (VI_RING - 1 in flight)
+
 // The footprint is always 2x2x2 in-bounds (see make_tap): fixed +1 / +D2 / +D1*D2 neighbours.
 // Walking a z run, the upper four corners of one plane are the lower four of the next whenever the
 // footprint moved by exactly one plane (the usual case for a smooth field): those are kept in
@@ -516,42 +537,77 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
             const float4 *vol = vk + vb;
             float4 *acc = Yb + vb;
             int off = t.valid ? (t.z0 * g.D1 + t.y) * g.D2 + t.x : 0;
+#ifdef PULPO_VI_BWD_XYZ
+            // own values (incoming gradient X, saved state v_k) of the next planes: asynchronous copies into this
+            // lane's slots of the warp's ring, VI_RING - 1 planes ahead
+            extern __shared__ __align__(16) float4 vi_ring[];
+            float4 *ring = vi_ring + (threadIdx.x >> 5) * (VI_RING * 64) + lane;   // slot d: X at ring[d*64], v at ring[d*64+32]
+            const int nz = t.z1 - t.z0;
+#pragma unroll
+            for (int d = 0; d < VI_RING - 1; ++d) {
+                if (t.valid && d < nz) {
+                    cp_async16(ring + d * 64, Pa + vb + off + (i64)d * sz);
+                    cp_async16(ring + d * 64 + 32, vol + off + (i64)d * sz);
+                }
+                cp_async_commit();
+            }
+#endif
             F3 carry = {0.f, 0.f, 0.f};   // corner (dz=1, dy=0, dx=0) of the previous plane, already combined in x and y
             F3 up[4];                     // COMBINE == 2: all four upper corners of the previous plane
 #pragma unroll
             for (int d = 0; d < 4; ++d) up[d] = carry;
             int carry_addr = NOADDR;
+#ifndef PULPO_VI_BWD_XYZ
             float4 Gn = zero4, vn = zero4;
             if (t.valid) {
-#ifdef PULPO_VI_BWD_XYZ
-                Gn = ld4v(Pa + vb + off);
-#else
                 const float4 p = ld4v(Pa + vb + off), y = ld4v(Ya + vb + off);
                 Gn = make_float4(p.x + y.x, p.y + y.y, p.z + y.z, 0.0f);
-#endif
                 vn = ld4v(vol + off);
             }
+#endif
             Corners kc;
             int prev_base = NOBASE;
+            int slot = 0;   // ring slot of the current plane
             for (int z = t.z0; z < t.z1; ++z, off += sz) {
+#ifdef PULPO_VI_BWD_XYZ
+                {   // request plane z + VI_RING - 1 into the slot consumed one iteration ago, then wait for plane z
+                    const int ahead = z - t.z0 + VI_RING - 1;
+                    const int wslot = slot == 0 ? VI_RING - 1 : slot - 1;
+                    if (t.valid && ahead < nz) {
+                        cp_async16(ring + wslot * 64, Pa + vb + off + (i64)(VI_RING - 1) * sz);
+                        cp_async16(ring + wslot * 64 + 32, vol + off + (i64)(VI_RING - 1) * sz);
+                    }
+                    cp_async_commit();
+                    cp_async_wait<VI_RING - 1>();
+                }
+                float4 G = zero4, v = zero4;
+                if (t.valid) {
+                    G = ring[slot * 64];
+                    v = ring[slot * 64 + 32];
+                    Ya[vb + off] = zero4;   // clear it for the step after next
+                }
+                slot = slot == VI_RING - 1 ? 0 : slot + 1;
+#else
                 const float4 G = Gn, v = vn;
                 if (t.valid) {
                     Ya[vb + off] = zero4;   // read above (or one iteration ago): clear it for the step after next
                     if (z + 1 < t.z1) {     // next plane's own values, requested ahead of this plane's gathers
-#ifdef PULPO_VI_BWD_XYZ
-                        Gn = ld4v(Pa + vb + off + sz);
-#else
                         const float4 p = ld4v(Pa + vb + off + sz), y = ld4v(Ya + vb + off + sz);
                         Gn = make_float4(p.x + y.x, p.y + y.y, p.z + y.z, 0.0f);
-#endif
                         vn = ld4v(vol + off + sz);
                     }
                 }
+#endif
                 float uz, uy, ux;
                 const VFoot f = make_vfoot<MODE>((float)z, yf, xf, v, g, &uz, &uy, &ux);
                 const int A = t.valid ? f.base : NOADDR;
                 if (t.valid) {
+#ifdef PULPO_VI_EXP_NOGATHER   // timing experiment only (wrong results): no corner gathers
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) kc.c[d] = v;
+#else
                     gather8(vol, f.base, vst, f.base == prev_base + sz, kc);
+#endif
                     prev_base = f.base;
                     // q[d] = <corner_d, G> over the 3 channels
                     float q[8];
@@ -598,7 +654,12 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
                             red3(q, up[0]); red3(q + 1, up[1]); red3(q + sy, up[2]); red3(q + sy + 1, up[3]);
                         }
                         float4 *q = acc + A;
+#ifdef PULPO_VI_EXP_NORED      // timing experiment only (wrong results): one reduction instead of four
+                        c[0].x += c[1].x + c[2].x + c[3].x; c[0].y += c[1].y + c[2].y + c[3].y; c[0].z += c[1].z + c[2].z + c[3].z;
+                        red3(q, c[0]);
+#else
                         red3(q, c[0]); red3(q + 1, c[1]); red3(q + sy, c[2]); red3(q + sy + 1, c[3]);
+#endif
 #pragma unroll
                         for (int d = 0; d < 4; ++d) up[d] = c[4 + d];
                         carry_addr = A + sz;
@@ -696,12 +757,13 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
 }
 
 template <typename K>
-static int coop_ctas(K kernel, int threads)
+static int coop_ctas(K kernel, int threads, size_t smem = 0)
 {
     int dev = 0, sms = kSMs, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;
 }
@@ -738,9 +800,9 @@ static void plan_items(VMulti &m, int total_warps)
 }
 
 template <typename K>
-static int launch_coop(K kernel, int threads, VMulti &m, void **args, cudaStream_t st)
+static int launch_coop(K kernel, int threads, VMulti &m, void **args, cudaStream_t st, size_t smem = 0)
 {
-    const int ctas = coop_ctas(kernel, threads);
+    const int ctas = coop_ctas(kernel, threads, smem);
     // lanes cover whole 8x4 patches, so size the grid by patch-padded voxels
     i64 padded = 0;
     for (int l = 0; l < m.n; ++l) padded += (i64)m.l[l].g.B * m.l[l].g.D0 * m.l[l].g.npy * VI_PY * m.l[l].g.npx * VI_PX;
@@ -748,7 +810,7 @@ static int launch_coop(K kernel, int threads, VMulti &m, void **args, cudaStream
     if (grid > ctas) grid = ctas;
     if (grid < 1) grid = 1;
     plan_items(m, (int)grid * (threads / 32));
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)kernel, dim3((unsigned int)grid), dim3(threads), args, 0, st);
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)kernel, dim3((unsigned int)grid), dim3(threads), args, smem, st);
     return e == cudaSuccess ? launch_status() : PULPO_ERR_CUDA;
 }
 
@@ -935,8 +997,13 @@ static int vecint_multi_bwd_impl(const pulpo_vecint_level *levels, int combine, 
     // (0), 0x200 -> lane + plane combining (1)
     PULPO_REQUIRE(variant <= 2, PULPO_ERR_UNSUPPORTED);
     const int comb = variant == 0 ? 2 : variant == 1 ? 0 : 1;
+#ifdef PULPO_VI_BWD_XYZ
+    const size_t bwd_smem = (size_t)(VI_BWD_THREADS / 32) * VI_RING * 64 * sizeof(float4);   // per-warp rings of own values
+#else
+    const size_t bwd_smem = 0;
+#endif
 #define PULPO_VI_BWD_CASE(M, C) \
-    if (coord_mode == M && comb == C) return launch_coop(vecint_bwd_kernel<M, C>, VI_BWD_THREADS, m, args, st);
+    if (coord_mode == M && comb == C) return launch_coop(vecint_bwd_kernel<M, C>, VI_BWD_THREADS, m, args, st, bwd_smem);
     PULPO_VI_BWD_CASE(0, 2) PULPO_VI_BWD_CASE(1, 2) PULPO_VI_BWD_CASE(2, 2)
     PULPO_VI_BWD_CASE(0, 0) PULPO_VI_BWD_CASE(2, 0)
     PULPO_VI_BWD_CASE(0, 1) PULPO_VI_BWD_CASE(2, 1)
