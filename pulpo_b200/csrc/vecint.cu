@@ -212,6 +212,12 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
     const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+// same, allocating in L1: the saved state is gathered again by this and neighbouring warps
+__device__ __forceinline__ void cp_async16_ca(void *smem_dst, const void *gsrc)
+{
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait()
@@ -222,6 +228,9 @@ __device__ __forceinline__ void cp_async_wait()
 #define PULPO_VI_RING 4
 #endif
 constexpr int VI_RING = PULPO_VI_RING;   // planes of own values staged per warp (VI_RING - 1 in flight)
+// Backward only.  Measured: backward 309 -> 269 us (ring depths 2, 3, 4 and 6 alike); the forward, whose gathers hit
+// L1 70 % of the time and whose register prefetch one plane ahead suffices, got slower with the same ring
+// (115 -> 128 us) and keeps its register prefetch.
 
 // The footprint is always 2x2x2 in-bounds (see make_tap): fixed +1 / +D2 / +D1*D2 neighbours.
 // Walking a z run, the upper four corners of one plane are the lower four of the next whenever the
@@ -547,7 +556,7 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
             for (int d = 0; d < VI_RING - 1; ++d) {
                 if (t.valid && d < nz) {
                     cp_async16(ring + d * 64, Pa + vb + off + (i64)d * sz);
-                    cp_async16(ring + d * 64 + 32, vol + off + (i64)d * sz);
+                    cp_async16_ca(ring + d * 64 + 32, vol + off + (i64)d * sz);
                 }
                 cp_async_commit();
             }
@@ -575,7 +584,7 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
                     const int wslot = slot == 0 ? VI_RING - 1 : slot - 1;
                     if (t.valid && ahead < nz) {
                         cp_async16(ring + wslot * 64, Pa + vb + off + (i64)(VI_RING - 1) * sz);
-                        cp_async16(ring + wslot * 64 + 32, vol + off + (i64)(VI_RING - 1) * sz);
+                        cp_async16_ca(ring + wslot * 64 + 32, vol + off + (i64)(VI_RING - 1) * sz);
                     }
                     cp_async_commit();
                     cp_async_wait<VI_RING - 1>();
