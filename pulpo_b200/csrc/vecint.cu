@@ -230,7 +230,12 @@ __device__ __forceinline__ void cp_async_wait()
 constexpr int VI_RING = PULPO_VI_RING;   // planes of own values staged per warp (VI_RING - 1 in flight)
 // Backward only.  Measured: backward 309 -> 269 us (ring depths 2, 3, 4 and 6 alike); the forward, whose gathers hit
 // L1 70 % of the time and whose register prefetch one plane ahead suffices, got slower with the same ring
-// (115 -> 128 us) and keeps its register prefetch.
+// (115 -> 128 us) and keeps its register prefetch.  Also measured and not kept: staging the NEXT plane's four upper
+// corners the same way (footprint base from the next plane's own value in the ring, double-buffered slots): correct,
+// but 279 vs 269 us -- the gathers cost L1 throughput, not exposed latency, and the extra sample-position
+// computation plus 64 KB more shared memory (less L1) outweigh the overlap.  Timing experiments on the kernel
+// before the ring (wrong results, timing only): no gathers 269 us, one scatter reduction instead of four 277 us,
+// both 216 us of 311 us -- most of the time was the serial own-load chain, which the ring removes.
 
 // The footprint is always 2x2x2 in-bounds (see make_tap): fixed +1 / +D2 / +D1*D2 neighbours.
 // Walking a z run, the upper four corners of one plane are the lower four of the next whenever the
@@ -611,12 +616,7 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
                 const VFoot f = make_vfoot<MODE>((float)z, yf, xf, v, g, &uz, &uy, &ux);
                 const int A = t.valid ? f.base : NOADDR;
                 if (t.valid) {
-#ifdef PULPO_VI_EXP_NOGATHER   // timing experiment only (wrong results): no corner gathers
-#pragma unroll
-                    for (int d = 0; d < 8; ++d) kc.c[d] = v;
-#else
                     gather8(vol, f.base, vst, f.base == prev_base + sz, kc);
-#endif
                     prev_base = f.base;
                     // q[d] = <corner_d, G> over the 3 channels
                     float q[8];
@@ -663,12 +663,7 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
                             red3(q, up[0]); red3(q + 1, up[1]); red3(q + sy, up[2]); red3(q + sy + 1, up[3]);
                         }
                         float4 *q = acc + A;
-#ifdef PULPO_VI_EXP_NORED      // timing experiment only (wrong results): one reduction instead of four
-                        c[0].x += c[1].x + c[2].x + c[3].x; c[0].y += c[1].y + c[2].y + c[3].y; c[0].z += c[1].z + c[2].z + c[3].z;
-                        red3(q, c[0]);
-#else
                         red3(q, c[0]); red3(q + 1, c[1]); red3(q + sy, c[2]); red3(q + sy + 1, c[3]);
-#endif
 #pragma unroll
                         for (int d = 0; d < 4; ++d) up[d] = c[4 + d];
                         carry_addr = A + sz;
