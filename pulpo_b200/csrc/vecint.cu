@@ -512,7 +512,9 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
             const float *f = L.in + (i64)b * 3 * S + v;
             Pa[i] = make_float4(__ldg(f), __ldg(f + S), __ldg(f + 2 * S), 0.0f);
             Ya[i] = zero4;
+#ifndef PULPO_VI_BWD_XYZ
             Yb[i] = zero4;
+#endif
         }
     }
     int flip = 0;   // which (P, Y) pair holds the incoming gradient of the current step
@@ -742,7 +744,11 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
                 unsigned int b = i / S, v = i - b * S;
                 unsigned int zy = v / (unsigned int)d2, x = v - zy * (unsigned int)d2;
                 unsigned int z = zy / (unsigned int)d1, yy = zy - z * (unsigned int)d1;
+#ifdef PULPO_VI_BWD_XYZ
+                const float4 p = Pa[i], y = zero4;   // the last step's Z state is all zero: not read
+#else
                 const float4 p = Pa[i], y = Ya[i];
+#endif
                 const float *go = F.out + (i64)b * 3 * Sf;
                 float *o = L.out + (i64)b * 3 * S + v;
                 o[0] = (p.x + y.x) * scale + 2.0f * up2_adjoint_point(go, d0, d1, d2, (int)z, (int)yy, (int)x);
@@ -753,7 +759,11 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
         }
         for (unsigned int i = tid; i < N; i += nthr) {
             unsigned int b = i / S, v = i - b * S;
+#ifdef PULPO_VI_BWD_XYZ
+            const float4 p = Pa[i], y = zero4;   // the last step's Z state is all zero: not read
+#else
             const float4 p = Pa[i], y = Ya[i];
+#endif
             float *o = L.out + (i64)b * 3 * S + v;
             o[0] = (p.x + y.x) * scale; o[S] = (p.y + y.y) * scale; o[2 * S] = (p.z + y.z) * scale;
         }
