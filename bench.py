@@ -36,6 +36,7 @@ WORKLOADS = {
     "oasis_160x192x224_5tot_4lat": ([160, 192, 224], 5, 4),
     "cube64_4tot_3lat": ([64, 64, 64], 4, 3),
 }
+CPU_WORKLOADS = ("oasis_160x192x224_5tot_4lat", "cube64_4tot_3lat")
 ALGO_BYTES_PER_VOXEL = 220.9   # SURVEY.md 8d, config 2, fwd+bwd incl. L2_reg
 METRIC = "hot-path fwd+bwd throughput (warp + integration + pyramid + NCC/KL/L2)"
 UNIT = "Gvoxel/s"
@@ -161,10 +162,13 @@ def _cpu_hot_path_step(T, torch, inputs, total_levels):
     return time.perf_counter() - t0, float(loss.detach())
 
 
-def cpu_baseline(budget_s, steps=1, warmup=0, want_workload=None):
+def cpu_baseline(budget_s, steps=1, warmup=0, want_workload=None, allow_smaller=True):
     """Reference PyTorch CPU path (oracle/torch_ref.py: the same ATen ops the reference calls)
-    on the host cores, on a bounded sample of the workload: the largest shape whose
-    (steps+warmup) passes fit the budget, calibrated on a 32^3 pass."""
+    on the host cores, on a bounded sample of the workload, calibrated on a 32^3 pass.
+    ``allow_smaller=False`` (the --impl reference arm): always the requested workload itself; when
+    (steps + warmup) passes do not fit the budget, fewer passes are run (never a smaller volume) and
+    the number actually run is reported.  ``allow_smaller=True`` (the in-line cpu_baseline of our own
+    arm, ~25 s): the largest shape whose passes fit the budget, named in ``sample``."""
     import torch
     from oracle import torch_ref as T
     from pulpo_b200 import synthetic as syn
@@ -178,12 +182,20 @@ def cpu_baseline(budget_s, steps=1, warmup=0, want_workload=None):
                   ("cube64_4tot_3lat", [64, 64, 64], 4, 3), ("cube32_4tot_3lat", [32, 32, 32], 4, 3)]
     if want_workload:
         candidates = [c for c in candidates if c[0] == want_workload] + candidates
-    chosen = candidates[-1]
-    for c in candidates:
-        n = c[1][0] * c[1][1] * c[1][2]
-        if per_voxel * n * 1.3 * (steps + warmup) <= budget_s:
-            chosen = c
-            break
+    if not allow_smaller:
+        chosen = candidates[0]
+        est = per_voxel * chosen[1][0] * chosen[1][1] * chosen[1][2] * 1.3
+        fit = max(1, int(budget_s / max(est, 1e-9)))
+        if steps + warmup > fit:          # fewer passes of the SAME workload, never another one
+            warmup = min(warmup, 1 if fit > 1 else 0)
+            steps = max(1, fit - warmup)
+    else:
+        chosen = candidates[-1]
+        for c in candidates:
+            n = c[1][0] * c[1][1] * c[1][2]
+            if per_voxel * n * 1.3 * (steps + warmup) <= budget_s:
+                chosen = c
+                break
     name, size, total, latent = chosen
     inputs = syn.make_hot_path_inputs(size, total, latent, seed=0)
     for _ in range(warmup):
@@ -191,9 +203,10 @@ def cpu_baseline(budget_s, steps=1, warmup=0, want_workload=None):
     times = [_cpu_hot_path_step(T, torch, inputs, total)[0] for _ in range(steps)]
     nvox = size[0] * size[1] * size[2]
     tot = sum(times)
-    return {"value": nvox * steps / tot / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d step(s) of %s (B=1) fwd+bwd via oracle/torch_ref.py (torch %s CPU, %d threads), %.2f s/step"
-                      % (steps, name, torch.__version__, cores, tot / steps)}, tot / steps, name
+    return {"value": nvox * steps / tot / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "workload": name,
+            "steps_run": steps, "warmup_run": warmup,
+            "sample": "%d step(s) (+%d warm-up) of %s (B=1) fwd+bwd via oracle/torch_ref.py (torch %s CPU, %d threads), %.2f s/step"
+                      % (steps, warmup, name, torch.__version__, cores, tot / steps)}, tot / steps, name
 
 
 def torch_cuda_baseline(dev, inputs, total_levels, steps=3):
@@ -227,15 +240,23 @@ def torch_cuda_baseline(dev, inputs, total_levels, steps=3):
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle/torch_ref.py, the same ATen ops
+    the reference calls) on all host cores, ALWAYS on the workload named in config.workload (the same one our arm
+    runs); if steps + warmup passes would exceed the time budget, fewer passes of that same workload are run
+    (cpu_baseline.steps_run says how many)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, ms, name = cpu_baseline(budget_s=150.0, steps=args.steps, warmup=args.warmup,
-                                want_workload=args.workload)
+    if args.workload not in CPU_WORKLOADS:
+        _emit({"impl": "reference", "unavailable": "workload %s has no CPU reference arm" % args.workload})
+        return
+    cb, ms, name = cpu_baseline(budget_s=args.ref_budget_s, steps=args.steps, warmup=args.warmup,
+                                want_workload=args.workload, allow_smaller=False)
+    assert name == args.workload
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "sample_workload": name, "batch_per_gpu": 1,
+            "config": {"workload": name, "same_config": True, "batch_per_gpu": 1, "steps_run": cb["steps_run"],
                        "note": "reference PyTorch CPU path on host cores; rank 0 only"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -581,6 +602,8 @@ def main():
     ap.add_argument("--field-max-abs", type=float, default=3.0,
                     help="max |v| of every level's synthetic velocity field in that level's voxels (SURVEY 8d: 3; the "
                          "coarse-to-fine sum then reaches ~45 level-0 voxels)")
+    ap.add_argument("--ref-budget-s", type=float, default=600.0,
+                    help="--impl reference: wall-clock budget; passes of the SAME workload are dropped (never the volume shrunk) to fit")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -242,6 +242,20 @@ int pulpo_moments_merge(float *mean_a, float *m2_a, int count_a, const float *me
 int pulpo_moments_std(const float *m2, float *std_out, int count, long long n,
                       pulpo_stream_t stream);
 
+/* ---- f-3 (rest): MSE map and global NCC(var, mse) of Evaluate.uncertainty, evaluate.py:1534-1545 ----
+ * pulpo_sqerr_update: acc (+)= (x - y)^2 per voxel, streamed over the MC samples (first != 0 overwrites);
+ *   the MSE map is acc / N (evaluate.py:1538: torch.mean((all_moved - y)**2, axis=0)).
+ * pulpo_global_ncc: Evaluate.ncc (evaluate.py:334-353, zero_norm=True) of two maps after per-map scaling,
+ *   a = scale_a * (square_a ? a_in^2 : a_in), v = scale_v * v_in (so the variance map std^2 and the mean of the
+ *   squared-error sums need no pass of their own):
+ *   out2[0] = sum((a - mean a) / (std a * n + 1e-15) * (v - mean v) / (std v + 1e-15)), population stds;
+ *   out2[1] = mean(a) (evaluate.py:1541 var.mean()).  ws: pulpo_global_ncc_ws_bytes(), zeroed once. */
+int pulpo_sqerr_update(const float *x, const float *y, float *acc, int first, long long n,
+                       pulpo_stream_t stream);
+size_t pulpo_global_ncc_ws_bytes(void);
+int pulpo_global_ncc(const float *a, const float *v, float scale_a, float scale_v, int square_a,
+                     long long n, float *out2, void *ws, size_t ws_bytes, pulpo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -220,9 +220,46 @@ def gen_jacdet():
     _save("jacdet", **arrs)
 
 
+def _reference_method_source(path, cls, name):
+    """Source of one method of the reference's evaluate.py, which cannot be imported here (matplotlib, seaborn,
+    h5py are absent): parsed with ast and compiled on its own -- the method body is the unmodified reference."""
+    import ast, textwrap
+    src = open(path).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name == name:
+                    return textwrap.dedent(ast.get_source_segment(src, fn))
+    raise KeyError(name)
+
+
+def gen_uncertainty():
+    """f-3: the per-pair numbers of Evaluate.uncertainty (evaluate.py:1534-1545) from explicit sample stacks:
+    moved_std = mean_c(std_n(all_moved)) (evaluate.py:243), mse = mean_n((all_moved - y)^2), var = moved_std^2,
+    ncc = Evaluate.ncc(var, mse) (the reference's own method, evaluate.py:334-353), var.mean()."""
+    torch.set_num_threads(1)
+    ns = {"np": np}
+    exec(_reference_method_source(os.path.join(ref_import.REF_ROOT, "evaluate.py"), "Evaluate", "ncc"), ns)
+    shape, N = (6, 10, 12), 9
+    g = torch.Generator().manual_seed(5)
+    y = torch.rand((1, 1) + shape, generator=g)
+    base = y + 0.1 * torch.randn((1, 1) + shape, generator=g)
+    amp = torch.rand((1, 1) + shape, generator=g) * 0.2
+    all_moved = base + amp * torch.randn((N, 1) + shape, generator=g)          # [N, 1, *S]
+    moved_std = torch.mean(torch.std(all_moved, axis=0), axis=0)                # evaluate.py:243
+    mse = np.array(torch.mean((all_moved - y) ** 2, axis=0).squeeze(0))        # evaluate.py:1538
+    var = np.array(moved_std ** 2)
+    ncc = ns["ncc"](None, var, mse)
+    _save("uncertainty", all_moved=all_moved, y=y, moved_std=moved_std, mse=mse, var=var,
+          ncc=np.float64(ncc), var_mean=np.float64(var.mean()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "jacdet":
         gen_jacdet()
+    elif len(sys.argv) > 1 and sys.argv[1] == "uncertainty":
+        gen_uncertainty()
     else:
         main()
         gen_jacdet()
+        gen_uncertainty()

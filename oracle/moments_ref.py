@@ -31,3 +31,32 @@ class TorchCpuOps:
     @staticmethod
     def std(m2, count):
         return torch.sqrt(m2 * torch.tensor(1.0 / (count - 1), dtype=torch.float32))
+
+    @staticmethod
+    def sqerr(x, y, acc, first):
+        d = (x - y.reshape(x.shape)) ** 2
+        if first:
+            acc.copy_(d)
+        else:
+            acc.add_(d)
+
+    @staticmethod
+    def global_ncc(a, v, scale_a, scale_v, square_a):
+        import numpy as np
+        a = a * a if square_a else a
+        r = ref_global_ncc((a * torch.tensor(scale_a, dtype=torch.float32)).numpy(),
+                           (v * torch.tensor(scale_v, dtype=torch.float32)).numpy())
+        return torch.tensor([r, float(np.mean(a.numpy() * np.float32(scale_a)))], dtype=torch.float32)
+
+
+def ref_global_ncc(a, v):
+    """Restatement of Evaluate.ncc (evaluate.py:334-353, zero_norm=True) on numpy arrays, fp32 like the reference:
+    both maps flattened and centred; the first divided by (population std x length + 1e-15), the second by
+    (population std + 1e-15); the result is their dot product (np.correlate in 'valid' mode of equal lengths)."""
+    import numpy as np
+    a = np.asarray(a).reshape(-1)
+    v = np.asarray(v).reshape(-1)
+    eps = 1e-15
+    an = (a - np.mean(a)) / (np.std(a) * len(a) + eps)
+    vn = (v - np.mean(v)) / (np.std(v) + eps)
+    return float(np.dot(an, vn))

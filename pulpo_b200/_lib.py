@@ -72,6 +72,9 @@ SIGNATURES = {
     "pulpo_moments_update": (_i, [_vp, _vp, _vp, _i, _ll, _vp]),
     "pulpo_moments_merge": (_i, [_vp, _vp, _i, _vp, _vp, _i, _ll, _vp]),
     "pulpo_moments_std": (_i, [_vp, _vp, _i, _ll, _vp]),
+    "pulpo_sqerr_update": (_i, [_vp, _vp, _vp, _i, _ll, _vp]),
+    "pulpo_global_ncc_ws_bytes": (_sz, []),
+    "pulpo_global_ncc": (_i, [_vp, _vp, _f, _f, _i, _ll, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

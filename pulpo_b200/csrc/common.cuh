@@ -129,6 +129,87 @@ __device__ __forceinline__ Tap make_tap(float vf, float d, const AxisConst &a, f
     return tp;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed (f32x2) variant: two voxels per instruction on Blackwell's FADD2 / FMUL2 / FFMA2.  The warp and
+// integration kernels are bound by instruction issue, and the sample-position chain is most of their
+// arithmetic; two voxels of the same axis share every constant, so the chain packs perfectly.  Same values,
+// bit for bit, as sample_pos / make_tap above -- two steps of the chain are fused where the fusion is exact:
+//   * n + 1 with n = 2 * (q - 0.5):  n is exact (a power-of-two scaling), so RN(n + 1) == fma(q - 0.5, 2, 1);
+//   * (t - 1) * 0.5 with t = RN((n + 1) * S):  halving commutes with rounding (t - 1 is never subnormal: it is 0
+//     or at least one ulp of a value near 1), so RN(t - 1) / 2 == fma(t, 0.5, -0.5).
+struct AxisConst2 {   // AxisConst with every constant duplicated into both halves of a register pair
+    float2 S, nSm1, rcp;
+    float Sm1, tmax, gmul, kf;
+};
+
+__host__ __device__ inline AxisConst2 make_axis2(int S)
+{
+    const AxisConst a = make_axis(S);
+    AxisConst2 r;
+    r.S.x = r.S.y = a.S;
+    r.nSm1.x = r.nSm1.y = -a.Sm1;
+    r.rcp.x = r.rcp.y = a.rcp;
+    r.Sm1 = a.Sm1; r.tmax = a.tmax; r.gmul = a.gmul; r.kf = a.kf;
+    return r;
+}
+
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// non-finite / absurd loc: NaN and +huge must end at S-1, -huge at 0, like the division-based chain does; clamping
+// loc itself (IEEE minNum drops the NaN in favour of the bound) keeps the FMA chain below finite
+__device__ __forceinline__ float tame(float x) { return fmaxf(fminf(x, 1e30f), -1e30f); }
+
+template <int MODE>
+__device__ __forceinline__ float2 sample_pos2(float2 vf, float2 d, const AxisConst2 &a)
+{
+    float2 loc = __fadd2_rn(vf, d);
+    if (MODE == PULPO_COORD_FAST) return __ffma2_rn(loc, splat2(a.kf), splat2(-0.5f));
+    float2 q;
+    if (MODE == PULPO_COORD_CPU_EXACT) {
+        loc.x = tame(loc.x); loc.y = tame(loc.y);
+        const float2 q0 = __fmul2_rn(loc, a.rcp);
+        const float2 r0 = __ffma2_rn(a.nSm1, q0, loc);
+        const float2 q1 = __ffma2_rn(r0, a.rcp, q0);
+        const float2 r1 = __ffma2_rn(a.nSm1, q1, loc);
+        q = __ffma2_rn(r1, a.rcp, q1);
+    } else {
+        q = __fmul2_rn(loc, a.rcp);
+    }
+    const float2 h = __fadd2_rn(q, splat2(-0.5f));
+    const float2 n1 = __ffma2_rn(h, splat2(2.0f), splat2(1.0f));          // == RN(2 * (q - 0.5) + 1)
+    if (MODE == PULPO_COORD_CPU_EXACT) {
+        const float2 t = __fmul2_rn(n1, a.S);
+        return __ffma2_rn(t, splat2(0.5f), splat2(-0.5f));               // == RN(t - 1) * 0.5
+    }
+    const float2 t = __ffma2_rn(n1, a.S, splat2(-1.0f));                   // torch-CUDA contracts (n + 1) * S - 1
+    return __fmul2_rn(t, splat2(0.5f));
+}
+
+struct Tap2 {
+    int bits0, bits1;      // float bits of 2^23 + i for the two voxels
+    float2 w0, w1;         // weights of corners i and i+1
+    float2 u;              // unclamped sample positions (backward: gradient mask)
+    int fl0, fl1;          // floor(p) (index dump)
+};
+
+template <int MODE>
+__device__ __forceinline__ Tap2 make_tap2(float2 vf, float2 d, const AxisConst2 &a)
+{
+    Tap2 tp;
+    tp.u = sample_pos2<MODE>(vf, d, a);
+    float2 p;
+    p.x = clip_pos(tp.u.x, a.Sm1); p.y = clip_pos(tp.u.y, a.Sm1);
+    const float2 t = __fadd2_rz(p, splat2(8388608.0f));
+    float2 tc;
+    tc.x = fminf(t.x, a.tmax); tc.y = fminf(t.y, a.tmax);
+    const float2 fl = __fadd2_rn(tc, splat2(-8388608.0f));
+    tp.bits0 = __float_as_int(tc.x); tp.bits1 = __float_as_int(tc.y);
+    tp.fl0 = __float_as_int(t.x) - kTapBias; tp.fl1 = __float_as_int(t.y) - kTapBias;
+    tp.w1 = __ffma2_rn(fl, splat2(-1.0f), p);              // p - i   (exact)
+    tp.w0 = __ffma2_rn(tp.w1, splat2(-1.0f), splat2(1.0f));   // == (i+1) - p bit for bit
+    return tp;
+}
+
 // offset of the low corner inside one [D0,D1,D2] volume from the three taps' float bits; the
 // 2^23 biases are removed by one precomputed constant (32-bit wrap-around arithmetic)
 __device__ __forceinline__ int tap_base(const Tap &tz, const Tap &ty, const Tap &tx, int D1, int D2, int unbias)

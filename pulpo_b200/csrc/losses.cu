@@ -383,6 +383,71 @@ moments_std_kernel(const float *__restrict__ m2, float *__restrict__ out, float 
         out[i] = sqrtf(m2[i] * inv_nm1);
 }
 
+
+// streaming per-voxel squared error of MC samples against the fixed image: acc += (x - y)^2  (the MSE map of
+// evaluate.py:1538, mean_n((all_moved - y)^2), without the [N, ...] sample stack)
+__global__ void __launch_bounds__(256)
+sqerr_update_kernel(const float *__restrict__ x, const float *__restrict__ y, float *__restrict__ acc, int first, i64 n)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const float d = x[i] - y[i];
+        acc[i] = first ? d * d : acc[i] + d * d;
+    }
+}
+
+// Evaluate.ncc(var, mse) (evaluate.py:334-353, zero_norm=True): global zero-normalised cross-correlation of two
+// maps, sum((a - mean a) / (std a * n + eps) * (v - mean v) / (std v + eps)) with population stds and eps = 1e-15.
+// One pass: per-CTA double partials of (sum a, sum v, sum aa, sum vv, sum av) scaled per element by `sa` / `sv`
+// (a = sa * a_in: the variance map is std^2 and the MSE map sum / N, so neither needs a pass of its own); the last
+// CTA to arrive combines them in a fixed order.
+constexpr int GNCC_MAX_CTAS = 1024;
+struct GnccWs {
+    unsigned int ticket, pad;
+    double part[5][GNCC_MAX_CTAS];
+};
+__global__ void __launch_bounds__(256)
+global_ncc_kernel(const float *__restrict__ a, const float *__restrict__ v, float sa, float sv, int square_a, i64 n,
+                  GnccWs *ws, float *out)
+{
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    double s[5] = {0, 0, 0, 0, 0};
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        float af = a[i];
+        if (square_a) af = af * af;          // var = moved_std ** 2 (evaluate.py:1539), fp32 like the reference
+        const double x = (double)(af * sa), y = (double)(v[i] * sv);
+        s[0] += x; s[1] += y; s[2] += x * x; s[3] += y * y; s[4] += x * y;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const double t = block_sum(s[k], red);
+        if (threadIdx.x == 0) ws->part[k][blockIdx.x] = t;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double tot[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        double t = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += ((volatile double *)ws->part[k])[i];
+        tot[k] = block_sum(t, red);
+    }
+    if (threadIdx.x == 0) {
+        const double N = (double)n, ma = tot[0] / N, mv = tot[1] / N;
+        const double va = fmax(tot[2] / N - ma * ma, 0.0), vv = fmax(tot[3] / N - mv * mv, 0.0);
+        const double cov = tot[4] - N * ma * mv;
+        const double eps = 1e-15;
+        out[0] = (float)(cov / ((sqrt(va) * N + eps) * (sqrt(vv) + eps)));
+        out[1] = (float)ma;                 // var.mean() of evaluate.py:1541 comes for free
+        ws->ticket = 0;
+    }
+}
+
 }  // namespace pulpo
 
 using namespace pulpo;
@@ -537,6 +602,28 @@ extern "C" int pulpo_moments_std(const float *m2, float *std_out, int count, lon
     PULPO_REQUIRE(m2 && std_out, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(count >= 2 && n > 0, PULPO_ERR_INVALID_SHAPE);
     moments_std_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(m2, std_out, 1.0f / (float)(count - 1), n);
+    return launch_status();
+}
+
+extern "C" int pulpo_sqerr_update(const float *x, const float *y, float *acc, int first, long long n, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(x && y && acc, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(n > 0, PULPO_ERR_INVALID_SHAPE);
+    sqerr_update_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, acc, first, n);
+    return launch_status();
+}
+
+extern "C" size_t pulpo_global_ncc_ws_bytes(void) { return sizeof(GnccWs); }
+
+extern "C" int pulpo_global_ncc(const float *a, const float *v, float scale_a, float scale_v, int square_a, long long n,
+                                float *out2, void *ws, size_t ws_bytes, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(a && v && out2 && ws, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(n > 0, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(ws_bytes >= sizeof(GnccWs), PULPO_ERR_WORKSPACE);
+    int grid = grid_for(n, 256, 4);
+    if (grid > GNCC_MAX_CTAS) grid = GNCC_MAX_CTAS;
+    global_ncc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, v, scale_a, scale_v, square_a, n, (GnccWs *)ws, out2);
     return launch_status();
 }
 

@@ -421,6 +421,9 @@ vecint_fwd_kernel(const VMulti m, int nsteps, int save, float scale)
         }
     }
     for (int k = 0; k < nsteps; ++k) {
+#ifdef PULPO_VI_NOSYNC   // timing experiment only (wrong results): upper bound of what removing the step barriers buys
+        if (k == 0)
+#endif
         grid.sync();
         const bool last = (k == nsteps - 1);
         for (unsigned int it = warp; it < m.items; it += nwarps) {
@@ -519,6 +522,9 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
     }
     int flip = 0;   // which (P, Y) pair holds the incoming gradient of the current step
     for (int k = nsteps - 1; k >= 0; --k, flip ^= 1) {
+#ifdef PULPO_VI_NOSYNC
+        if (k == nsteps - 1)
+#endif
         grid.sync();
 #ifdef PULPO_VI_TRACE
         if (threadIdx.x == 0 && blockIdx.x < 148 && k < 32) g_vi_trace[blockIdx.x * 64 + 2 * k] = gtime();

@@ -39,7 +39,7 @@ struct WarpGeom {
     unsigned int items;      // B * D0 * nyb * nxb  (one per warp)
     int unbias;
     FastDiv dnxb, dnyb, dD0;
-    AxisConst a0, a1, a2;
+    AxisConst2 a0, a1, a2;   // packed: the kernels process the WR rows of a thread as WR/2 pairs (FADD2 / FMUL2 / FFMA2)
 };
 
 static int make_geom(WarpGeom &g, int B, int C, int D0, int D1, int D2)
@@ -54,7 +54,7 @@ static int make_geom(WarpGeom &g, int B, int C, int D0, int D1, int D2)
     g.items = (unsigned int)items;
     g.unbias = tap_unbias(D1, D2);
     g.dnxb = make_fastdiv(g.nxb); g.dnyb = make_fastdiv(g.nyb); g.dD0 = make_fastdiv(D0);
-    g.a0 = make_axis(D0); g.a1 = make_axis(D1); g.a2 = make_axis(D2);
+    g.a0 = make_axis2(D0); g.a1 = make_axis2(D1); g.a2 = make_axis2(D2);
     return PULPO_OK;
 }
 
@@ -120,6 +120,59 @@ __device__ __forceinline__ float interp8(const C8 &k, const Foot &f)
     acc = __fadd_rn(acc, __fmul_rn(k.c110, __fmul_rn(w10, f.wz1)));
     acc = __fadd_rn(acc, __fmul_rn(k.c111, __fmul_rn(w11, f.wz1)));
     return acc;
+}
+
+// ---- two voxels (rows y, y+1 of the same column and plane) per instruction
+struct Foot2 {
+    int base0, base1;
+    float2 wx0, wx1, wy0, wy1, wz0, wz1;
+    float2 uz, uy, ux;   // unclamped sample positions (backward)
+};
+
+template <int MODE>
+__device__ __forceinline__ Foot2 make_foot2(float zf, float yf, float xf, float2 dz, float2 dy, float2 dx, const WarpGeom &g,
+                                            int *fl = nullptr)
+{
+    const Tap2 tz = make_tap2<MODE>(splat2(zf), dz, g.a0);
+    const Tap2 ty = make_tap2<MODE>(make_float2(yf, yf + 1.0f), dy, g.a1);
+    const Tap2 tx = make_tap2<MODE>(splat2(xf), dx, g.a2);
+    Foot2 f;
+    f.base0 = (tz.bits0 * g.D1 + ty.bits0) * g.D2 + tx.bits0 - g.unbias;
+    f.base1 = (tz.bits1 * g.D1 + ty.bits1) * g.D2 + tx.bits1 - g.unbias;
+    f.wx0 = tx.w0; f.wx1 = tx.w1; f.wy0 = ty.w0; f.wy1 = ty.w1; f.wz0 = tz.w0; f.wz1 = tz.w1;
+    f.uz = tz.u; f.uy = ty.u; f.ux = tx.u;
+    if (fl) { fl[0] = tz.fl0; fl[1] = ty.fl0; fl[2] = tx.fl0; fl[3] = tz.fl1; fl[4] = ty.fl1; fl[5] = tx.fl1; }
+    return f;
+}
+
+__device__ __forceinline__ float2 pair(float a, float b) { return make_float2(a, b); }
+
+// interp8 for two voxels at once: the same products and sums in the same order (no FMA), so each half is
+// bit-identical to interp8
+__device__ __forceinline__ float2 interp8x2(const C8 &a, const C8 &b, const Foot2 &f)
+{
+    const float2 w00 = __fmul2_rn(f.wx0, f.wy0), w01 = __fmul2_rn(f.wx1, f.wy0);
+    const float2 w10 = __fmul2_rn(f.wx0, f.wy1), w11 = __fmul2_rn(f.wx1, f.wy1);
+    float2 acc = __fmul2_rn(pair(a.c000, b.c000), __fmul2_rn(w00, f.wz0));
+    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c001, b.c001), __fmul2_rn(w01, f.wz0)));
+    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c010, b.c010), __fmul2_rn(w10, f.wz0)));
+    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c011, b.c011), __fmul2_rn(w11, f.wz0)));
+    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c100, b.c100), __fmul2_rn(w00, f.wz1)));
+    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c101, b.c101), __fmul2_rn(w01, f.wz1)));
+    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c110, b.c110), __fmul2_rn(w10, f.wz1)));
+    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c111, b.c111), __fmul2_rn(w11, f.wz1)));
+    return acc;
+}
+
+// spatial gradient of the interpolant at the two sample points (backward, gather half): difference along one axis,
+// interpolated along the other two; FMA contraction is fine here (gradients are compared with a tolerance)
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, splat2(-1.0f), a); }
+__device__ __forceinline__ float2 lerp_diff2(float2 d00, float2 d01, float2 d10, float2 d11, float2 u0, float2 u1, float2 v0,
+                                             float2 v1)
+{
+    const float2 lo = __ffma2_rn(d01, u1, __fmul2_rn(d00, u0));
+    const float2 hi = __ffma2_rn(d11, u1, __fmul2_rn(d10, u0));
+    return __ffma2_rn(hi, v1, __fmul2_rn(lo, v0));
 }
 
 struct WItem {
@@ -222,15 +275,17 @@ warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, f
                        l2_fwd_terms(f + 2 * S, dx, ok, t, lane, sy, sz, inner);
         }
         const float zf = (float)t.z, xf = (float)t.x;
-        Foot ft[WR];
+        Foot2 ft[WR / 2];
 #pragma unroll
-        for (int j = 0; j < WR; ++j) {
-            int fl[3];
-            ft[j] = make_foot<MODE>(zf, (float)(t.y0 + j), xf, dz[j], dy[j], dx[j], g, nullptr, nullptr, nullptr,
-                                    IDX ? fl : nullptr);
-            if (IDX && ok[j]) {
+        for (int jp = 0; jp < WR / 2; ++jp) {
+            const int j = 2 * jp;
+            int fl[6];
+            ft[jp] = make_foot2<MODE>(zf, (float)(t.y0 + j), xf, pair(dz[j], dz[j + 1]), pair(dy[j], dy[j + 1]),
+                                      pair(dx[j], dx[j + 1]), g, IDX ? fl : nullptr);
+            if (IDX) {
                 int32_t *o = idx + (i64)t.b * 3 * S + v0 + j * sy;
-                o[0] = fl[0]; o[S] = fl[1]; o[2 * S] = fl[2];
+                if (ok[j]) { o[0] = fl[0]; o[S] = fl[1]; o[2 * S] = fl[2]; }
+                if (ok[j + 1]) { o[sy] = fl[3]; o[S + sy] = fl[4]; o[2 * S + sy] = fl[5]; }
             }
         }
         for (int c = 0; c < g.C; ++c) {
@@ -238,14 +293,18 @@ warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, f
             float *o = out + ((i64)t.b * g.C + c) * S + v0;
             // all 8*WR corner gathers are issued before the first interpolation (no branch in between: the
             // footprint of a lane outside the volume is clamped in-bounds, so its loads are legal and just
-            // unused) -- the kernel is bound by load latency, not by the L1 pipe
+            // unused) -- the kernel is bound by load latency and instruction issue, not by the L1 pipe
             C8 q[WR];
 #pragma unroll
-            for (int j = 0; j < WR; ++j) q[j] = gather8(im, ft[j].base, gst);
+            for (int jp = 0; jp < WR / 2; ++jp) {
+                q[2 * jp] = gather8(im, ft[jp].base0, gst);
+                q[2 * jp + 1] = gather8(im, ft[jp].base1, gst);
+            }
 #pragma unroll
-            for (int j = 0; j < WR; ++j) {
-                const float res = interp8(q[j], ft[j]);
-                if (ok[j]) o[j * sy] = res;
+            for (int jp = 0; jp < WR / 2; ++jp) {
+                const float2 res = interp8x2(q[2 * jp], q[2 * jp + 1], ft[jp]);
+                if (ok[2 * jp]) o[(2 * jp) * sy] = res.x;
+                if (ok[2 * jp + 1]) o[(2 * jp + 1) * sy] = res.y;
             }
         }
     }
@@ -335,19 +394,15 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
     load_rows<!REG>(f + 2 * S, sy, ok, dx);
     const float zf = (float)t.z, xf = (float)t.x;
     // autograd chain of 2*(loc/(S-1)-0.5) after the sampler's S/2:  (m*g*2)/(S-1)
-    const float kz = 2.0f * g.a0.rcp, ky = 2.0f * g.a1.rcp, kx = 2.0f * g.a2.rcp;
-    float rz[WR], ry[WR], rx[WR];
-    Foot ft[WR];
-    float mz[WR], my[WR], mx[WR];
+    const float kz = 2.0f * g.a0.rcp.x, ky = 2.0f * g.a1.rcp.x, kx = 2.0f * g.a2.rcp.x;
+    float2 rz2[WR / 2], ry2[WR / 2], rx2[WR / 2];
+    Foot2 ft[WR / 2];
 #pragma unroll
-    for (int j = 0; j < WR; ++j) {
-        float uz, uy, ux;
-        ft[j] = make_foot<MODE>(zf, (float)(t.y0 + j), xf, dz[j], dy[j], dx[j], g, &uz, &uy, &ux);
-        // zero gradient wherever the border clamp is active (p <= 0 or p >= S-1)
-        mz[j] = (uz > 0.0f && uz < g.a0.Sm1) ? g.a0.gmul : 0.0f;
-        my[j] = (uy > 0.0f && uy < g.a1.Sm1) ? g.a1.gmul : 0.0f;
-        mx[j] = (ux > 0.0f && ux < g.a2.Sm1) ? g.a2.gmul : 0.0f;
-        rz[j] = ry[j] = rx[j] = 0.0f;
+    for (int jp = 0; jp < WR / 2; ++jp) {
+        const int j = 2 * jp;
+        ft[jp] = make_foot2<MODE>(zf, (float)(t.y0 + j), xf, pair(dz[j], dz[j + 1]), pair(dy[j], dy[j + 1]),
+                                  pair(dx[j], dx[j + 1]), g);
+        rz2[jp] = ry2[jp] = rx2[jp] = splat2(0.0f);
     }
     for (int c = 0; c < g.C; ++c) {
         const i64 off = ((i64)t.b * g.C + c) * S;
@@ -355,41 +410,63 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
         load_rows<true>(gout + off + v0, sy, ok, go);
         C8 qq[WR];   // all gathers first (see the forward)
 #pragma unroll
-        for (int j = 0; j < WR; ++j) qq[j] = gather8(img + off, ft[j].base, gst);
+        for (int jp = 0; jp < WR / 2; ++jp) {
+            qq[2 * jp] = gather8(img + off, ft[jp].base0, gst);
+            qq[2 * jp + 1] = gather8(img + off, ft[jp].base1, gst);
+        }
 #pragma unroll
-        for (int j = 0; j < WR; ++j) {
-            const Foot &k = ft[j];
-            const C8 &q = qq[j];
+        for (int jp = 0; jp < WR / 2; ++jp) {
+            const Foot2 &k = ft[jp];
+            const C8 &a = qq[2 * jp], &b = qq[2 * jp + 1];
+            const float2 c000 = pair(a.c000, b.c000), c001 = pair(a.c001, b.c001), c010 = pair(a.c010, b.c010),
+                         c011 = pair(a.c011, b.c011), c100 = pair(a.c100, b.c100), c101 = pair(a.c101, b.c101),
+                         c110 = pair(a.c110, b.c110), c111 = pair(a.c111, b.c111);
             // d/dx: difference along x, interpolated along y and z; likewise for y and z
-            const float sx = ((q.c001 - q.c000) * k.wy0 + (q.c011 - q.c010) * k.wy1) * k.wz0 +
-                             ((q.c101 - q.c100) * k.wy0 + (q.c111 - q.c110) * k.wy1) * k.wz1;
-            const float sy_ = ((q.c010 - q.c000) * k.wx0 + (q.c011 - q.c001) * k.wx1) * k.wz0 +
-                              ((q.c110 - q.c100) * k.wx0 + (q.c111 - q.c101) * k.wx1) * k.wz1;
-            const float sz_ = ((q.c100 - q.c000) * k.wx0 + (q.c101 - q.c001) * k.wx1) * k.wy0 +
-                              ((q.c110 - q.c010) * k.wx0 + (q.c111 - q.c011) * k.wx1) * k.wy1;
-            rx[j] += sx * go[j];
-            ry[j] += sy_ * go[j];
-            rz[j] += sz_ * go[j];
-            if (SCATTER && ok[j]) {
-                float *o = gimg + off + k.base;
-                const float w00 = k.wx0 * k.wy0, w01 = k.wx1 * k.wy0, w10 = k.wx0 * k.wy1, w11 = k.wx1 * k.wy1;
-                const float g0 = go[j] * k.wz0, g1 = go[j] * k.wz1;
-                atomicAdd(o, w00 * g0);
-                atomicAdd(o + 1, w01 * g0);
-                atomicAdd(o + sy, w10 * g0);
-                atomicAdd(o + sy + 1, w11 * g0);
-                atomicAdd(o + sz, w00 * g1);
-                atomicAdd(o + sz + 1, w01 * g1);
-                atomicAdd(o + sz + sy, w10 * g1);
-                atomicAdd(o + sz + sy + 1, w11 * g1);
+            const float2 sx = lerp_diff2(sub2(c001, c000), sub2(c011, c010), sub2(c101, c100), sub2(c111, c110), k.wy0, k.wy1,
+                                         k.wz0, k.wz1);
+            const float2 sy_ = lerp_diff2(sub2(c010, c000), sub2(c011, c001), sub2(c110, c100), sub2(c111, c101), k.wx0, k.wx1,
+                                          k.wz0, k.wz1);
+            const float2 sz_ = lerp_diff2(sub2(c100, c000), sub2(c101, c001), sub2(c110, c010), sub2(c111, c011), k.wx0, k.wx1,
+                                          k.wy0, k.wy1);
+            const float2 go2 = pair(go[2 * jp], go[2 * jp + 1]);
+            rx2[jp] = __ffma2_rn(sx, go2, rx2[jp]);
+            ry2[jp] = __ffma2_rn(sy_, go2, ry2[jp]);
+            rz2[jp] = __ffma2_rn(sz_, go2, rz2[jp]);
+            if (SCATTER) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (!ok[2 * jp + h]) continue;
+                    float *o = gimg + off + (h ? k.base1 : k.base0);
+                    const float wx0 = h ? k.wx0.y : k.wx0.x, wx1 = h ? k.wx1.y : k.wx1.x, wy0 = h ? k.wy0.y : k.wy0.x,
+                                wy1 = h ? k.wy1.y : k.wy1.x, wz0 = h ? k.wz0.y : k.wz0.x, wz1 = h ? k.wz1.y : k.wz1.x;
+                    const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
+                    const float g0 = go[2 * jp + h] * wz0, g1 = go[2 * jp + h] * wz1;
+                    atomicAdd(o, w00 * g0);
+                    atomicAdd(o + 1, w01 * g0);
+                    atomicAdd(o + sy, w10 * g0);
+                    atomicAdd(o + sy + 1, w11 * g0);
+                    atomicAdd(o + sz, w00 * g1);
+                    atomicAdd(o + sz + 1, w01 * g1);
+                    atomicAdd(o + sz + sy, w10 * g1);
+                    atomicAdd(o + sz + sy + 1, w11 * g1);
+                }
             }
         }
     }
+    float rz[WR], ry[WR], rx[WR];
 #pragma unroll
-    for (int j = 0; j < WR; ++j) {
-        rz[j] = (mz[j] * rz[j]) * kz;
-        ry[j] = (my[j] * ry[j]) * ky;
-        rx[j] = (mx[j] * rx[j]) * kx;
+    for (int jp = 0; jp < WR / 2; ++jp) {
+        const Foot2 &k = ft[jp];
+        // zero gradient wherever the border clamp is active (p <= 0 or p >= S-1)
+        const float2 mz = pair((k.uz.x > 0.0f && k.uz.x < g.a0.Sm1) ? g.a0.gmul : 0.0f, (k.uz.y > 0.0f && k.uz.y < g.a0.Sm1) ? g.a0.gmul : 0.0f);
+        const float2 my = pair((k.uy.x > 0.0f && k.uy.x < g.a1.Sm1) ? g.a1.gmul : 0.0f, (k.uy.y > 0.0f && k.uy.y < g.a1.Sm1) ? g.a1.gmul : 0.0f);
+        const float2 mx = pair((k.ux.x > 0.0f && k.ux.x < g.a2.Sm1) ? g.a2.gmul : 0.0f, (k.ux.y > 0.0f && k.ux.y < g.a2.Sm1) ? g.a2.gmul : 0.0f);
+        const float2 z2 = __fmul2_rn(__fmul2_rn(mz, rz2[jp]), splat2(kz));
+        const float2 y2 = __fmul2_rn(__fmul2_rn(my, ry2[jp]), splat2(ky));
+        const float2 x2 = __fmul2_rn(__fmul2_rn(mx, rx2[jp]), splat2(kx));
+        rz[2 * jp] = z2.x; rz[2 * jp + 1] = z2.y;
+        ry[2 * jp] = y2.x; ry[2 * jp + 1] = y2.y;
+        rx[2 * jp] = x2.x; rx[2 * jp + 1] = x2.y;
     }
     if (REG) {
         const float k = reg_scale_k;

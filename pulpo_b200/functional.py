@@ -528,3 +528,25 @@ def moments_std(m2, count):
     out = torch.empty_like(m2)
     check(_lib.lib().pulpo_moments_std(_ptr(m2), _ptr(out), int(count), m2.numel(), _stream()), "moments_std")
     return out
+
+
+def sqerr_update(x, y, acc, first):
+    """acc (+)= (x - y)**2 per voxel: the streamed numerator of the MSE map (evaluate.py:1538)."""
+    x, y = _prep(x, "x"), _prep(y, "y")
+    if x.numel() != y.numel() or x.numel() != acc.numel():
+        raise RuntimeError("sqerr_update: x %s, y %s, acc %s" % (tuple(x.shape), tuple(y.shape), tuple(acc.shape)))
+    check(_lib.lib().pulpo_sqerr_update(_ptr(x), _ptr(y), _ptr(acc), int(bool(first)), x.numel(), _stream()), "sqerr_update")
+
+
+def global_ncc(a, v, scale_a=1.0, scale_v=1.0, square_a=False):
+    """Evaluate.ncc(a', v') of evaluate.py:334-353 (zero_norm=True) with a' = scale_a * (a**2 if square_a else a),
+    v' = scale_v * v.  Returns a 2-element CUDA tensor: (ncc, mean(a'))."""
+    a, v = _prep(a, "a"), _prep(v, "v")
+    if a.numel() != v.numel():
+        raise RuntimeError("global_ncc: %d vs %d elements" % (a.numel(), v.numel()))
+    lib = _lib.lib()
+    ws = torch.zeros(lib.pulpo_global_ncc_ws_bytes(), dtype=torch.uint8, device=a.device)
+    out = torch.empty(2, dtype=torch.float32, device=a.device)
+    check(lib.pulpo_global_ncc(_ptr(a), _ptr(v), float(scale_a), float(scale_v), int(bool(square_a)), a.numel(), _ptr(out),
+                               _ptr(ws), ws.numel(), _stream()), "global_ncc")
+    return out

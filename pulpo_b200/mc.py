@@ -8,9 +8,9 @@ per-voxel MSE ``mean((all_moved - y)**2, axis=0)``.
 
 Here no stack exists.  Every (pair, sample) is an independent hot-path instance, so the N samples
 are dealt to the ranks; each rank streams its samples through per-voxel Welford states
-``(count, mean, M2)`` (``pulpo_moments_update``), the partial states are all-gathered
-(NCCL over NVLink: 8 B/voxel/channel per rank) and Chan-merged in rank order
-(``pulpo_moments_merge``), and ``std = sqrt(M2 / (N - 1))`` (``pulpo_moments_std``), channel mean
+``(count, mean, M2)`` (``pulpo_moments_update``), the partial states are reduced to rank 0 over a binomial tree
+(NCCL send/recv over NVLink: every rank sends its 8 B/voxel/channel once; a Chan merge,
+``pulpo_moments_merge``, at every hop), and ``std = sqrt(M2 / (N - 1))`` (``pulpo_moments_std``), channel mean
 and square follow.  Sample *i* always draws its noise from ``seed0 + i`` (see ``sample_generator``),
 so any sharding -- 1, 2, 4 or 8 ranks -- sees the same N samples and the merged maps agree up to
 fp32 merge order.
@@ -46,6 +46,14 @@ class _KernelOps:
     @staticmethod
     def std(m2, count):
         return PF.moments_std(m2, count)
+
+    @staticmethod
+    def sqerr(x, y, acc, first):
+        PF.sqerr_update(x, y, acc, first)
+
+    @staticmethod
+    def global_ncc(a, v, scale_a, scale_v, square_a):
+        return PF.global_ncc(a, v, scale_a, scale_v, square_a)
 
 
 def shard_samples(num_samples: int, rank: int, world: int) -> List[int]:
@@ -103,57 +111,162 @@ class MCMoments:
         return self.std_channel_mean() ** 2
 
 
-def merge_across_ranks(local: Dict[str, MCMoments], group=None, dst: Optional[int] = 0) -> Dict[str, MCMoments]:
-    """All-gather every rank's ``(count, mean, M2)`` and Chan-merge them in rank order (deterministic
-    for a given world size).  With ``dst`` set only that rank merges (the others return their
-    local states untouched); ``dst=None`` merges everywhere."""
+class MCSqErr:
+    """Streaming per-voxel sum of squared errors of the MC samples against the fixed image ``y``:
+    ``mse() == torch.mean((all_moved - y)**2, axis=0)`` of evaluate.py:1538 without the sample stack."""
+
+    def __init__(self, shape, device, ops=None):
+        self.ops = ops if ops is not None else _KernelOps
+        self.count = 0
+        self.acc = torch.zeros(tuple(shape), dtype=torch.float32, device=device)
+
+    def update(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        if tuple(x.shape) != tuple(self.acc.shape) or x.numel() != y.numel():
+            raise RuntimeError("MCSqErr.update: sample %s, target %s, state %s"
+                               % (tuple(x.shape), tuple(y.shape), tuple(self.acc.shape)))
+        self.ops.sqerr(x.detach().contiguous(), y.detach().contiguous(), self.acc, self.count == 0)
+        self.count += 1
+
+    def mse(self) -> torch.Tensor:
+        if self.count < 1:
+            raise RuntimeError("MCSqErr.mse needs at least 1 sample")
+        return self.acc / float(self.count)
+
+
+def uncertainty_metrics(moved: MCMoments, sqerr: MCSqErr) -> Dict[str, object]:
+    """The per-pair numbers of ``Evaluate.uncertainty`` (evaluate.py:1534-1545): variance map
+    ``moved_std ** 2``, MSE map, ``ncc(var, mse)`` (evaluate.py:334-353) and ``var.mean()``.
+    One extra pass over the two maps: squaring the std and scaling the error sums ride in the NCC kernel."""
+    if moved.count != sqerr.count:
+        raise RuntimeError("uncertainty_metrics: %d samples in the moments, %d in the squared errors"
+                           % (moved.count, sqerr.count))
+    std = moved.std_channel_mean()                       # [*S]
+    r = moved.ops.global_ncc(std, sqerr.acc.reshape(std.shape), 1.0, 1.0 / float(sqerr.count), True)
+    return {"var": std ** 2, "mse": sqerr.mse().reshape(std.shape), "ncc": r[0], "var_mean": r[1]}
+
+
+def _check_same_maps(local_meta, group):
+    """Every rank must hold the same maps with the same shapes; a rank that drew no sample (empty explicit
+    ``sample_ids``) may hold none.  Decided on ALL ranks before any tensor collective, so a mismatch raises
+    everywhere instead of leaving the other ranks blocked in a collective."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    metas = [None] * world
+    dist.all_gather_object(metas, local_meta, group=group)
+    shapes = {}
+    for r, m in enumerate(metas):
+        for name, (shape, _count) in m.items():
+            if shapes.setdefault(name, tuple(shape)) != tuple(shape):
+                raise RuntimeError("merge_across_ranks: map %r has shape %s on rank %d but %s elsewhere"
+                                   % (name, tuple(shape), r, shapes[name]))
+    return shapes, metas
+
+
+def merge_across_ranks(local: Dict[str, "MCMoments | MCSqErr"], group=None, dst: Optional[int] = 0, device=None,
+                       ops=None) -> Dict[str, "MCMoments | MCSqErr"]:
+    """Reduce every rank's partial state to rank ``dst`` (``dst=None``: rank 0, then broadcast to all).
+
+    ``MCMoments``: binomial-tree reduction of ``(count, mean, M2)`` with a Chan merge at every hop -- each rank
+    sends its state ONCE (8 B/voxel/channel over NVLink, log2(world) hops deep) and needs one receive buffer,
+    instead of all-gathering world x (mean, M2) to every rank; the merge order is fixed by the world size, so the
+    result is deterministic.  ``MCSqErr``: one ``reduce(SUM)`` of the error sums.  Ranks other than ``dst``
+    return their local (partial) states."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    names = sorted(local.keys())
-    dev = local[names[0]].mean.device
-    counts = torch.tensor([local[n].count for n in names], dtype=torch.int64, device=dev)
-    all_counts = [torch.empty_like(counts) for _ in range(world)]
-    dist.all_gather(all_counts, counts, group=group)
+    root = 0 if dst is None else int(dst)
+    meta = {n: (tuple(st.acc.shape if isinstance(st, MCSqErr) else st.mean.shape), st.count) for n, st in local.items()}
+    kinds = {n: isinstance(st, MCSqErr) for n, st in local.items()}
+    shapes, metas = _check_same_maps({n: (meta[n][0], meta[n][1], ) for n in meta}, group)
+    all_kinds = [None] * world
+    dist.all_gather_object(all_kinds, kinds, group=group)
+    for k in all_kinds:
+        for n, v in k.items():
+            kinds.setdefault(n, v)
+    if device is None:
+        if not local:
+            raise RuntimeError("merge_across_ranks: a rank without local maps must pass `device`")
+        any_st = next(iter(local.values()))
+        device = (any_st.acc if isinstance(any_st, MCSqErr) else any_st.mean).device
+    if ops is None and local:
+        ops = next(iter(local.values())).ops
+    rel = (rank - root) % world
     merged = {}
-    for j, n in enumerate(names):
-        st = local[n]
-        packed = torch.stack([st.mean, st.m2])                       # one collective per map
-        parts = [torch.empty_like(packed) for _ in range(world)]
-        dist.all_gather(parts, packed, group=group)
-        if dst is not None and rank != dst:
-            merged[n] = st
+    for n in sorted(shapes):
+        st = local.get(n)
+        if st is None:                                    # this rank drew no sample: zero-count state
+            st = MCSqErr(shapes[n], device, ops=ops) if kinds[n] else MCMoments(shapes[n], device, ops=ops)
+        if kinds[n]:
+            total = torch.tensor([st.count], dtype=torch.int64, device=device)
+            out = MCSqErr(shapes[n], device, ops=st.ops)
+            out.acc.copy_(st.acc)
+            if dst is None:
+                dist.all_reduce(out.acc, group=group)
+                dist.all_reduce(total, group=group)
+            else:
+                dist.reduce(out.acc, dst=dist.get_global_rank(group, root) if group is not None else root, group=group)
+                dist.all_reduce(total, group=group)
+            out.count = int(total.item())
+            merged[n] = out if (dst is None or rank == root) else st
             continue
-        out = MCMoments(st.mean.shape, dev, ops=st.ops)
-        for r in range(world):                                        # fixed order: rank 0, 1, 2, ...
-            out.merge_state(parts[r][0], parts[r][1], int(all_counts[r][j].item()))
-        merged[n] = out
+        acc = MCMoments(shapes[n], device, ops=st.ops)
+        acc.merge_state(st.mean, st.m2, st.count)
+        buf = torch.empty((2,) + tuple(shapes[n]), dtype=torch.float32, device=device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=device)
+        step = 1
+        while step < world:
+            if rel % (2 * step) == step:                  # sender: hand the partial state down the tree, then done
+                peer = (rel - step + root) % world
+                peer = dist.get_global_rank(group, peer) if group is not None else peer
+                dist.send(torch.tensor([acc.count], dtype=torch.int64, device=device), dst=peer, group=group)
+                dist.send(torch.stack([acc.mean, acc.m2]), dst=peer, group=group)
+                break
+            if rel % (2 * step) == 0 and rel + step < world:
+                peer = (rel + step + root) % world
+                peer = dist.get_global_rank(group, peer) if group is not None else peer
+                dist.recv(cnt, src=peer, group=group)
+                dist.recv(buf, src=peer, group=group)
+                acc.merge_state(buf[0], buf[1], int(cnt.item()))
+            step *= 2
+        if dst is None:
+            packed = torch.stack([acc.mean, acc.m2])
+            total = torch.tensor([acc.count], dtype=torch.int64, device=device)
+            src = dist.get_global_rank(group, root) if group is not None else root
+            dist.broadcast(packed, src=src, group=group)
+            dist.broadcast(total, src=src, group=group)
+            acc.mean.copy_(packed[0]); acc.m2.copy_(packed[1]); acc.count = int(total.item())
+            merged[n] = acc
+        else:
+            merged[n] = acc if rank == root else st
     return merged
 
 
 def mc_uncertainty(sample_fn: Callable[[int, torch.Generator], Dict[str, torch.Tensor]], num_samples: int,
                    seed0: int = 0, device=None, group=None, dst: Optional[int] = 0, ops=None,
-                   sample_ids: Optional[Iterable[int]] = None) -> Dict[str, MCMoments]:
-    """Run this rank's share of ``num_samples`` MC samples and merge the per-voxel moments.
+                   sample_ids: Optional[Iterable[int]] = None,
+                   targets: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, "MCMoments | MCSqErr"]:
+    """Run this rank's share of ``num_samples`` MC samples and merge the per-voxel statistics.
 
     ``sample_fn(sample_id, generator)`` runs one deformation sample (``gauss_sampler(mu, sigma,
     generator=generator)`` -> decode -> warp) under ``torch.no_grad()`` and returns the maps to
     track, e.g. ``{"moved0": outputs[0][0], "final0": final_dfs[0][0]}`` (each ``[C, *S]``).
-    Returns ``{name: MCMoments}`` holding all ``num_samples`` samples on rank ``dst``.
+    ``targets`` maps a map name to the fixed image it is compared with: for those maps the squared errors are
+    streamed too and returned under ``name + ":sqerr"`` (the MSE map of evaluate.py:1538).
+    Returns ``{name: MCMoments | MCSqErr}`` holding all ``num_samples`` samples on rank ``dst``.
     """
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         world, rank = dist.get_world_size(group), dist.get_rank(group)
     else:
         world, rank = 1, 0
-    if world > 1 and num_samples < world:
+    if world > 1 and num_samples < world and sample_ids is None:
         raise ValueError("mc_uncertainty: %d samples cannot be dealt to %d ranks (every rank needs at least one)"
                          % (num_samples, world))
     ids = list(sample_ids) if sample_ids is not None else shard_samples(num_samples, rank, world)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    states: Dict[str, MCMoments] = {}
+    states: Dict[str, object] = {}
     with torch.no_grad():
         for i in ids:
             maps = sample_fn(i, sample_generator(seed0, i, device))
@@ -161,4 +274,9 @@ def mc_uncertainty(sample_fn: Callable[[int, torch.Generator], Dict[str, torch.T
                 if name not in states:
                     states[name] = MCMoments(t.shape, t.device, ops=ops)
                 states[name].update(t)
-    return merge_across_ranks(states, group=group, dst=dst) if world > 1 else states
+                if targets is not None and name in targets:
+                    key = name + ":sqerr"
+                    if key not in states:
+                        states[key] = MCSqErr(t.shape, t.device, ops=ops)
+                    states[key].update(t, targets[name])
+    return merge_across_ranks(states, group=group, dst=dst, device=device, ops=ops) if world > 1 else states

@@ -34,7 +34,7 @@ def _sample_fn_factory(dev):
         v = {l: gauss_sampler(mu[l], sg[l], generator=gen) for l in mu}
         _, final = combine_dfs(v, SIZE)
         return {"final0": final[0][0], "moved0": st(final[0], xc)[0]}
-    return sample_fn
+    return sample_fn, y.to(dev)[0]
 
 
 def _worker(rank, world, port, out_dir):
@@ -44,10 +44,12 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from pulpo_b200 import mc
-        res = mc.mc_uncertainty(_sample_fn_factory(dev), N, seed0=11, device=dev, dst=0)
+        fn, y = _sample_fn_factory(dev)
+        res = mc.mc_uncertainty(fn, N, seed0=11, device=dev, dst=0, targets={"moved0": y})
         if rank == 0:
-            torch.save({"count": res["final0"].count, "std": res["final0"].std().cpu(), "var": res["moved0"].variance_map().cpu()},
-                       os.path.join(out_dir, "r0.pt"))
+            m = mc.uncertainty_metrics(res["moved0"], res["moved0:sqerr"])
+            torch.save({"count": res["final0"].count, "std": res["final0"].std().cpu(), "var": res["moved0"].variance_map().cpu(),
+                        "mse": m["mse"].cpu(), "ncc": float(m["ncc"])}, os.path.join(out_dir, "r0.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -60,7 +62,11 @@ def test_mc_uncertainty_two_gpus_nccl(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     got = torch.load(os.path.join(str(tmp_path), "r0.pt"))
     dev = torch.device("cuda", 0)
-    one = mc.mc_uncertainty(_sample_fn_factory(dev), N, seed0=11, device=dev)
+    fn, y = _sample_fn_factory(dev)
+    one = mc.mc_uncertainty(fn, N, seed0=11, device=dev, targets={"moved0": y})
+    m = mc.uncertainty_metrics(one["moved0"], one["moved0:sqerr"])
     assert got["count"] == N
+    torch.testing.assert_close(got["mse"], m["mse"].cpu(), rtol=1e-4, atol=1e-7)
+    assert abs(got["ncc"] - float(m["ncc"])) <= 1e-3 * abs(float(m["ncc"])) + 1e-6
     torch.testing.assert_close(got["std"], one["final0"].std().cpu(), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(got["var"], one["moved0"].variance_map().cpu(), rtol=1e-4, atol=1e-7)

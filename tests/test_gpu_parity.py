@@ -718,6 +718,26 @@ def test_moments_kernels_match_torch_std(PF):
     assert_close(a.std_channel_mean().cpu().numpy(), ref.std(0).mean(0).cpu().numpy(), 1e-5, "mc std channel mean")
 
 
+def test_uncertainty_metrics_kernels_vs_reference_golden(PF):
+    """f-3: streaming squared-error map + global NCC(var, mse) kernels against the numbers the reference's own
+    formulas give on explicit sample stacks (evaluate.py:1534-1545, Evaluate.ncc :334-353; golden uncertainty.npz)."""
+    from pulpo_b200 import mc
+    g = load_golden("uncertainty")
+    moved, y = dev(g["all_moved"]), dev(g["y"])
+    mom, sq = mc.MCMoments(moved.shape[1:], "cuda"), mc.MCSqErr(moved.shape[1:], "cuda")
+    for i in range(moved.shape[0]):
+        mom.update(moved[i])
+        sq.update(moved[i], y[0])
+    r = mc.uncertainty_metrics(mom, sq)
+    assert_close(r["var"].cpu().numpy(), g["var"], 1e-6, "var map")
+    assert_close(r["mse"].cpu().numpy(), g["mse"], 1e-6, "mse map")
+    assert_loss_close(float(r["ncc"]), float(g["ncc"]), "ncc(var, mse)", rtol=1e-4)
+    assert_loss_close(float(r["var_mean"]), float(g["var_mean"]), "var.mean()", rtol=1e-5)
+    # the kernel alone on the golden maps: same number as the reference method to fp32 round-off
+    out = PF.global_ncc(dev(g["var"]), dev(g["mse"]))
+    assert_loss_close(float(out[0]), float(g["ncc"]), "global_ncc kernel", rtol=2e-5)
+
+
 def test_mc_uncertainty_hot_path_matches_stacked_reference_semantics(PF):
     """Config 3 at small size: N MC samples of (gauss_sampler -> combine -> integrate -> warp), streamed
     through the moments kernels, against torch.std over explicit stacks (evaluate.py:243-251) of the

@@ -31,11 +31,16 @@ def _sample(i, gen):
     return {"final0": base + 0.5 * noise, "moved0": (0.1 * noise[:1]).abs()}
 
 
+def _target():
+    return torch.linspace(0.0, 0.3, steps=int(torch.tensor(SHAPE[1:]).prod())).reshape((1,) + SHAPE[1:])
+
+
 def _worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        res = mc.mc_uncertainty(_sample, N_SAMPLES, seed0=123, device=torch.device("cpu"), ops=TorchCpuOps, dst=0)
+        res = mc.mc_uncertainty(_sample, N_SAMPLES, seed0=123, device=torch.device("cpu"), ops=TorchCpuOps, dst=0,
+                                targets={"moved0": _target()})
         # config 5: per-rank batch-mean losses averaged over equal shards == global batch mean
         g = torch.Generator().manual_seed(7)
         per_pair = torch.rand(4, generator=g)              # 4 pairs, 2 per rank
@@ -45,7 +50,9 @@ def _worker(rank, world, port, out_dir):
         t /= world
         if rank == 0:
             torch.save({"count": res["final0"].count, "std": res["final0"].std(), "mean": res["final0"].mean,
-                        "var_map": res["moved0"].variance_map(), "loss": t, "loss_ref": per_pair.mean()},
+                        "var_map": res["moved0"].variance_map(), "loss": t, "loss_ref": per_pair.mean(),
+                        "mse": res["moved0:sqerr"].mse(), "sq_count": res["moved0:sqerr"].count,
+                        "metrics": mc.uncertainty_metrics(res["moved0"], res["moved0:sqerr"])},
                        os.path.join(out_dir, "r0.pt"))
         else:
             assert res["final0"].count == len(mc.shard_samples(N_SAMPLES, rank, world))   # untouched local state
@@ -89,3 +96,63 @@ def test_mc_sharded_over_two_gloo_ranks_matches_unsharded(tmp_path):
     torch.testing.assert_close(got["mean"], stack.mean(dim=0), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(got["var_map"], moved.std(dim=0).mean(dim=0) ** 2, rtol=1e-4, atol=1e-8)
     torch.testing.assert_close(got["loss"], got["loss_ref"], rtol=1e-6, atol=0)
+    # f-3: MSE map and global NCC(var, mse) from the merged streaming states == the stack-based reference formulas
+    from oracle.moments_ref import ref_global_ncc
+    mse_ref = ((moved - _target()) ** 2).mean(dim=0)
+    var_ref = moved.std(dim=0).mean(dim=0) ** 2
+    assert got["sq_count"] == N_SAMPLES
+    torch.testing.assert_close(got["mse"], mse_ref, rtol=1e-5, atol=1e-8)
+    ncc_ref = ref_global_ncc(var_ref.numpy(), mse_ref.squeeze(0).numpy())
+    assert abs(float(got["metrics"]["ncc"]) - ncc_ref) <= 1e-4 * abs(ncc_ref) + 1e-6
+
+
+def _worker_tree(rank, world, port, out_dir):
+    """3 ranks (not a power of two) with an explicit sample deal that leaves rank 2 without samples: the empty rank
+    still takes part in every collective with zero-count states, and dst=None leaves the merged state on all ranks."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ids = {0: [0, 1, 2, 3, 4, 5], 1: [6, 7, 8, 9, 10], 2: []}[rank]
+        res = mc.mc_uncertainty(_sample, N_SAMPLES, seed0=123, device=torch.device("cpu"), ops=TorchCpuOps, dst=None,
+                                sample_ids=ids, targets={"moved0": _target()})
+        torch.save({"count": res["final0"].count, "std": res["final0"].std(), "mse": res["moved0:sqerr"].mse()},
+                   os.path.join(out_dir, "r%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_mc_tree_merge_three_ranks_one_empty(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker_tree, args=(3, port, str(tmp_path)), nprocs=3, join=True)
+    stack = torch.stack([_sample(i, mc.sample_generator(123, i, "cpu"))["final0"] for i in range(N_SAMPLES)])
+    moved = torch.stack([_sample(i, mc.sample_generator(123, i, "cpu"))["moved0"] for i in range(N_SAMPLES)])
+    for r in range(3):
+        got = torch.load(os.path.join(str(tmp_path), "r%d.pt" % r))
+        assert got["count"] == N_SAMPLES
+        torch.testing.assert_close(got["std"], stack.std(dim=0), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(got["mse"], ((moved - _target()) ** 2).mean(dim=0), rtol=1e-5, atol=1e-8)
+
+
+def _worker_mismatch(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shape = SHAPE if rank == 0 else (3, 6, 5, 5)
+        st = mc.MCMoments(shape, "cpu", ops=TorchCpuOps)
+        st.update(torch.zeros(shape))
+        try:
+            mc.merge_across_ranks({"m": st}, dst=0)
+            ok = False
+        except RuntimeError:
+            ok = True                      # raised on EVERY rank, before any tensor collective: nobody hangs
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write(str(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_merge_shape_mismatch_raises_on_all_ranks(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker_mismatch, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(open(os.path.join(str(tmp_path), "ok%d" % r)).read() == "True" for r in range(2))

@@ -124,3 +124,23 @@ def test_numpy_oracle_jacobian_det_matches_reference_fixture():
         assert np.array_equal(J.jacobian_det(g["df_" + t], normalize=False), g["det_nonorm_" + t])
         assert abs(J.jdet_std(g["df_" + t], 0.7) - float(g["jdetstd_" + t])) <= 1e-6 * abs(float(g["jdetstd_" + t]))
     assert (g["det_nonorm_b"] <= 0).any(), "fixture should contain folded voxels"
+
+
+def test_uncertainty_metrics_oracle_vs_reference_golden():
+    """f-3: streaming moments + squared errors + global NCC (oracle ops) against the stack-based numbers and the
+    reference's own Evaluate.ncc (tests/golden/uncertainty.npz, generated by oracle/gen_golden.py)."""
+    from oracle.moments_ref import TorchCpuOps, ref_global_ncc
+    from pulpo_b200 import mc
+    g = load_golden("uncertainty")
+    moved, y = torch.from_numpy(g["all_moved"]), torch.from_numpy(g["y"])
+    assert_loss_close(ref_global_ncc(g["var"], g["mse"]), float(g["ncc"]), "ncc restatement", rtol=1e-6)
+    mom = mc.MCMoments(moved.shape[1:], "cpu", ops=TorchCpuOps)
+    sq = mc.MCSqErr(moved.shape[1:], "cpu", ops=TorchCpuOps)
+    for i in range(moved.shape[0]):
+        mom.update(moved[i])
+        sq.update(moved[i], y[0])
+    r = mc.uncertainty_metrics(mom, sq)
+    assert_close(r["var"].numpy(), g["var"], 1e-6, "var map")
+    assert_close(r["mse"].numpy(), g["mse"], 1e-6, "mse map")
+    assert_loss_close(float(r["ncc"]), float(g["ncc"]), "ncc(var, mse)", rtol=1e-4)   # streaming vs stacked var
+    assert_loss_close(float(r["var_mean"]), float(g["var_mean"]), "var.mean()", rtol=1e-5)
