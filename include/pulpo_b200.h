@@ -62,6 +62,18 @@ int pulpo_warp3d_fwd(const float *img, const float *df, float *out, int32_t *idx
 int pulpo_warp3d_bwd(const float *gout, const float *img, const float *df, float *gimg, float *gdf,
                      int B, int C, int D0, int D1, int D2, int coord_mode, pulpo_stream_t stream);
 
+/* Same two entry points for an image whose spatial size [I0,I1,I2] differs from the field's [D0,D1,D2]:
+ * grid_sample normalises with the FIELD size (the transformer's `size`, src/network_blocks.py:106-107) and
+ * unnormalises, clamps and gathers with the IMAGE size; the output has the field's size.  The reference does
+ * this when a level-sized field resamples a full-resolution image or segmentation in level_res mode
+ * (evaluate.py:198, 240, 246).  img / gimg: [B,C,I0,I1,I2]; df / gdf / out / gout: field-sized. */
+int pulpo_warp3d_fwd_img(const float *img, const float *df, float *out, int32_t *idx_dbg, int B, int C,
+                         int D0, int D1, int D2, int I0, int I1, int I2, int coord_mode,
+                         pulpo_stream_t stream);
+int pulpo_warp3d_bwd_img(const float *gout, const float *img, const float *df, float *gimg,
+                         float *gdf, int B, int C, int D0, int D1, int D2, int I0, int I1, int I2,
+                         int coord_mode, pulpo_stream_t stream);
+
 /* a2 fused with f-1 (L2_reg, src/losses.py:208-222): the warp and the regulariser read the same
  * full-resolution field in the same step (src/models.py:160-162).  reg_out (device scalar) =
  * L2_reg(df, lamb); ws: pulpo_reduce_ws_bytes() bytes, zeroed once by the caller. */
@@ -255,6 +267,14 @@ int pulpo_sqerr_update(const float *x, const float *y, float *acc, int first, lo
 size_t pulpo_global_ncc_ws_bytes(void);
 int pulpo_global_ncc(const float *a, const float *v, float scale_a, float scale_v, int square_a,
                      long long n, float *out2, void *ws, size_t ws_bytes, pulpo_stream_t stream);
+
+/* ---- PULPo.training_step's total (src/models.py:164): kl*beta + recon + reg over all levels ----
+ * losses: [rows, cols] per-term x per-level scalars the loss kernels wrote (weights already folded in);
+ * total (nullable) = their sum in a fixed order; running (nullable, [rows]) = the per-term sums, added to
+ * what is there when accumulate != 0 (so a multi-GPU job can all-reduce the logged scalars once per K steps
+ * instead of once per step) or overwritten. */
+int pulpo_loss_total(const float *losses, int rows, int cols, float *total, float *running,
+                     int accumulate, pulpo_stream_t stream);
 
 #ifdef __cplusplus
 }

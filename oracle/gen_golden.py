@@ -254,12 +254,46 @@ def gen_uncertainty():
           ncc=np.float64(ncc), var_mean=np.float64(var.mean()))
 
 
+def gen_warp_img_size():
+    """a2 with an image larger than the field: a level-sized SpatialTransformer resampling a full-resolution image /
+    segmentation, as Evaluate.predict does in level_res mode (evaluate.py:198, 240, 246)."""
+    torch.set_num_threads(1)
+    nb, ls, cp, md = ref_import.load()
+    fshape, ishape, B, C = (5, 6, 7), (10, 12, 14), 2, 3
+    df = syn.make_field(fshape, 21, batch=B, max_abs=2.5)
+    img = syn.make_field(ishape, 22, batch=B, max_abs=1.0, channels=C)
+    d, im = df.clone().requires_grad_(True), img.clone().requires_grad_(True)
+    out = nb.SpatialTransformer(fshape)(d, im)
+    gout = _randn(out.shape, 23)
+    out.backward(gout)
+    _save("warp_img_size", df=df, img=img, out=out, gout=gout, gdf=d.grad, gimg=im.grad)
+
+
+def gen_resize16():
+    """a4 at x16: the output resize of the coarsest latent level in df_resolution="full_res" at config 2
+    (10x12x14 -> 160x192x224, src/components/pulpo.py:146,297); small volume, same factor."""
+    torch.set_num_threads(1)
+    nb, ls, cp, md = ref_import.load()
+    xin = syn.make_field((2, 3, 2), 22, batch=1, max_abs=2.0)
+    xi = xin.clone().requires_grad_(True)
+    out = nb.ResizeTransform(1 / 16, 3)(xi)
+    gout = _randn(out.shape, 8)
+    out.backward(gout)
+    _save("resize_up16", x=xin, out=out, gout=gout, gx=xi.grad)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "jacdet":
         gen_jacdet()
     elif len(sys.argv) > 1 and sys.argv[1] == "uncertainty":
         gen_uncertainty()
+    elif len(sys.argv) > 1 and sys.argv[1] == "warp_img_size":
+        gen_warp_img_size()
+    elif len(sys.argv) > 1 and sys.argv[1] == "resize16":
+        gen_resize16()
     else:
         main()
         gen_jacdet()
         gen_uncertainty()
+        gen_warp_img_size()
+        gen_resize16()

@@ -1,8 +1,8 @@
-"""Import the REAL reference (read-only, /root/reference) -- build container only.
+"""Import the REAL reference: /root/reference (read-only, build container) or, on the GPU box, the
+unmodified copy of its `src` package staged under oracle/_ref by oracle/stage_ref.py.
 
-TEST INFRASTRUCTURE ONLY.  /root/reference does not exist on the GPU box, so nothing that
-runs there may call this; it is used by oracle/gen_golden.py (fixture generation) and by
-CPU tests that skip when the reference tree is absent.
+TEST INFRASTRUCTURE ONLY.  Used by oracle/gen_golden.py (fixture generation), by CPU tests that skip when
+no reference tree is present, and by the whole-model drop-in test on the GPU (tests/test_gpu_dropin.py).
 
 ``src.models`` needs ``pytorch_lightning`` and ``torchvision`` symbols that are not
 installed / not needed; a minimal stub is injected into ``sys.modules``.
@@ -13,7 +13,10 @@ import os
 import sys
 import types
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/stage_ref.py (GPU box)
 REF_ROOT = os.environ.get("PULPO_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "src")) and os.path.isdir(os.path.join(_STAGED, "src")):
+    REF_ROOT = _STAGED
 
 
 def available() -> bool:

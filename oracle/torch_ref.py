@@ -28,7 +28,7 @@ def identity_grid(size, device=None):
 def warp(df, img, grid=None):
     """src/network_blocks.py:101-121 -- normalise with (S-1), sample with align_corners=False,
     border padding, channel order reversed to (x, y, z) for grid_sample."""
-    size = img.shape[2:]
+    size = df.shape[2:]          # the transformer's `size` is the field's grid; the image may be larger (grid_sample)
     if grid is None:
         grid = identity_grid(size, df.device)
     loc = grid + df
@@ -165,18 +165,18 @@ def loss_weights(latent_levels, lk_offset, ndims=3, full_res=False):
 
 # --------------------------------------------------------------------------- whole hot path
 def hot_path_losses(x, y, individual_dfs, mus, sigmas, total_levels, beta=0.1, gamma=0.05,
-                    lamb=0.025, with_reg=True):
+                    lamb=0.025, with_reg=True, full_res=False):
     """One pass of the hot path (the starred rows): per level
     combine -> integrate -> output resize -> warp, then hierarchical NCC + KL (+ L2) losses.
     ``individual_dfs[l]`` stands for the VelocityField conv output (pulpo.py:303), ``mus`` /
     ``sigmas`` for the encoder outputs.  Returns (total, parts, outputs)."""
     L = len(individual_dfs)
     lk = total_levels - L
-    win, kl_w, rec_w, reg_w = loss_weights(L, lk)
-    lx = moving_pyramid(x, L, lk)
+    win, kl_w, rec_w, reg_w = loss_weights(L, lk, 3, full_res)
+    lx = moving_pyramid(x, L, lk, full_res)
     combined, final, moved = {}, {}, {}
     for l in reversed(range(L)):
-        out_factor = x.shape[2] // individual_dfs[l].shape[2] if l == 0 else 1
+        out_factor = x.shape[2] // individual_dfs[l].shape[2] if (l == 0 or full_res) else 1   # pulpo.py:146
         combined[l], final[l], moved[l] = decoder_level(
             individual_dfs[l], lx[l], combined.get(l + 1), out_factor)
     kl = sum(kl_w[l] * kl_diag(mus[l], sigmas[l], torch.zeros_like(mus[l]), torch.ones_like(sigmas[l]))

@@ -36,6 +36,8 @@ SIGNATURES = {
     "pulpo_strerror": (ctypes.c_char_p, [_i]),
     "pulpo_warp3d_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_warp3d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_warp3d_fwd_img": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_warp3d_bwd_img": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_warp3d_l2reg_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_warp3d_l2reg_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_vecint_ws_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
@@ -72,6 +74,7 @@ SIGNATURES = {
     "pulpo_moments_update": (_i, [_vp, _vp, _vp, _i, _ll, _vp]),
     "pulpo_moments_merge": (_i, [_vp, _vp, _i, _vp, _vp, _i, _ll, _vp]),
     "pulpo_moments_std": (_i, [_vp, _vp, _i, _ll, _vp]),
+    "pulpo_loss_total": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp]),
     "pulpo_sqerr_update": (_i, [_vp, _vp, _vp, _i, _ll, _vp]),
     "pulpo_global_ncc_ws_bytes": (_sz, []),
     "pulpo_global_ncc": (_i, [_vp, _vp, _f, _f, _i, _ll, _vp, _vp, _sz, _vp]),

@@ -142,18 +142,38 @@ struct AxisConst2 {   // AxisConst with every constant duplicated into both halv
     float Sm1, tmax, gmul, kf;
 };
 
-__host__ __device__ inline AxisConst2 make_axis2(int S)
+// S: size of the axis the displacement field lives on (normalisation, src/network_blocks.py:106-107); Simg: size of
+// the sampled image along that axis (grid_sample's unnormalise, clamp and gather).  They differ when a level-sized
+// field resamples a full-resolution image (evaluate.py:198,240,246).
+__host__ __device__ inline AxisConst2 make_axis2(int S, int Simg)
 {
-    const AxisConst a = make_axis(S);
+    const AxisConst a = make_axis(S), i = make_axis(Simg);
     AxisConst2 r;
-    r.S.x = r.S.y = a.S;
+    r.S.x = r.S.y = i.S;
     r.nSm1.x = r.nSm1.y = -a.Sm1;
     r.rcp.x = r.rcp.y = a.rcp;
-    r.Sm1 = a.Sm1; r.tmax = a.tmax; r.gmul = a.gmul; r.kf = a.kf;
+    r.Sm1 = i.Sm1; r.tmax = i.tmax; r.gmul = i.gmul; r.kf = i.S / a.Sm1;
     return r;
 }
+__host__ __device__ inline AxisConst2 make_axis2(int S) { return make_axis2(S, S); }
 
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// a + b, both halves rounded to nearest, that ptxas does NOT contract with a preceding packed multiply: ptxas 12.9
+// fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with -fmad=false), which would break bit-identity with the CPU
+// sampler's separately rounded products and sums.  The .ftz flag on the add alone blocks the fusion; it only matters
+// for subnormal operands / results (|x| < 1.2e-38), which the interpolation of image intensities never produces
+// unless the exact value is already that small.
+__device__ __forceinline__ float2 add2_nofuse(float2 a, float2 b)
+{
+    unsigned long long ua, ub, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+    asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(ua), "l"(ub));
+    float2 o;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+    return o;
+}
 
 // non-finite / absurd loc: NaN and +huge must end at S-1, -huge at 0, like the division-based chain does; clamping
 // loc itself (IEEE minNum drops the NaN in favour of the bound) keeps the FMA chain below finite

@@ -448,6 +448,23 @@ global_ncc_kernel(const float *__restrict__ a, const float *__restrict__ v, floa
     }
 }
 
+// total = sum of the step's per-term / per-level loss scalars (fixed order), optionally also accumulated into a
+// running per-term sum -- replaces the ATen reduction that used to sit in the captured step, and lets multi-GPU
+// runs all-reduce the loss scalars once per K steps instead of once per step
+__global__ void loss_total_kernel(const float *__restrict__ losses, int rows, int cols, float *total, float *running,
+                                  int accumulate)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float t = 0.0f;
+    for (int r = 0; r < rows; ++r) {
+        float rs = 0.0f;
+        for (int c = 0; c < cols; ++c) rs += losses[r * cols + c];
+        if (running) running[r] = accumulate ? running[r] + rs : rs;
+        t += rs;
+    }
+    if (total) *total = t;
+}
+
 }  // namespace pulpo
 
 using namespace pulpo;
@@ -624,6 +641,15 @@ extern "C" int pulpo_global_ncc(const float *a, const float *v, float scale_a, f
     int grid = grid_for(n, 256, 4);
     if (grid > GNCC_MAX_CTAS) grid = GNCC_MAX_CTAS;
     global_ncc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, v, scale_a, scale_v, square_a, n, (GnccWs *)ws, out2);
+    return launch_status();
+}
+
+extern "C" int pulpo_loss_total(const float *losses, int rows, int cols, float *total, float *running, int accumulate,
+                                pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(losses && (total || running), PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(rows > 0 && cols > 0 && rows * cols <= 4096, PULPO_ERR_INVALID_SHAPE);
+    loss_total_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(losses, rows, cols, total, running, accumulate);
     return launch_status();
 }
 

@@ -34,7 +34,8 @@ namespace pulpo {
 constexpr int WR = PULPO_WARP_WR;
 
 struct WarpGeom {
-    int B, C, D0, D1, D2, S;
+    int B, C, D0, D1, D2, S;   // output / displacement-field grid
+    int I1, I2, Si;            // sampled image: rows, row length, voxels per channel (== D1, D2, S unless the sizes differ)
     int nxb, nyb;            // 32-voxel blocks per row, WR-row blocks per plane
     unsigned int items;      // B * D0 * nyb * nxb  (one per warp)
     int unbias;
@@ -42,40 +43,23 @@ struct WarpGeom {
     AxisConst2 a0, a1, a2;   // packed: the kernels process the WR rows of a thread as WR/2 pairs (FADD2 / FMUL2 / FFMA2)
 };
 
-static int make_geom(WarpGeom &g, int B, int C, int D0, int D1, int D2)
+static int make_geom(WarpGeom &g, int B, int C, int D0, int D1, int D2, int I0 = 0, int I1 = 0, int I2 = 0)
 {
-    i64 S = (i64)D0 * D1 * D2;
+    if (I0 <= 0) { I0 = D0; I1 = D1; I2 = D2; }
+    i64 S = (i64)D0 * D1 * D2, Si = (i64)I0 * I1 * I2;
     if (S >= (1ll << 31) || D0 > (1 << 22) || D1 > (1 << 22) || D2 > (1 << 22)) return PULPO_ERR_INVALID_SHAPE;
+    if (Si >= (1ll << 31) || I0 > (1 << 22) || I1 > (1 << 22) || I2 > (1 << 22) || I0 < 2 || I1 < 2 || I2 < 2) return PULPO_ERR_INVALID_SHAPE;
     g.B = B; g.C = C; g.D0 = D0; g.D1 = D1; g.D2 = D2; g.S = (int)S;
+    g.I1 = I1; g.I2 = I2; g.Si = (int)Si;
     g.nxb = (D2 + 31) / 32;
     g.nyb = (D1 + WR - 1) / WR;
     i64 items = (i64)B * D0 * g.nyb * g.nxb;
     if (items * 32 >= (1ll << 32)) return PULPO_ERR_INVALID_SHAPE;
     g.items = (unsigned int)items;
-    g.unbias = tap_unbias(D1, D2);
+    g.unbias = tap_unbias(I1, I2);
     g.dnxb = make_fastdiv(g.nxb); g.dnyb = make_fastdiv(g.nyb); g.dD0 = make_fastdiv(D0);
-    g.a0 = make_axis2(D0); g.a1 = make_axis2(D1); g.a2 = make_axis2(D2);
+    g.a0 = make_axis2(D0, I0); g.a1 = make_axis2(D1, I1); g.a2 = make_axis2(D2, I2);
     return PULPO_OK;
-}
-
-struct Foot {        // trilinear footprint of one voxel: 2x2x2 corners, always inside the volume
-    int base;        // offset of the low corner inside one [D0,D1,D2] volume
-    float wx0, wx1, wy0, wy1, wz0, wz1;
-};
-
-template <int MODE>
-__device__ __forceinline__ Foot make_foot(float zf, float yf, float xf, float dz, float dy, float dx,
-                                          const WarpGeom &g, float *uz = nullptr, float *uy = nullptr,
-                                          float *ux = nullptr, int *fl = nullptr)
-{
-    Tap tz = make_tap<MODE>(zf, dz, g.a0, uz);
-    Tap ty = make_tap<MODE>(yf, dy, g.a1, uy);
-    Tap tx = make_tap<MODE>(xf, dx, g.a2, ux);
-    Foot f;
-    f.base = tap_base(tz, ty, tx, g.D1, g.D2, g.unbias);
-    f.wx0 = tx.w0; f.wx1 = tx.w1; f.wy0 = ty.w0; f.wy1 = ty.w1; f.wz0 = tz.w0; f.wz1 = tz.w1;
-    if (fl) { fl[0] = tz.floor_p; fl[1] = ty.floor_p; fl[2] = tx.floor_p; }
-    return f;
 }
 
 // 8 corners of one footprint (fixed neighbour offsets)
@@ -106,22 +90,6 @@ __device__ __forceinline__ C8 gather8(const float *im, int base, const GStride &
     return k;
 }
 
-// same corner order and op order as the CPU grid sampler: bit-identical to torch-CPU
-__device__ __forceinline__ float interp8(const C8 &k, const Foot &f)
-{
-    const float w00 = __fmul_rn(f.wx0, f.wy0), w01 = __fmul_rn(f.wx1, f.wy0);
-    const float w10 = __fmul_rn(f.wx0, f.wy1), w11 = __fmul_rn(f.wx1, f.wy1);
-    float acc = __fmul_rn(k.c000, __fmul_rn(w00, f.wz0));
-    acc = __fadd_rn(acc, __fmul_rn(k.c001, __fmul_rn(w01, f.wz0)));
-    acc = __fadd_rn(acc, __fmul_rn(k.c010, __fmul_rn(w10, f.wz0)));
-    acc = __fadd_rn(acc, __fmul_rn(k.c011, __fmul_rn(w11, f.wz0)));
-    acc = __fadd_rn(acc, __fmul_rn(k.c100, __fmul_rn(w00, f.wz1)));
-    acc = __fadd_rn(acc, __fmul_rn(k.c101, __fmul_rn(w01, f.wz1)));
-    acc = __fadd_rn(acc, __fmul_rn(k.c110, __fmul_rn(w10, f.wz1)));
-    acc = __fadd_rn(acc, __fmul_rn(k.c111, __fmul_rn(w11, f.wz1)));
-    return acc;
-}
-
 // ---- two voxels (rows y, y+1 of the same column and plane) per instruction
 struct Foot2 {
     int base0, base1;
@@ -137,8 +105,8 @@ __device__ __forceinline__ Foot2 make_foot2(float zf, float yf, float xf, float2
     const Tap2 ty = make_tap2<MODE>(make_float2(yf, yf + 1.0f), dy, g.a1);
     const Tap2 tx = make_tap2<MODE>(splat2(xf), dx, g.a2);
     Foot2 f;
-    f.base0 = (tz.bits0 * g.D1 + ty.bits0) * g.D2 + tx.bits0 - g.unbias;
-    f.base1 = (tz.bits1 * g.D1 + ty.bits1) * g.D2 + tx.bits1 - g.unbias;
+    f.base0 = (tz.bits0 * g.I1 + ty.bits0) * g.I2 + tx.bits0 - g.unbias;
+    f.base1 = (tz.bits1 * g.I1 + ty.bits1) * g.I2 + tx.bits1 - g.unbias;
     f.wx0 = tx.w0; f.wx1 = tx.w1; f.wy0 = ty.w0; f.wy1 = ty.w1; f.wz0 = tz.w0; f.wz1 = tz.w1;
     f.uz = tz.u; f.uy = ty.u; f.ux = tx.u;
     if (fl) { fl[0] = tz.fl0; fl[1] = ty.fl0; fl[2] = tx.fl0; fl[3] = tz.fl1; fl[4] = ty.fl1; fl[5] = tx.fl1; }
@@ -147,20 +115,20 @@ __device__ __forceinline__ Foot2 make_foot2(float zf, float yf, float xf, float2
 
 __device__ __forceinline__ float2 pair(float a, float b) { return make_float2(a, b); }
 
-// interp8 for two voxels at once: the same products and sums in the same order (no FMA), so each half is
-// bit-identical to interp8
+// trilinear interpolation of two voxels at once: same corner order and op order as the CPU grid sampler (products and
+// sums rounded separately, no FMA), so each half is bit-identical to torch-CPU
 __device__ __forceinline__ float2 interp8x2(const C8 &a, const C8 &b, const Foot2 &f)
 {
     const float2 w00 = __fmul2_rn(f.wx0, f.wy0), w01 = __fmul2_rn(f.wx1, f.wy0);
     const float2 w10 = __fmul2_rn(f.wx0, f.wy1), w11 = __fmul2_rn(f.wx1, f.wy1);
     float2 acc = __fmul2_rn(pair(a.c000, b.c000), __fmul2_rn(w00, f.wz0));
-    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c001, b.c001), __fmul2_rn(w01, f.wz0)));
-    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c010, b.c010), __fmul2_rn(w10, f.wz0)));
-    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c011, b.c011), __fmul2_rn(w11, f.wz0)));
-    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c100, b.c100), __fmul2_rn(w00, f.wz1)));
-    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c101, b.c101), __fmul2_rn(w01, f.wz1)));
-    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c110, b.c110), __fmul2_rn(w10, f.wz1)));
-    acc = __fadd2_rn(acc, __fmul2_rn(pair(a.c111, b.c111), __fmul2_rn(w11, f.wz1)));
+    acc = add2_nofuse(acc, __fmul2_rn(pair(a.c001, b.c001), __fmul2_rn(w01, f.wz0)));
+    acc = add2_nofuse(acc, __fmul2_rn(pair(a.c010, b.c010), __fmul2_rn(w10, f.wz0)));
+    acc = add2_nofuse(acc, __fmul2_rn(pair(a.c011, b.c011), __fmul2_rn(w11, f.wz0)));
+    acc = add2_nofuse(acc, __fmul2_rn(pair(a.c100, b.c100), __fmul2_rn(w00, f.wz1)));
+    acc = add2_nofuse(acc, __fmul2_rn(pair(a.c101, b.c101), __fmul2_rn(w01, f.wz1)));
+    acc = add2_nofuse(acc, __fmul2_rn(pair(a.c110, b.c110), __fmul2_rn(w10, f.wz1)));
+    acc = add2_nofuse(acc, __fmul2_rn(pair(a.c111, b.c111), __fmul2_rn(w11, f.wz1)));
     return acc;
 }
 
@@ -255,7 +223,7 @@ warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, f
     const unsigned int nwarps = gridDim.x * 8u;
     const int lane = threadIdx.x & 31;
     const int S = g.S, sy = g.D2, sz = g.D1 * g.D2;
-    const GStride gst = make_gstride(sy, sz);
+    const GStride gst = make_gstride(g.I2, g.I1 * g.I2);
     float reg_acc = 0.0f;
     // persistent: whole waves of resident CTAs stride over the work items (one warp-item at a time)
     for (unsigned int w = (blockIdx.x * 256u + threadIdx.x) >> 5; w < g.items; w += nwarps) {
@@ -289,7 +257,7 @@ warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, f
             }
         }
         for (int c = 0; c < g.C; ++c) {
-            const float *im = img + ((i64)t.b * g.C + c) * S;
+            const float *im = img + ((i64)t.b * g.C + c) * g.Si;
             float *o = out + ((i64)t.b * g.C + c) * S + v0;
             // all 8*WR corner gathers are issued before the first interpolation (no branch in between: the
             // footprint of a lane outside the volume is clamped in-bounds, so its loads are legal and just
@@ -379,7 +347,8 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
     const unsigned int nwarps = gridDim.x * 8u;
     const int lane = threadIdx.x & 31;
     const int S = g.S, sy = g.D2, sz = g.D1 * g.D2;
-    const GStride gst = make_gstride(sy, sz);
+    const int isy = g.I2, isz = g.I1 * g.I2;
+    const GStride gst = make_gstride(isy, isz);
     const float reg_scale_k = REG ? (reg_gloss ? __ldg(reg_gloss) : 1.0f) * reg_k : 0.0f;
     for (unsigned int w = (blockIdx.x * 256u + threadIdx.x) >> 5; w < g.items; w += nwarps) {   // persistent, warp-uniform
     const WItem t = decode_witem(w, lane, g);
@@ -405,14 +374,14 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
         rz2[jp] = ry2[jp] = rx2[jp] = splat2(0.0f);
     }
     for (int c = 0; c < g.C; ++c) {
-        const i64 off = ((i64)t.b * g.C + c) * S;
+        const i64 off = ((i64)t.b * g.C + c) * S, ioff = ((i64)t.b * g.C + c) * g.Si;
         float go[WR];
         load_rows<true>(gout + off + v0, sy, ok, go);
         C8 qq[WR];   // all gathers first (see the forward)
 #pragma unroll
         for (int jp = 0; jp < WR / 2; ++jp) {
-            qq[2 * jp] = gather8(img + off, ft[jp].base0, gst);
-            qq[2 * jp + 1] = gather8(img + off, ft[jp].base1, gst);
+            qq[2 * jp] = gather8(img + ioff, ft[jp].base0, gst);
+            qq[2 * jp + 1] = gather8(img + ioff, ft[jp].base1, gst);
         }
 #pragma unroll
         for (int jp = 0; jp < WR / 2; ++jp) {
@@ -436,19 +405,19 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     if (!ok[2 * jp + h]) continue;
-                    float *o = gimg + off + (h ? k.base1 : k.base0);
+                    float *o = gimg + ioff + (h ? k.base1 : k.base0);
                     const float wx0 = h ? k.wx0.y : k.wx0.x, wx1 = h ? k.wx1.y : k.wx1.x, wy0 = h ? k.wy0.y : k.wy0.x,
                                 wy1 = h ? k.wy1.y : k.wy1.x, wz0 = h ? k.wz0.y : k.wz0.x, wz1 = h ? k.wz1.y : k.wz1.x;
                     const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
                     const float g0 = go[2 * jp + h] * wz0, g1 = go[2 * jp + h] * wz1;
                     atomicAdd(o, w00 * g0);
                     atomicAdd(o + 1, w01 * g0);
-                    atomicAdd(o + sy, w10 * g0);
-                    atomicAdd(o + sy + 1, w11 * g0);
-                    atomicAdd(o + sz, w00 * g1);
-                    atomicAdd(o + sz + 1, w01 * g1);
-                    atomicAdd(o + sz + sy, w10 * g1);
-                    atomicAdd(o + sz + sy + 1, w11 * g1);
+                    atomicAdd(o + isy, w10 * g0);
+                    atomicAdd(o + isy + 1, w11 * g0);
+                    atomicAdd(o + isz, w00 * g1);
+                    atomicAdd(o + isz + 1, w01 * g1);
+                    atomicAdd(o + isz + isy, w10 * g1);
+                    atomicAdd(o + isz + isy + 1, w11 * g1);
                 }
             }
         }
@@ -507,10 +476,10 @@ static unsigned int persistent_grid(unsigned int items, int per_sm)
 
 template <int MODE>
 static int launch_fwd(const float *img, const float *df, float *out, int32_t *idx, float *reg_out, ReduceWs *ws,
-                      double reg_scale, int B, int C, int D0, int D1, int D2, cudaStream_t st)
+                      double reg_scale, int B, int C, int D0, int D1, int D2, int I0, int I1, int I2, cudaStream_t st)
 {
     WarpGeom g;
-    int rc = make_geom(g, B, C, D0, D1, D2);
+    int rc = make_geom(g, B, C, D0, D1, D2, I0, I1, I2);
     if (rc != PULPO_OK) return rc;
     const unsigned int grid = persistent_grid(g.items, PULPO_WARP_FWD_CTAS);
     if (idx)
@@ -524,11 +493,11 @@ static int launch_fwd(const float *img, const float *df, float *out, int32_t *id
 
 template <int MODE>
 static int launch_bwd(const float *gout, const float *img, const float *df, float *gimg, float *gdf,
-                      const float *reg_gloss, float reg_k, bool reg, int B, int C, int D0, int D1, int D2,
-                      cudaStream_t st)
+                      const float *reg_gloss, float reg_k, bool reg, int B, int C, int D0, int D1, int D2, int I0, int I1,
+                      int I2, cudaStream_t st)
 {
     WarpGeom g;
-    int rc = make_geom(g, B, C, D0, D1, D2);
+    int rc = make_geom(g, B, C, D0, D1, D2, I0, I1, I2);
     if (rc != PULPO_OK) return rc;
     const unsigned int grid = persistent_grid(g.items, PULPO_WARP_BWD_CTAS);
     if (gimg && reg)
@@ -543,21 +512,22 @@ static int launch_bwd(const float *gout, const float *img, const float *df, floa
 }
 
 static int warp_fwd_dispatch(const float *img, const float *df, float *out, int32_t *idx, float *reg_out, void *ws,
-                             double reg_scale, int B, int C, int D0, int D1, int D2, int coord_mode, cudaStream_t st)
+                             double reg_scale, int B, int C, int D0, int D1, int D2, int coord_mode, cudaStream_t st,
+                             int I0 = 0, int I1 = 0, int I2 = 0)
 {
     ReduceWs *w = (ReduceWs *)ws;
     if (coord_mode == PULPO_COORD_CPU_EXACT)
-        return launch_fwd<0>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, st);
-    return launch_fwd<1>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, st);
+        return launch_fwd<0>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, I0, I1, I2, st);
+    return launch_fwd<1>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, I0, I1, I2, st);
 }
 
 static int warp_bwd_dispatch(const float *gout, const float *img, const float *df, float *gimg, float *gdf,
                              const float *reg_gloss, float reg_k, bool reg, int B, int C, int D0, int D1, int D2,
-                             int coord_mode, cudaStream_t st)
+                             int coord_mode, cudaStream_t st, int I0 = 0, int I1 = 0, int I2 = 0)
 {
     if (coord_mode == PULPO_COORD_CPU_EXACT)
-        return launch_bwd<0>(gout, img, df, gimg, gdf, reg_gloss, reg_k, reg, B, C, D0, D1, D2, st);
-    return launch_bwd<1>(gout, img, df, gimg, gdf, reg_gloss, reg_k, reg, B, C, D0, D1, D2, st);
+        return launch_bwd<0>(gout, img, df, gimg, gdf, reg_gloss, reg_k, reg, B, C, D0, D1, D2, I0, I1, I2, st);
+    return launch_bwd<1>(gout, img, df, gimg, gdf, reg_gloss, reg_k, reg, B, C, D0, D1, D2, I0, I1, I2, st);
 }
 
 static double l2reg_scale(float lamb, int B, int D0, int D1, int D2)
@@ -590,6 +560,28 @@ extern "C" int pulpo_warp3d_bwd(const float *gout, const float *img, const float
     PULPO_REQUIRE(coord_mode == 0 || coord_mode == 1, PULPO_ERR_UNSUPPORTED);
     return warp_bwd_dispatch(gout, img, df, gimg, gdf, nullptr, 0.0f, false, B, C, D0, D1, D2, coord_mode,
                              (cudaStream_t)stream);
+}
+
+extern "C" int pulpo_warp3d_fwd_img(const float *img, const float *df, float *out, int32_t *idx_dbg, int B, int C,
+                                    int D0, int D1, int D2, int I0, int I1, int I2, int coord_mode, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(img && df && out, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2 && I0 >= 2 && I1 >= 2 && I2 >= 2, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(coord_mode == 0 || coord_mode == 1, PULPO_ERR_UNSUPPORTED);
+    return warp_fwd_dispatch(img, df, out, idx_dbg, nullptr, nullptr, 0.0, B, C, D0, D1, D2, coord_mode,
+                             (cudaStream_t)stream, I0, I1, I2);
+}
+
+extern "C" int pulpo_warp3d_bwd_img(const float *gout, const float *img, const float *df, float *gimg, float *gdf,
+                                    int B, int C, int D0, int D1, int D2, int I0, int I1, int I2, int coord_mode,
+                                    pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(gout && img && df, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(gimg || gdf, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2 && I0 >= 2 && I1 >= 2 && I2 >= 2, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(coord_mode == 0 || coord_mode == 1, PULPO_ERR_UNSUPPORTED);
+    return warp_bwd_dispatch(gout, img, df, gimg, gdf, nullptr, 0.0f, false, B, C, D0, D1, D2, coord_mode,
+                             (cudaStream_t)stream, I0, I1, I2);
 }
 
 extern "C" int pulpo_warp3d_l2reg_fwd(const float *img, const float *df, float *out, float lamb, float *reg_out,

@@ -57,13 +57,20 @@ class _Warp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, df, img, coord_mode):
         df, img = _prep(df, "df"), _prep(img, "moving_image")
-        B, C, D0, D1, D2 = _dims5(img, "moving_image")
-        if tuple(df.shape) != (B, 3, D0, D1, D2):
-            raise RuntimeError("pulpo_b200: df must be [B,3,*size] matching moving_image, got %s vs %s"
+        B, C, I0, I1, I2 = _dims5(img, "moving_image")
+        Bd, Cd, D0, D1, D2 = _dims5(df, "df")
+        if Bd != B or Cd != 3:
+            raise RuntimeError("pulpo_b200: df must be [B,3,*size] with moving_image's batch size, got %s vs %s"
                                % (tuple(df.shape), tuple(img.shape)))
-        out = torch.empty_like(img)
-        check(_lib.lib().pulpo_warp3d_fwd(_ptr(img), _ptr(df), _ptr(out), None, B, C, D0, D1, D2, coord_mode,
-                                          _stream()), "warp3d_fwd")
+        # grid_sample semantics: the output has the field's spatial size; the image may have another one (a
+        # level-sized field resampling a full-resolution image, evaluate.py:198,240,246)
+        out = torch.empty((B, C, D0, D1, D2), dtype=torch.float32, device=img.device)
+        if (I0, I1, I2) == (D0, D1, D2):
+            check(_lib.lib().pulpo_warp3d_fwd(_ptr(img), _ptr(df), _ptr(out), None, B, C, D0, D1, D2, coord_mode,
+                                              _stream()), "warp3d_fwd")
+        else:
+            check(_lib.lib().pulpo_warp3d_fwd_img(_ptr(img), _ptr(df), _ptr(out), None, B, C, D0, D1, D2, I0, I1, I2,
+                                                  coord_mode, _stream()), "warp3d_fwd_img")
         ctx.save_for_backward(df, img)
         ctx.coord_mode = coord_mode
         return out
@@ -72,13 +79,18 @@ class _Warp(torch.autograd.Function):
     def backward(ctx, gout):
         df, img = ctx.saved_tensors
         gout = _prep(gout, "grad_output")
-        B, C, D0, D1, D2 = img.shape
+        B, C, I0, I1, I2 = img.shape
+        D0, D1, D2 = df.shape[2:]
         need_df, need_img = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gdf = torch.empty_like(df) if need_df else None
         gimg = torch.zeros_like(img) if need_img else None
         if need_df or need_img:
-            check(_lib.lib().pulpo_warp3d_bwd(_ptr(gout), _ptr(img), _ptr(df), _ptr(gimg), _ptr(gdf), B, C, D0, D1,
-                                              D2, ctx.coord_mode, _stream()), "warp3d_bwd")
+            if (I0, I1, I2) == (D0, D1, D2):
+                check(_lib.lib().pulpo_warp3d_bwd(_ptr(gout), _ptr(img), _ptr(df), _ptr(gimg), _ptr(gdf), B, C, D0, D1,
+                                                  D2, ctx.coord_mode, _stream()), "warp3d_bwd")
+            else:
+                check(_lib.lib().pulpo_warp3d_bwd_img(_ptr(gout), _ptr(img), _ptr(df), _ptr(gimg), _ptr(gdf), B, C, D0,
+                                                      D1, D2, I0, I1, I2, ctx.coord_mode, _stream()), "warp3d_bwd_img")
         return gdf, gimg, None
 
 

@@ -88,8 +88,12 @@ class HotPathPipeline:
         L = self.L
         total = self.plan.run(v["x"], v["y"], {l: v["df%d" % l] for l in range(L)}, {l: v["mu%d" % l] for l in range(L)},
                               {l: v["sigma%d" % l] for l in range(L)})
-        self.dres[0:1].copy_(total.view(1))
-        torch.sum(self.plan.losses, dim=1, out=self.dres[1:4])   # kl, recon, reg
+        # (total, kl, recon, reg) for the D2H read, by the library's own one-block kernel (no ATen op in the graph)
+        from ._lib import check
+        import ctypes
+        check(self.plan.lib.pulpo_loss_total(ctypes.c_void_p(self.plan.losses.data_ptr()), 3, L,
+                                             ctypes.c_void_p(self.dres.data_ptr()), ctypes.c_void_p(self.dres.data_ptr() + 4), 0,
+                                             ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)), "loss_total")
 
     def _capture(self, slot):
         cur = torch.cuda.current_stream(self.dev)

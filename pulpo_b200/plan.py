@@ -43,7 +43,7 @@ def _p(t, byte_offset=0):
 class HotPathPlan:
     def __init__(self, input_size, total_levels, latent_levels, batch=1, beta=0.1, gamma=0.05, lamb=0.025,
                  with_reg=True, nsteps=7, coord_mode=CPU_EXACT, device=None, multi_stream=True, fuse_reg=True,
-                 vecint_mode=CPU_EXACT, fuse_combine=False, pool_pyramid=True, aux_early=False):
+                 vecint_mode=CPU_EXACT, fuse_combine=False, pool_pyramid=True, aux_early=False, df_resolution="level_res"):
         self.L = L = latent_levels
         self.B = B = batch
         self.lk = lk = total_levels - latent_levels
@@ -58,15 +58,24 @@ class HotPathPlan:
         self.lib = _lib.lib()
         self.full = tuple(int(s) for s in input_size)
         sizes = level_sizes(self.full, total_levels)
+        if df_resolution not in ("level_res", "full_res"):
+            raise ValueError("df_resolution must be 'level_res' or 'full_res' (src/components/pulpo.py:146)")
+        self.df_resolution = df_resolution
+        full_res = df_resolution == "full_res"
         self.insz = {l: tuple(sizes[lk + l]) for l in range(L)}
-        self.outsz = {l: (self.full if l == 0 else self.insz[l]) for l in range(L)}
+        # outsize rule of Autoencoder.__init__ (src/components/pulpo.py:146): level 0 and, in full_res mode, every level
+        # warp / compare at the input size; the integration always runs at the latent size (:297)
+        self.outsz = {l: (self.full if (l == 0 or full_res) else self.insz[l]) for l in range(L)}
+        self.ofac = {}
         for l in range(L):
-            if l == 0 and self.insz[0] != self.full and tuple(2 * s for s in self.insz[0]) != self.full:
-                raise NotImplementedError("HotPathPlan: level-0 output resize must be x1 or x2 (got %s -> %s)"
-                                          % (self.insz[0], self.full))
+            f = [o // i for o, i in zip(self.outsz[l], self.insz[l])]
+            if any(i * f[0] != o for o, i in zip(self.outsz[l], self.insz[l])) or f[0] < 1 or f[0] > 64:
+                raise NotImplementedError("HotPathPlan: the output resize of level %d must be one integer factor <= 64 "
+                                          "(got %s -> %s)" % (l, self.insz[l], self.outsz[l]))
+            self.ofac[l] = f[0]
             if l + 1 < L and tuple(2 * s for s in self.insz[l + 1]) != self.insz[l]:
                 raise ValueError("level sizes must halve exactly (reference DFAdder would shape-mismatch)")
-        win, kl_w, rec_w, reg_w = loss_config(L, lk)
+        win, kl_w, rec_w, reg_w = loss_config(L, lk, 3, df_resolution)
         self.win = win
         self.kl_weight = {l: float(beta * kl_w[l]) for l in range(L)}
         self.gamma_eff = {l: float(gamma * rec_w[l]) for l in range(L)}
@@ -78,7 +87,7 @@ class HotPathPlan:
         lib = self.lib
         # moving pyramid: pooled[i] = x pooled (i+1) times; level l >= 1 uses pooled[lk + l - 1]
         self.pooled, s = [], self.full
-        for _ in range(lk + L - 1 if L > 1 else 0):
+        for _ in range((lk + L - 1) if (L > 1 and not full_res) else 0):   # full_res: every level warps x itself
             s = tuple((v + 1) // 2 for v in s)
             self.pooled.append(buf(B, 1, *s))
         self.yt = {l: buf(B, 1, *self.outsz[l]) for l in range(L) if self.outsz[l] != self.full}
@@ -100,6 +109,7 @@ class HotPathPlan:
         self.gsigma = {l: buf(B, 3, *self.insz[l]) for l in range(L)}
         self.losses = torch.zeros(3, L, dtype=torch.float32, device=dev)        # rows: kl, recon, reg
         self.total = torch.zeros((), dtype=torch.float32, device=dev)
+        self.running = torch.zeros(3, dtype=torch.float32, device=dev)          # per-term sums over the steps run so far
         # reduction workspaces (ticket counters must start at zero; kernels reset them)
         rbytes = lib.pulpo_reduce_ws_bytes()
         self.ws_klm = torch.zeros(lib.pulpo_kl_multi_ws_bytes(), dtype=torch.uint8, device=dev)
@@ -147,7 +157,9 @@ class HotPathPlan:
         def aux_work(after):
             if ms:
                 aux.wait_event(after)
-            if self.pool_pyramid:
+            if not self.pooled:
+                pass
+            elif self.pool_pyramid:
                 outs = (ctypes.c_void_p * len(self.pooled))(*[t.data_ptr() for t in self.pooled])
                 call(lib.pulpo_avgpool2_pyramid_fwd, _p(x), outs, len(self.pooled), B, 1, *self.full, H(aux))
                 ev = torch.cuda.Event()
@@ -179,7 +191,7 @@ class HotPathPlan:
         ev_kl = aux_work(start) if self.aux_early else None
         lx = {0: x}
         for l in range(1, L):
-            lx[l] = self.pooled[self.lk + l - 1]
+            lx[l] = x if self.df_resolution == "full_res" else self.pooled[self.lk + l - 1]
 
         # ---- coarse-to-fine field combination (pulpo.py:308) on the current stream (or, fuse_combine, inside the
         #      integration launch)
@@ -219,7 +231,8 @@ class HotPathPlan:
                 s.wait_event(ev_int)
             # resize the integrated field to the output size
             if dout != din:
-                call(lib.pulpo_resize_up_fwd, _p(self.integ[l]), None, _p(self.final[l]), 2, 2.0, B, 3, *din, hs)
+                call(lib.pulpo_resize_up_fwd, _p(self.integ[l]), None, _p(self.final[l]), self.ofac[l], float(self.ofac[l]),
+                     B, 3, *din, hs)
             # warp the (pooled) moving image
             if ms and l in ev_lx:
                 s.wait_event(ev_lx[l])
@@ -251,7 +264,8 @@ class HotPathPlan:
                 call(lib.pulpo_l2reg_bwd, None, _p(self.final[l]), self.lamb_eff[l], _p(self.gfinal[l]), 1, B, 3,
                      *dout, hs)
             if dout != din:
-                call(lib.pulpo_resize_up_bwd, _p(self.gfinal[l]), _p(self.ginteg[l]), 2, 2.0, 0, B, 3, *din, hs)
+                call(lib.pulpo_resize_up_bwd, _p(self.gfinal[l]), _p(self.ginteg[l]), self.ofac[l], float(self.ofac[l]), 0,
+                     B, 3, *din, hs)
             ev_done[l] = torch.cuda.Event()
             ev_done[l].record(s)
 
@@ -260,8 +274,7 @@ class HotPathPlan:
         if ms:
             for l in range(L):
                 aux.wait_event(ev_done[l])
-            with torch.cuda.stream(aux):
-                torch.sum(self.losses, dim=(0, 1), out=self.total)
+            call(lib.pulpo_loss_total, _p(self.losses), 3, L, _p(self.total), _p(self.running), 1, H(aux))
             ev_total = torch.cuda.Event()
             ev_total.record(aux)
 
@@ -283,9 +296,77 @@ class HotPathPlan:
         if ms:
             cur.wait_event(ev_total)
         else:
-            torch.sum(self.losses, dim=(0, 1), out=self.total)
+            call(lib.pulpo_loss_total, _p(self.losses), 3, L, _p(self.total), _p(self.running), 1, H(cur))
         self.launches = n[0]
         return self.total
+
+    # ------------------------------------------------------------------------------------------
+    def run_forward(self, x, dfs, levels=None):
+        """Inference half of ``run`` (MC uncertainty sampling, evaluate.py:205-251 -> models.py:312-331,349-368):
+        combine -> integrate -> output resize -> warp for every level, no losses, no backward.  ``dfs[l]`` are the
+        sampled velocity fields.  Results in ``self.comb / self.integ / self.final / self.moved``; graph-capturable."""
+        lib, L, B, mode = self.lib, self.L, self.B, self.mode
+        cur = torch.cuda.current_stream(self.dev)
+        ms = self.multi_stream
+        lv = [self.streams[l] if ms else cur for l in range(L)]
+        aux = self.streams[L] if ms else cur
+        n = [0]
+
+        def call(fn, *a):
+            n[0] += 1
+            check(fn(*a), fn.__name__ if hasattr(fn, "__name__") else "")
+
+        def H(s):
+            return _vp(s.cuda_stream)
+
+        start = torch.cuda.Event()
+        start.record(cur)
+        ev_lx = None
+        if self.pooled:
+            if ms:
+                aux.wait_event(start)
+            if self.pool_pyramid:
+                outs = (ctypes.c_void_p * len(self.pooled))(*[t.data_ptr() for t in self.pooled])
+                call(lib.pulpo_avgpool2_pyramid_fwd, _p(x), outs, len(self.pooled), B, 1, *self.full, H(aux))
+            else:
+                src, shape = x, self.full
+                for dst in self.pooled:
+                    call(lib.pulpo_avgpool2_fwd, _p(src), _p(dst), B, 1, *shape, H(aux))
+                    src, shape = dst, tuple(dst.shape[2:])
+            ev_lx = torch.cuda.Event()
+            ev_lx.record(aux)
+        lx = {0: x}
+        for l in range(1, L):
+            lx[l] = x if self.df_resolution == "full_res" else self.pooled[self.lk + l - 1]
+        comb = {L - 1: dfs[L - 1]}
+        for l in range(L - 2, -1, -1):
+            call(lib.pulpo_resize_up_fwd, _p(comb[l + 1]), _p(dfs[l]), _p(self.comb[l]), 2, 2.0, B, 3, *self.insz[l + 1], H(cur))
+            comb[l] = self.comb[l]
+        lv_arr = (_lib.VecIntLevel * L)()
+        for l in range(L):
+            ws, scr = self.vi_ws[l], self.vi_scr[l]
+            lv_arr[l] = _lib.VecIntLevel(comb[l].data_ptr(), self.integ[l].data_ptr(), ws.data_ptr(), ws.numel() * 4,
+                                         scr.data_ptr(), scr.numel() * 4, *self.insz[l])
+        call(lib.pulpo_vecint_multi_fwd, lv_arr, L, self.nsteps, 1, B, self.vi_mode, H(cur))
+        ev_int = torch.cuda.Event()
+        ev_int.record(cur)
+        for l in range(L - 1, -1, -1):
+            s = lv[l]
+            if ms:
+                s.wait_event(ev_int)
+                if ev_lx is not None and l > 0:
+                    s.wait_event(ev_lx)
+            din, dout = self.insz[l], self.outsz[l]
+            if dout != din:
+                call(lib.pulpo_resize_up_fwd, _p(self.integ[l]), None, _p(self.final[l]), self.ofac[l], float(self.ofac[l]),
+                     B, 3, *din, H(s))
+            call(lib.pulpo_warp3d_fwd, _p(lx[l]), _p(self.final[l]), _p(self.moved[l]), None, B, 1, *dout, mode, H(s))
+            if ms:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                cur.wait_event(ev)
+        self.launches = n[0]
+        return self.moved
 
     # convenience -----------------------------------------------------------------------------
     def outputs(self):

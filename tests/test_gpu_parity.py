@@ -309,7 +309,7 @@ def test_combine_up2_golden(PF):
     assert_grad_close(ind.grad.cpu().numpy(), g["gindiv"], "combine gindiv")
 
 
-@pytest.mark.parametrize("f", [2, 4, 8])
+@pytest.mark.parametrize("f", [2, 4, 8, 16])
 def test_resize_up_golden(PF, f):
     from pulpo_b200.network_blocks import ResizeTransform
     g = load_golden("resize_up%d" % f)
@@ -700,6 +700,51 @@ def test_plan_matches_autograd_modules_config1(PF):
         assert_grad_close(plan.gsigma[l].cpu().numpy(), s[l].grad.cpu().numpy(), "gsigma %d" % l)
 
 
+def test_plan_full_res_mode_vs_torch_oracle_and_modules(PF):
+    """df_resolution="full_res" (src/components/pulpo.py:146: every level warps / compares at the input size, output
+    resize factors 2 / 4 / 8 here and 16 at config 2) through the graph-captured plan: all losses, moved images, final
+    fields and input gradients against the torch-CPU restatement, and the same losses from the autograd modules."""
+    from oracle import torch_ref as T
+    from pulpo_b200 import synthetic as syn
+    from pulpo_b200.models import RegistrationHotPath
+    size, total, latent = [32, 48, 64], 4, 3
+    x, y, dfs, mus, sgs = syn.make_hot_path_inputs(size, total, latent, seed=4)
+    dev_in = (x.cuda(), y.cuda(), {l: dfs[l].cuda() for l in dfs}, {l: mus[l].cuda() for l in dfs},
+              {l: sgs[l].cuda() for l in dfs})
+    plan = _run_plan(dev_in, total, latent, size, 1, True, True, df_resolution="full_res")
+    assert [plan.ofac[l] for l in range(latent)] == [2, 4, 8]
+    d_ref = {l: dfs[l].clone().requires_grad_(True) for l in dfs}
+    m_ref = {l: mus[l].clone().requires_grad_(True) for l in dfs}
+    s_ref = {l: sgs[l].clone().requires_grad_(True) for l in dfs}
+    ref, parts, ref_out = T.hot_path_losses(x, y, d_ref, m_ref, s_ref, total, full_res=True)
+    ref.backward()
+    assert_loss_close(plan.total.item(), ref.item(), "total (full_res)")
+    for l in range(latent):
+        assert tuple(plan.moved[l].shape[2:]) == tuple(size)
+        assert_close(plan.moved[l].cpu().numpy(), ref_out["moved"][l].detach().numpy(), FIELD_ATOL, "moved %d" % l)
+        assert_close(plan.final[l].cpu().numpy(), ref_out["final"][l].detach().numpy(), FIELD_ATOL, "final %d" % l)
+        assert_grad_close(plan.gdf[l].cpu().numpy(), d_ref[l].grad.numpy(), "gdf %d" % l)
+        assert_grad_close(plan.gmu[l].cpu().numpy(), m_ref[l].grad.numpy(), "gmu %d" % l)
+    d = {l: dfs[l].cuda().requires_grad_(True) for l in dfs}
+    loss, _, _ = RegistrationHotPath(size, total, latent, df_resolution="full_res").cuda()(dev_in[0], dev_in[1], d, dev_in[3], dev_in[4])
+    assert_loss_close(loss.item(), ref.item(), "modules total (full_res)")
+
+
+def test_warp_image_larger_than_field_golden(PF):
+    """A level-sized field resampling a full-resolution image (grid_sample normalises with the field size and
+    samples the image at its own size; evaluate.py:198,240,246): forward bit-identical, both gradients."""
+    from pulpo_b200.network_blocks import SpatialTransformer
+    g = load_golden("warp_img_size")
+    df, img = dev(g["df"], True), dev(g["img"], True)
+    out = SpatialTransformer(tuple(g["df"].shape[2:]))(df, img)
+    assert tuple(out.shape) == tuple(g["out"].shape)
+    assert np.array_equal(out.detach().cpu().numpy(), g["out"]), \
+        "not bit-identical: max-abs %.3e" % np.abs(out.detach().cpu().numpy() - g["out"]).max()
+    out.backward(dev(g["gout"]))
+    assert_grad_close(df.grad.cpu().numpy(), g["gdf"], "gdf")
+    assert_grad_close(img.grad.cpu().numpy(), g["gimg"], "gimg")
+
+
 # ----------------------------------------------------------------------------- MC moments (f-3, config 3)
 def test_moments_kernels_match_torch_std(PF):
     from pulpo_b200 import mc
@@ -965,3 +1010,82 @@ def test_transform_segmentation_many_channels_and_image_gradient(PF):
     out.backward(gout.cuda())
     gimg_ref, gdf_ref = cport.warp3d_bwd(gout.numpy(), df.numpy(), seg.numpy())
     assert_grad_close(img.grad.cpu().numpy(), gimg_ref, "segmentation gimg")
+
+
+# ----------------------------------------------------------------------------- NaN / Inf propagation
+# The reference stops training when a loss turns NaN (src/models.py:188-194): the kernels must let non-finite values
+# through exactly where torch does -- no silent clamping -- and must not invent them where torch stays finite
+# (grid_sample sends a NaN / +-Inf sample position to a border voxel: the output there is finite).
+def _same_nonfinite(a, b, what, atol=FIELD_ATOL, superset=False):
+    """``superset``: the kernels keep every trilinear footprint 2x2x2 in-bounds -- at a sample position of exactly
+    S-1 they read corner S-2 with weight 0 where torch skips the out-of-range corner S -- so a non-finite value at
+    S-2 gives 0 * Inf = NaN here and a finite number in torch.  Never fewer non-finite values than torch, and equal
+    wherever both are finite; a loss that is NaN in torch is NaN here."""
+    a, b = a.detach().cpu().numpy(), b.detach().cpu().numpy()
+    if superset:
+        assert not np.any(~np.isfinite(b) & np.isfinite(a)), "%s: finite where torch is not" % what
+        fin = np.isfinite(a) & np.isfinite(b)
+    else:
+        assert np.array_equal(np.isnan(a), np.isnan(b)), "%s: NaN pattern differs (%d vs %d NaNs)" % (what, np.isnan(a).sum(), np.isnan(b).sum())
+        assert np.array_equal(np.isposinf(a), np.isposinf(b)) and np.array_equal(np.isneginf(a), np.isneginf(b)), what + ": Inf pattern"
+        fin = np.isfinite(b)
+    assert_close(a[fin], b[fin], atol, what + " (finite part)")
+
+
+def test_nonfinite_warp_matches_torch(PF):
+    from oracle import torch_ref as T
+    from pulpo_b200 import synthetic as syn
+    shape = (8, 9, 12)
+    df = syn.make_field(shape, 3, max_abs=2.0)
+    img = syn.make_field(shape, 4, max_abs=1.0, channels=2)
+    df[0, 0, 2, 3, 4] = float("nan"); df[0, 1, 5, 5, 5] = float("inf"); df[0, 2, 1, 1, 1] = float("-inf")
+    df[0, 2, 6, 2, 7] = 1e30; df[0, 0, 3, 3, 3] = -1e30
+    img[0, 0, 4, 4, 6] = float("nan"); img[0, 1, 2, 2, 2] = float("inf")
+    ref = T.warp(df, img)
+    out = PF.warp(df.cuda(), img.cuda())
+    _same_nonfinite(out, ref, "warp", atol=1e-6)
+    # sampling indices stay bit-exact for the non-finite positions too (NaN, +Inf -> S-1; -Inf -> 0)
+    from oracle import cport
+    _, idx = PF.warp_indices(df.cuda(), img.cuda())
+    _, idx_ref = cport.warp3d_fwd(df.numpy(), img.numpy(), want_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), idx_ref)
+
+
+def test_nonfinite_vecint_matches_torch(PF):
+    from oracle import torch_ref as T
+    from pulpo_b200 import synthetic as syn
+    vec = syn.make_field((8, 10, 12), 5, max_abs=3.0)
+    vec[0, 1, 3, 4, 5] = float("nan")
+    _same_nonfinite(PF.vecint(vec.cuda(), 7), T.vecint(vec, 7), "vecint (NaN)", atol=1e-5)
+    vec[0, 0, 6, 2, 9] = float("inf")       # sends samples to the border: the zero-weight-corner caveat applies
+    _same_nonfinite(PF.vecint(vec.cuda(), 7), T.vecint(vec, 7), "vecint (NaN + Inf)", atol=1e-5, superset=True)
+
+
+@pytest.mark.parametrize("bad", [float("nan"), float("inf")])
+def test_nonfinite_losses_match_torch(PF, bad):
+    from oracle import torch_ref as T
+    from pulpo_b200 import synthetic as syn
+    shape = (12, 16, 48)
+    x, y = syn.make_pair(shape, 1)
+    xb = x.clone(); xb[0, 0, 5, 6, 7] = bad
+    for win in (9, 3):      # TMA-staged kernel (D2 >= 44) and its small-window variant
+        got, ref = PF.ncc_loss(xb.cuda(), y.cuda(), win, 0.05), T.ncc_loss(xb, y, win, 0.05)
+        assert torch.isnan(ref) and torch.isnan(got.cpu()), "NCC(win %d) must turn NaN like torch (got %r, ref %r)" % (win, got, ref)
+    xs = x[:, :, :6, :7, :9].contiguous(); ys = y[:, :, :6, :7, :9].contiguous()   # generic kernel
+    xs[0, 0, 1, 2, 3] = bad
+    assert torch.isnan(T.ncc_loss(xs, ys, 5, 0.05)) and torch.isnan(PF.ncc_loss(xs.cuda(), ys.cuda(), 5, 0.05).cpu())
+    f = syn.make_field((6, 8, 10), 2, max_abs=2.0); f[0, 2, 3, 4, 5] = bad
+    got, ref = PF.l2_reg(f.cuda(), 0.025), T.l2_reg(f, 0.025)
+    _same_nonfinite(got, ref, "L2_reg")
+    mu = syn.make_field((6, 8, 10), 6, max_abs=1.0); sg = mu.abs() + 0.1
+    mub = mu.clone(); mub[0, 0, 1, 1, 1] = bad
+    z, o = torch.zeros_like(mu), torch.ones_like(mu)
+    _same_nonfinite(PF.kl_diag(mub.cuda(), sg.cuda(), z.cuda(), o.cuda()), T.kl_diag(mub, sg, z, o), "KL (mu)")
+    sgb = sg.clone(); sgb[0, 1, 2, 2, 2] = bad
+    _same_nonfinite(PF.kl_diag(mu.cuda(), sgb.cuda(), z.cuda(), o.cuda()), T.kl_diag(mu, sgb, z, o), "KL (sigma)")
+    # and the gradient carries the NaN back to the offending element (anomaly mode would flag it there)
+    m = mub.cuda().requires_grad_(True)
+    PF.kl_diag(m, sg.cuda(), z.cuda(), o.cuda()).backward()
+    mr = mub.clone().requires_grad_(True)
+    T.kl_diag(mr, sg, z, o).backward()
+    assert np.array_equal(np.isnan(m.grad.cpu().numpy()), np.isnan(mr.grad.numpy()))
