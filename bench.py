@@ -33,11 +33,15 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # name: (input_size, total_levels, latent_levels)
-    "oasis_160x192x224_5tot_4lat": ([160, 192, 224], 5, 4),
-    "cube64_4tot_3lat": ([64, 64, 64], 4, 3),
+    "oasis_160x192x224_5tot_4lat": ([160, 192, 224], 5, 4),      # BASELINE.json configs[1] (and [4] with --batch / --grad-allreduce)
+    "cube64_4tot_3lat": ([64, 64, 64], 4, 3),                    # configs[0]
+    "oasis_4tot_4lat": ([160, 192, 224], 4, 4),                  # configs[3]: total = latent levels -> level 0 integrates at full resolution
+    "vecint_fullres": ([160, 192, 224], 1, 1),                   # configs[3]: stand-alone VecInt((160,192,224), 7) fwd + bwd
+    "mc128": ([160, 192, 224], 5, 4),                            # configs[2]: 128 MC deformation samples per pair, sharded over the ranks
 }
 CPU_WORKLOADS = ("oasis_160x192x224_5tot_4lat", "cube64_4tot_3lat")
 ALGO_BYTES_PER_VOXEL = 220.9   # SURVEY.md 8d, config 2, fwd+bwd incl. L2_reg
+SURVEY_BYTES_PER_VOXEL = {"oasis_160x192x224_5tot_4lat": ALGO_BYTES_PER_VOXEL, "cube64_4tot_3lat": 220.7, "oasis_4tot_4lat": 739.0}
 METRIC = "hot-path fwd+bwd throughput (warp + integration + pyramid + NCC/KL/L2)"
 UNIT = "Gvoxel/s"
 
@@ -55,6 +59,9 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx, self.proc, self.lines = gpu_index, None, []
         self.nvml, self.handle, self.samples, self.stop_flag, self.thread = None, None, [], False, None
+        self.inert = gpu_index is None       # ranks other than 0: no polling thread fighting the launch thread for the GIL
+        if self.inert:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -78,6 +85,8 @@ class ClockSampler:
     window = "timed region"
 
     def count_inside(self):
+        if self.inert:
+            return 99
         t1 = self.t_end if self.t_end is not None else time.perf_counter()
         return sum(1 for t, _, _ in self.samples if self.t_begin <= t <= t1) if self.nvml is not None else 99
 
@@ -91,6 +100,8 @@ class ClockSampler:
         """Start polling (call it before the warm-up so the thread is up and running when the timed region
         starts); ``mark_begin`` / ``mark_end`` bracket the region on the host clock."""
         self.t_begin, self.t_end = time.perf_counter(), None
+        if self.inert:
+            return
         if self.nvml is not None:
             self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
@@ -108,6 +119,8 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.inert:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled on this rank"]}
         if self.nvml is not None:
             n = self.nvml
             self.stop_flag = True
@@ -263,6 +276,58 @@ def run_reference(args):
     _emit(line)
 
 
+def kernel_breakdown(prof_step, prof_steps, peak, peak_src):
+    """Run ``prof_step`` a few times with CUDA events around every C-ABI call; returns the per-entry-point table, the
+    roofline object of the launch shape with the largest share of the step, and the algorithmic bytes of one step
+    (sum over its calls, pulpo_b200/roofline.py = SURVEY.md 8d)."""
+    import torch
+    from pulpo_b200 import _lib
+    from pulpo_b200.roofline import algo_bytes
+    _lib.profiler.enabled, _lib.profiler.timing = True, True
+    _lib.profiler.reset()
+    for _ in range(prof_steps):
+        prof_step()
+    torch.cuda.synchronize()
+    _lib.profiler.enabled = _lib.profiler.timing = False
+    agg, shapes = {}, {}
+    for name, cargs, s_ev, e_ev in _lib.profiler.records:
+        t_ms, nb = s_ev.elapsed_time(e_ev), algo_bytes(name, cargs)
+        a = agg.setdefault(name, {"ms": 0.0, "bytes": 0, "calls": 0})
+        a["ms"] += t_ms; a["bytes"] += nb; a["calls"] += 1
+        g = shapes.setdefault((name, nb), {"ms": 0.0, "n": 0})   # one entry per distinct launch shape
+        g["ms"] += t_ms; g["n"] += 1
+    breakdown = {k: {"ms_per_step": v["ms"] / prof_steps, "calls_per_step": v["calls"] / prof_steps,
+                     "algo_MB_per_step": v["bytes"] / prof_steps / 1e6,
+                     "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None}
+                 for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+    (dname, dbytes), dg = max(shapes.items(), key=lambda kv: kv[1]["ms"])
+    d_ms = dg["ms"] / dg["n"]
+    achieved = dbytes / (d_ms * 1e-3) / 1e9
+    # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture of this same command
+    # (profiles/<tag>_traffic.json, written by scripts/summarize_ncu_full.py); None when no capture is committed
+    traffic, traffic_src = None, None
+    try:
+        import glob
+        for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
+            tj = json.load(open(path))
+            for kname, rec in tj.items():
+                if rec.get("entry_point") == dname or KERNEL_OF_ENTRY.get(dname) == kname:
+                    traffic, traffic_src = rec["dram_bytes_per_launch"], os.path.relpath(path, ROOT)
+    except Exception:
+        pass
+    roofline = {"kernel": dname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "bytes_per_launch": dbytes, "us_per_launch": d_ms * 1e3, "launches_timed": dg["n"],
+                "share_of_step": dg["ms"] / sum(v["ms"] for v in agg.values()),
+                "note": "launch shape with the largest share of the step; algorithmic bytes (SURVEY.md 8d) / mean CUDA-event duration"}
+    return breakdown, roofline, sum(v["bytes"] for v in agg.values()) / prof_steps
+
+
+KERNEL_OF_ENTRY = {"pulpo_vecint_multi_bwd": "vecint_bwd_kernel<0, 2>", "pulpo_vecint_multi_fwd": "vecint_fwd_kernel<0>",
+                   "pulpo_warp3d_l2reg_bwd": "warp3d_bwd_kernel<0, 0, 1>", "pulpo_warp3d_l2reg_fwd": "warp3d_fwd_kernel<0, 0, 1>",
+                   "pulpo_ncc_fwd": "ncc_tma_kernel<9, 1>", "pulpo_ncc_bwd": "ncc_tma_kernel<9, 0>"}
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -319,10 +384,16 @@ def run_ours(args):
         ss = {l: s[l].detach() for l in s}
 
     def exchange(parts3):
-        # the only exchange this path has: the three loss scalars (gradients of the convs live upstream)
+        # the only exchange the path itself has: the three loss scalars (gradients of the convs live upstream)
         if world > 1:
             scal.copy_(parts3)
             dist.all_reduce(scal)
+
+    # config 5 (BASELINE.json configs[4]): data-parallel training also all-reduces the conv encoder/decoder gradients
+    # (14 667 012 fp32 = 58.7 MB at n0=32, 5/4 levels).  The convs are out of scope, so a buffer of that
+    # size stands for them; its all-reduce is issued asynchronously at the start of a step and waited for at its
+    # end, i.e. it overlaps the hot path of the same step on NCCL's own stream.
+    gradbuf = torch.zeros(14667012, device=dev) if (args.grad_allreduce and world > 1) else None
 
     def compute():
         """One hot-path forward+backward (the part that is captured as a CUDA graph)."""
@@ -337,7 +408,8 @@ def run_ours(args):
 
     def step():
         loss = compute()
-        exchange(plan.losses.sum(dim=1) if plan is not None else step.parts)
+        if plan is None:
+            exchange(step.parts)
         return loss
 
     # ---- warm-up (eager), then capture the step as ONE CUDA graph
@@ -368,11 +440,19 @@ def run_ours(args):
         launch_mode = "eager"
 
     def run_step():
+        work = dist.all_reduce(gradbuf, async_op=True) if gradbuf is not None else None
         if graph is not None:
-            graph.replay()
-            exchange(plan.losses.sum(dim=1))   # NCCL all-reduce of the loss scalars stays outside the graph
+            graph.replay()     # the per-term loss sums accumulate on the device (plan.running): no per-step collective
         else:
             step()
+        if work is not None:
+            work.wait()        # stream-side wait: the next step's kernels queue behind the all-reduce
+
+    def sync_losses():
+        # ONE all-reduce of the logged loss scalars per timed region instead of one per step
+        if world > 1 and plan is not None:
+            scal.copy_(plan.running)
+            dist.all_reduce(scal)
 
     # count our kernel launches per step (C-ABI calls; each enqueues exactly one kernel)
     _lib.profiler.enabled, _lib.profiler.timing = True, False
@@ -388,16 +468,18 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- timed region: EXACTLY K steps, CUDA events, max over ranks
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local if rank == 0 else None)    # NVML is polled on rank 0 only
     clocks.start()
     for _ in range(args.warmup):
         run_step()
+    sync_losses()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks.mark_begin()
     e0.record()
     for _ in range(args.steps):
         run_step()
+    sync_losses()
     e1.record()
     barrier()
     clocks.mark_end()
@@ -433,14 +515,17 @@ def run_ours(args):
         e2e_api = "pulpo_b200.pipeline.HotPathPipeline.submit/result (packed pinned batch, copy/compute overlap)"
 
         def e2e_run(n):
-            last = None
+            last, acc = None, [0.0, 0.0, 0.0]
             for k in range(n):
                 t = pipe.submit(hbs[k % 2])
                 if last is not None:
                     r = pipe.result(last)        # D2H read of the previous step's result
-                    exchange(torch.tensor(r[1:], device=dev)) if world > 1 else None
+                    acc = [a + b for a, b in zip(acc, r[1:])]
                 last = t
-            return pipe.result(last)
+            r = pipe.result(last)
+            if world > 1:                        # the logged scalars: one all-reduce per region, not per step
+                exchange(torch.tensor([a + b for a, b in zip(acc, r[1:])], device=dev))
+            return r
     else:
         d2h_bytes = 4
         e2e_api = "pulpo_b200.models.RegistrationHotPath forward + backward (autograd modules)"
@@ -476,46 +561,10 @@ def run_ours(args):
         prof_step = lambda: plan1.run(x, y, dd, mm, ss)
         prof_step()
         torch.cuda.synchronize()
-    _lib.profiler.enabled, _lib.profiler.timing = True, True
-    _lib.profiler.reset()
-    prof_steps = max(2, min(args.steps, 5))
-    for _ in range(prof_steps):
-        prof_step()
-    torch.cuda.synchronize()
-    _lib.profiler.enabled = _lib.profiler.timing = False
-    agg, shapes = {}, {}
-    for name, cargs, s_ev, e_ev in _lib.profiler.records:
-        t_ms, nb = s_ev.elapsed_time(e_ev), algo_bytes(name, cargs)
-        a = agg.setdefault(name, {"ms": 0.0, "bytes": 0, "calls": 0})
-        a["ms"] += t_ms; a["bytes"] += nb; a["calls"] += 1
-        g = shapes.setdefault((name, nb), {"ms": 0.0, "n": 0})   # one entry per distinct launch shape
-        g["ms"] += t_ms; g["n"] += 1
-    breakdown = {k: {"ms_per_step": v["ms"] / prof_steps, "calls_per_step": v["calls"] / prof_steps,
-                     "algo_MB_per_step": v["bytes"] / prof_steps / 1e6,
-                     "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None}
-                 for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
-    (dname, dbytes), dg = max(shapes.items(), key=lambda kv: kv[1]["ms"])
-    d_ms = dg["ms"] / dg["n"]
-    achieved = dbytes / (d_ms * 1e-3) / 1e9
-    # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture of this same command
-    # (profiles/<tag>_traffic.json, written by scripts/summarize_ncu_full.py); None when no capture is committed
-    traffic, traffic_src = None, None
-    kmap = {"pulpo_vecint_multi_bwd": "vecint_bwd_kernel<0, 2>", "pulpo_vecint_multi_fwd": "vecint_fwd_kernel<0>",
-            "pulpo_warp3d_l2reg_bwd": "warp3d_bwd_kernel<0, 0, 1>", "pulpo_warp3d_l2reg_fwd": "warp3d_fwd_kernel<0, 0, 1>",
-            "pulpo_ncc_fwd": "ncc_tma_kernel<9, 1>", "pulpo_ncc_bwd": "ncc_tma_kernel<9, 0>"}
-    try:
-        import glob
-        for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
-            tj = json.load(open(path))
-            if kmap.get(dname) in tj:
-                traffic, traffic_src = tj[kmap[dname]]["dram_bytes_per_launch"], os.path.relpath(path, ROOT)
-    except Exception:
-        pass
-    roofline = {"kernel": dname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "bytes_per_launch": dbytes, "us_per_launch": d_ms * 1e3, "launches_timed": dg["n"],
-                "share_of_step": dg["ms"] / sum(v["ms"] for v in agg.values()),
-                "note": "launch shape with the largest share of the step; algorithmic bytes (SURVEY.md 8d) / mean CUDA-event duration"}
+    breakdown, roofline, step_algo_bytes = kernel_breakdown(prof_step, max(2, min(args.steps, 5)), peak, peak_src)
+    # SURVEY.md 8d totals where it states them (they count the regulariser's own read of the field, which the fused
+    # warp kernels do not pay again); otherwise the sum of the per-call algorithmic bytes of one step
+    algo_bpv = SURVEY_BYTES_PER_VOXEL.get(args.workload, step_algo_bytes / float(B * nvox))
 
     if rank == 0:
         cb = None
@@ -530,7 +579,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "pairs_per_gpu": B, "voxels_per_pair": nvox,
                        "levels": "%d total / %d latent, level_res, 7 integration steps" % (total, latent),
-                       "launch": launch_mode, "engine": args.engine, "parallelism": "pairs sharded over %d GPU(s), no data-path collective" % world,
+                       "launch": launch_mode, "engine": args.engine,
+                       "parallelism": "pairs sharded over %d GPU(s), no data-path collective; loss scalars all-reduced once per timed region%s"
+                                      % (world, "; 58.7 MB gradient stand-in all-reduced every step (overlapped)" if gradbuf is not None else ""),
                        "l2": "per-step working set ~1.5 GB >> 126 MB L2; no explicit flush",
                        "velocity_fields": "smooth N(0,1), max |v| = %g voxels per level, sigma = %s" % (args.field_max_abs,
                            "%g voxels of each level's grid" % args.field_sigma_vox if args.field_sigma_vox is not None
@@ -542,9 +593,9 @@ def run_ours(args):
             "gpu_launches_per_step": launches_per_step,
             "clocks": clk,
             "roofline": roofline,
-            "path_roofline": {"algo_bytes_per_voxel": ALGO_BYTES_PER_VOXEL,
-                              "achieved": value / world * ALGO_BYTES_PER_VOXEL, "peak": peak, "unit": "GB/s",
-                              "frac": value / world * ALGO_BYTES_PER_VOXEL / peak, "peak_source": peak_src},
+            "path_roofline": {"algo_bytes_per_voxel": algo_bpv,
+                              "achieved": value / world * algo_bpv, "peak": peak, "unit": "GB/s",
+                              "frac": value / world * algo_bpv / peak, "peak_source": peak_src},
             "kernels": breakdown,
         }
         if cb is not None:
@@ -558,6 +609,259 @@ def run_ours(args):
             except Exception as e:  # pragma: no cover
                 line["torch_cuda_baseline"] = {"value": None, "what": "failed: %r" % (e,)}
         _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+
+# ------------------------------------------------------------------------------------------ shared rank plumbing
+def _rank_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- pulpo_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from pulpo_b200 import _lib
+    _lib.lib()   # fail loudly if the CUDA library is missing
+    return torch, dist, world, rank, local, dev
+
+
+def _timed(torch, dist, world, dev, local, rank, warmup, steps, fn, after=None):
+    """W warm-up calls, then exactly K calls of ``fn`` between CUDA events, barrier + synchronize on both sides,
+    max over ranks; clocks sampled during the region on rank 0."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    clocks = ClockSampler(local if rank == 0 else None)
+    clocks.start()
+    for _ in range(warmup):
+        fn()
+    if after:
+        after()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.mark_begin()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    if after:
+        after()
+    e1.record()
+    barrier()
+    clocks.mark_end()
+    if clocks.count_inside() < 3:
+        t_stop = time.perf_counter() + 0.25
+        while time.perf_counter() < t_stop:
+            fn()
+            torch.cuda.synchronize()
+        clocks.mark_end()
+        clocks.window = "timed region + 0.25 s continuation at the same load (untimed)"
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, clk
+
+
+# ------------------------------------------------------------------------------------------ config 4 (i): stand-alone VecInt
+def run_vecint_fullres(args):
+    """BASELINE.json configs[3]: 7-step scaling and squaring at full 160x192x224 resolution -- stand-alone
+    VecInt((160,192,224), 7) forward + backward through the C ABI (pulpo_vecint_fwd / pulpo_vecint_bwd), one field per
+    GPU.  Algorithmic bytes: 7 * 24 B (fwd) + 7 * 36 B (bwd) = 420 B per voxel."""
+    import ctypes
+    torch, dist, world, rank, local, dev = _rank_setup()
+    from pulpo_b200 import _lib, synthetic as syn
+    from pulpo_b200.roofline import measured_peaks
+    lib = _lib.lib()
+    size = WORKLOADS[args.workload][0]
+    nvox, B, nsteps = size[0] * size[1] * size[2], args.batch, 7
+    vp = ctypes.c_void_p
+    vec_h = syn.make_field(size, 100 + rank, batch=B, max_abs=args.field_max_abs).pin_memory()
+    gout_h = syn.make_field(size, 200 + rank, batch=B, max_abs=1.0).pin_memory()
+    vec, gout = vec_h.to(dev), gout_h.to(dev)
+    out, gvec = torch.empty_like(vec), torch.empty_like(vec)
+    ws = torch.empty(lib.pulpo_vecint_ws_bytes(nsteps, 1, B, *size) // 4, device=dev)
+    scr = torch.empty(lib.pulpo_vecint_bwd_scratch_bytes(B, *size) // 4, device=dev)
+
+    def compute():
+        st = vp(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.pulpo_vecint_fwd(vp(vec.data_ptr()), vp(out.data_ptr()), vp(ws.data_ptr()), ws.numel() * 4, nsteps, 1, B,
+                                        *size, 0, st), "vecint_fwd")
+        _lib.check(lib.pulpo_vecint_bwd(vp(gout.data_ptr()), vp(ws.data_ptr()), vp(gvec.data_ptr()), vp(scr.data_ptr()),
+                                        scr.numel() * 4, nsteps, B, *size, 0, st), "vecint_bwd")
+    for _ in range(3):
+        compute()
+    torch.cuda.synchronize()
+    graph, launch_mode = None, "eager"
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            compute()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            compute()
+        launch_mode = "cuda_graph"
+    step = graph.replay if graph is not None else compute
+    ms_total, clk = _timed(torch, dist, world, dev, local, rank, args.warmup, args.steps, step)
+    ms_step = ms_total / args.steps
+    value = world * B * nvox / (ms_step * 1e-3) / 1e9
+    # e2e: pinned host fields in, a 4-byte checksum of the gradient out, every step
+    chk_h = torch.zeros(1).pin_memory()
+
+    def e2e_step():
+        vec.copy_(vec_h, non_blocking=True)
+        gout.copy_(gout_h, non_blocking=True)
+        step()
+        chk_h.copy_(gvec.view(-1)[:1], non_blocking=True)       # D2H read of (one element of) the step's result
+        torch.cuda.current_stream().synchronize()
+    e2e_steps = max(4, min(args.steps, 10))
+    ms_e2e, _ = _timed(torch, dist, world, dev, local, rank, 2, e2e_steps, e2e_step)
+    peak, peak_src = measured_peaks(ROOT)
+    breakdown, roofline, step_bytes = kernel_breakdown(compute, max(2, min(args.steps, 5)), peak, peak_src)
+    if rank == 0:
+        bpv = step_bytes / float(B * nvox)
+        _emit({"metric": "scaling-and-squaring fwd+bwd throughput (7 steps, full resolution)", "value": value, "unit": UNIT,
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": args.workload, "fields_per_gpu": B, "voxels_per_field": nvox, "nsteps": nsteps,
+                          "launch": launch_mode, "l2": "7 saved states x 110 MB + 3 gradient states >> 126 MB L2; no explicit flush",
+                          "velocity_field": "smooth N(0,1), max |v| = %g voxels" % args.field_max_abs},
+               "e2e": {"value": world * B * nvox / (ms_e2e / e2e_steps * 1e-3) / 1e9, "unit": UNIT,
+                       "h2d_bytes_per_step": 2 * B * 3 * nvox * 4, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / e2e_steps,
+                       "steps": e2e_steps, "api": "pulpo_vecint_fwd / pulpo_vecint_bwd (C ABI) with pinned host vec / grad_output"},
+               "gpu_launches": 2 * args.steps * (B if B > 1 else 1), "gpu_launches_per_step": 2 * (B if B > 1 else 1), "clocks": clk,
+               "roofline": roofline,
+               "path_roofline": {"algo_bytes_per_voxel": bpv, "achieved": value / world * bpv, "peak": peak, "unit": "GB/s",
+                                 "frac": value / world * bpv / peak, "peak_source": peak_src},
+               "kernels": breakdown})
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ config 3: MC uncertainty
+def run_mc128(args):
+    """BASELINE.json configs[2]: uncertainty inference -- N = 128 MC deformation samples of one OASIS-shaped pair,
+    dealt round-robin to the ranks (16 per GPU on 8), per-voxel statistics streamed on every rank (Welford moments of
+    moved / final / individual fields of every level + squared errors of the level-0 moved image), partial states
+    reduced to rank 0 over a binomial tree (NCCL send/recv + Chan merge) and the variance map, MSE map and
+    NCC(var, mse) of Evaluate.uncertainty (evaluate.py:1534-1545) formed there -- all inside the timed region.
+    A "step" = the whole N-sample job for one pair.  Sample i draws its noise from Philox seed seed0 + i on whatever
+    rank runs it, so any rank count sees the same 128 samples.  Reference loop: evaluate.py:205-251."""
+    torch, dist, world, rank, local, dev = _rank_setup()
+    from pulpo_b200 import _lib, mc, synthetic as syn
+    from pulpo_b200.plan import HotPathPlan
+    from pulpo_b200.roofline import measured_peaks
+    size, total, latent = WORKLOADS[args.workload]
+    nvox, N = size[0] * size[1] * size[2], args.samples
+    x_h, y_h, d_h, m_h, s_h = syn.make_hot_path_inputs(size, total, latent, seed=0, max_abs=args.field_max_abs)   # same pair on every rank
+    x, y = x_h.to(dev), y_h.to(dev)
+    mu = {l: d_h[l].to(dev) for l in range(latent)}              # posterior mean of the velocity field (stands for the conv output)
+    sg = {l: (0.3 * s_h[l]).to(dev) for l in range(latent)}
+    plan = HotPathPlan(size, total, latent, batch=1, device=dev, with_reg=False)
+    z = {l: torch.empty_like(mu[l]) for l in range(latent)}      # static sample buffers the graph reads
+    for _ in range(2):
+        plan.run_forward(x, z)
+    torch.cuda.synchronize()
+    tracked = ["moved%d" % l for l in range(latent)] + ["final%d" % l for l in range(latent)] + ["indiv%d" % l for l in range(latent)]
+    bufs = {}
+    for l in range(latent):
+        bufs["moved%d" % l], bufs["final%d" % l], bufs["indiv%d" % l] = plan.moved[l][0], plan.final[l][0], z[l][0]
+    stats = mc.StreamingStats(bufs, targets={"moved0": y[0]})
+
+    def one_sample():            # everything of a sample but the noise: forward pass + all statistics, one CUDA graph
+        plan.run_forward(x, z)
+        stats.update()
+    graph, launch_mode = None, "eager"
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            one_sample()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            one_sample()
+        launch_mode = "cuda_graph per sample (forward + statistics)"
+    launches_fwd = plan.launches + 2
+    ids = mc.shard_samples(N, rank, world)
+    result = {}
+
+    def job():
+        stats.reset()
+        for i in ids:
+            gen = mc.sample_generator(args.seed0, i, dev)
+            for l in range(latent):    # gauss_sampler (src/network_blocks.py:7-8), z = mu + sigma * eps, one kernel per level
+                torch.normal(mu[l], sg[l], generator=gen, out=z[l])
+            graph.replay() if graph is not None else one_sample()
+            stats.count += 1
+        states = mc.merge_across_ranks(stats.states(), dst=0, device=dev)
+        if rank == 0:
+            m = mc.uncertainty_metrics(states["moved0"], states["moved0:sqerr"])
+            result.update(var=m["var"], mse=m["mse"], ncc=m["ncc"], var_mean=m["var_mean"],
+                          std={k: states[k].std_channel_mean() for k in tracked})
+    ms_total, clk = _timed(torch, dist, world, dev, local, rank, max(1, min(args.warmup, 2)), args.steps, job)
+    ms_step = ms_total / args.steps
+    value = N * nvox / (ms_step * 1e-3) / 1e9
+    # e2e: the pair comes from pinned host memory and the variance map goes back to the host, every job
+    xp, yp = x_h.pin_memory(), y_h.pin_memory()
+    var_host = torch.empty(size, dtype=torch.float32).pin_memory()
+
+    def e2e_job():
+        x.copy_(xp, non_blocking=True)
+        y.copy_(yp, non_blocking=True)
+        job()
+        if rank == 0:
+            var_host.copy_(result["var"].reshape(size), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e, _ = _timed(torch, dist, world, dev, local, rank, 1, e2e_steps, e2e_job)
+    peak, peak_src = measured_peaks(ROOT)
+    state = {"m": None}
+
+    def prof_one():      # one sample + its moment updates, eager, single stream
+        g = mc.sample_generator(args.seed0, 0, dev)
+        for l in range(latent):
+            z[l].normal_(generator=g)
+            z[l].mul_(sg[l]).add_(mu[l])
+        plan1.run_forward(x, z)
+        if state["m"] is None:
+            state["m"] = {k: mc.MCMoments(v.shape, dev) for k, v in (("moved0", plan1.moved[0][0]), ("final0", plan1.final[0][0]))}
+        state["m"]["moved0"].update(plan1.moved[0][0])
+        state["m"]["final0"].update(plan1.final[0][0])
+    plan1 = HotPathPlan(size, total, latent, batch=1, device=dev, with_reg=False, multi_stream=False)
+    prof_one()
+    breakdown, roofline, _ = kernel_breakdown(prof_one, 3, peak, peak_src)
+    if rank == 0:
+        per_sample_launches = launches_fwd
+        _emit({"metric": "MC uncertainty inference throughput (128 deformation samples per pair, variance map on rank 0)",
+               "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)),
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "samples_per_s": N / (ms_step * 1e-3),
+               "config": {"workload": args.workload, "samples": N, "samples_per_gpu": len(ids), "voxels_per_sample": nvox,
+                          "levels": "%d total / %d latent, level_res, 7 integration steps" % (total, latent), "launch": launch_mode,
+                          "tracked_maps": tracked + ["moved0:sqerr"],
+                          "parallelism": "samples dealt round-robin to %d GPU(s); binomial-tree reduce of (count, mean, M2) to rank 0 "
+                                         "(NCCL send/recv), reduce(SUM) of the squared errors" % world,
+                          "l2": "per-sample working set ~0.9 GB >> 126 MB L2; no explicit flush"},
+               "e2e": {"value": N * nvox / (ms_e2e / e2e_steps * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": 2 * nvox * 4,
+                       "d2h_bytes_per_step": nvox * 4, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                       "api": "pulpo_b200.mc.mc_uncertainty + uncertainty_metrics (pinned host pair in, variance map out)"},
+               "gpu_launches": per_sample_launches * len(ids) * args.steps, "gpu_launches_per_step": per_sample_launches * len(ids),
+               "clocks": clk, "roofline": roofline, "kernels": breakdown,
+               "uncertainty": {"ncc_var_mse": float(result["ncc"]), "var_mean": float(result["var_mean"])}})
     if world > 1:
         dist.destroy_process_group()
 
@@ -604,12 +908,20 @@ def main():
                          "coarse-to-fine sum then reaches ~45 level-0 voxels)")
     ap.add_argument("--ref-budget-s", type=float, default=600.0,
                     help="--impl reference: wall-clock budget; passes of the SAME workload are dropped (never the volume shrunk) to fit")
+    ap.add_argument("--grad-allreduce", type=int, default=0,
+                    help="N > 1: also all-reduce a 58.7 MB stand-in for the conv gradients every step, overlapped with the hot path (config 5)")
+    ap.add_argument("--seed0", type=int, default=0, help="mc128: Philox seed of sample 0 (sample i uses seed0 + i)")
+    ap.add_argument("--samples", type=int, default=128, help="mc128: MC deformation samples per pair (dealt to the ranks)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "vecint_fullres":
+        run_vecint_fullres(args)
+    elif args.workload == "mc128":
+        run_mc128(args)
     else:
         run_ours(args)
 

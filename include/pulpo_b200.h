@@ -276,6 +276,21 @@ int pulpo_global_ncc(const float *a, const float *v, float scale_a, float scale_
 int pulpo_loss_total(const float *losses, int rows, int cols, float *total, float *running,
                      int accumulate, pulpo_stream_t stream);
 
+/* The same statistics for ALL tracked maps of one MC sample in one launch that can sit in a CUDA graph: the number
+ * of samples seen so far lives in device memory (*count_dev; this sample is number *count_dev + 1) and is bumped by
+ * pulpo_counter_add afterwards, so one captured launch serves every sample of the loop at evaluate.py:227-235.
+ * target / sqerr_acc nullable (both or neither): sqerr_acc (+)= (x - target)^2.  `maps` is a HOST array, <= 32. */
+typedef struct pulpo_moments_map {
+    const float *x;
+    float *mean, *m2;
+    const float *target;
+    float *sqerr_acc;
+    long long n;
+} pulpo_moments_map;
+int pulpo_moments_update_multi(const pulpo_moments_map *maps, int nmaps, const int *count_dev,
+                               pulpo_stream_t stream);
+int pulpo_counter_add(int *counter_dev, int value, int reset, pulpo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -465,6 +465,50 @@ __global__ void loss_total_kernel(const float *__restrict__ losses, int rows, in
     if (total) *total = t;
 }
 
+// All tracked maps of one MC sample in ONE launch, graph-capturable: the sample count lives in device memory (the
+// kernel uses *count_dev + 1; pulpo_counter_add bumps it afterwards), so the same captured launch serves every
+// sample.  Per map: Welford update of (mean, M2) and, where a target is given, the squared-error sum.
+constexpr int MM_MAXMAPS = 32;
+struct MomentsMaps {
+    int n;
+    pulpo_moments_map m[MM_MAXMAPS];
+};
+__global__ void __launch_bounds__(256)
+moments_update_multi_kernel(const MomentsMaps maps, const int *__restrict__ count_dev)
+{
+    const int count = *count_dev + 1;
+    const float inv_count = 1.0f / (float)count;
+    const bool first = count == 1;
+    for (int k = 0; k < maps.n; ++k) {
+        const pulpo_moments_map &mp = maps.m[k];
+        const float *__restrict__ x = mp.x;
+        float *__restrict__ mean = mp.mean, *__restrict__ m2 = mp.m2, *__restrict__ acc = mp.sqerr_acc;
+        const float *__restrict__ y = mp.target;
+        const i64 n = mp.n;
+        for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+            const float v = x[i];
+            if (first) {
+                mean[i] = v;
+                m2[i] = 0.0f;
+            } else {
+                const float mu = mean[i];
+                const float d = v - mu;
+                const float mu2 = mu + d * inv_count;
+                mean[i] = mu2;
+                m2[i] += d * (v - mu2);
+            }
+            if (acc) {
+                const float e = v - y[i];
+                acc[i] = first ? e * e : acc[i] + e * e;
+            }
+        }
+    }
+}
+__global__ void counter_add_kernel(int *ctr, int v, int reset)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) *ctr = reset ? v : *ctr + v;
+}
+
 }  // namespace pulpo
 
 using namespace pulpo;
@@ -650,6 +694,30 @@ extern "C" int pulpo_loss_total(const float *losses, int rows, int cols, float *
     PULPO_REQUIRE(losses && (total || running), PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(rows > 0 && cols > 0 && rows * cols <= 4096, PULPO_ERR_INVALID_SHAPE);
     loss_total_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(losses, rows, cols, total, running, accumulate);
+    return launch_status();
+}
+
+extern "C" int pulpo_moments_update_multi(const pulpo_moments_map *maps, int nmaps, const int *count_dev, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(maps && count_dev, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(nmaps >= 1 && nmaps <= MM_MAXMAPS, PULPO_ERR_INVALID_SHAPE);
+    MomentsMaps mm;
+    mm.n = nmaps;
+    long long biggest = 0;
+    for (int k = 0; k < nmaps; ++k) {
+        PULPO_REQUIRE(maps[k].x && maps[k].mean && maps[k].m2 && (!maps[k].sqerr_acc || maps[k].target), PULPO_ERR_NULL_POINTER);
+        PULPO_REQUIRE(maps[k].n > 0, PULPO_ERR_INVALID_SHAPE);
+        mm.m[k] = maps[k];
+        if (maps[k].n > biggest) biggest = maps[k].n;
+    }
+    moments_update_multi_kernel<<<grid_for(biggest, 256, 8), 256, 0, (cudaStream_t)stream>>>(mm, count_dev);
+    return launch_status();
+}
+
+extern "C" int pulpo_counter_add(int *counter_dev, int value, int reset, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(counter_dev, PULPO_ERR_NULL_POINTER);
+    counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter_dev, value, reset);
     return launch_status();
 }
 

@@ -76,12 +76,18 @@ struct VLevel {
     float4 *ws;         // fwd: states ; bwd: saved states
     float4 *scr;        // bwd: two (own, scatter) pairs
     unsigned int item0; // first work item of this level in the joint list
+    // dataflow synchronisation (see "Step synchronisation" below): tail of the caller's workspace
+    unsigned int *rowdone;   // [B * nzrun * npy] steps-completed counters, one per row of x-adjacent work items
+    float *ctamax;           // [gridDim.x] per-CTA max |v_0| of this level
+    int l1safe;              // every 128-byte line of a state belongs to exactly one work item (D2 % 8 == 0, aligned base)
     VGeom g;
 };
 struct VMulti {
     int n;
     unsigned int items;   // total
     int combine;          // fold the Laplacian-pyramid combination into the launch (see below)
+    int dataflow;         // steps synchronised item to item through rowdone counters instead of grid barriers
+    unsigned int *err;    // dataflow: sticky "a wait timed out" flag
     const float *indiv[VI_MAXL];   // combine: the levels' individual fields
     VLevel l[VI_MAXL];
 };
@@ -162,6 +168,17 @@ static int make_vgeom(VGeom &g, int B, int D0, int D1, int D2)
     g.npy = (D1 + VI_PY - 1) / VI_PY;
     g.a0 = make_axis(D0); g.a1 = make_axis(D1); g.a2 = make_axis(D2);
     return PULPO_OK;
+}
+
+// grid.sync() behind a condition the compiler cannot fold (`live` is a kernel parameter, always > 0).  Measured on
+// B200 (CUDA 12.9): with the bare call in the step loop a step cost ~5 us on top of its work, with the call inside a
+// conditional ~1.4 us (forward 100 -> 73 us, backward 211 -> 176 us at 80x96x112; no-barrier bound 64 / 160 us).  The
+// SASS differs only by a BSSY / BSYNC convergence-barrier pair that the conditional wraps around the barrier sequence
+// (thread 0 of warp 0 arrives and polls alone): the warps leave the barrier reconverged.
+__device__ __forceinline__ void grid_barrier(cg::grid_group &grid, int live)
+{
+    if (live > 0) grid.sync();
+    __syncwarp();
 }
 
 struct Item {
@@ -320,6 +337,102 @@ __device__ __forceinline__ VFoot make_vfoot(float zf, float yf, float xf, const 
     return f;
 }
 
+// ---- Step synchronisation.  Step k+1 of a work item reads, besides its own voxels, only voxels within the
+// reach of the step-k field: |p - x| <= |v_k| + 0.5 per axis (sample_pos: p = (x + v) S / (S - 1) - 0.5, clamped
+// into the volume), and |v_k| <= 2^k max|v_0| because each step adds an interpolated -- convex -- value of the
+// field to itself.  So instead of a grid-wide barrier per step (7 + 7 of them; the barriers with their cold-L1
+// restart and tail were ~35 % of the forward and ~22 % of the backward, measured with the barriers removed),
+// an item waits only for the rows of items within that reach: every item bumps its row's counter when it
+// finishes a step (red.release.gpu: MEMBAR + REDG, no L1 invalidation) and polls its neighbours' rows with relaxed
+// loads.  No acquire fence (CCTL.IVALL would empty the SM's L1 on every wait): a state is written once (save_steps)
+// and, where `l1safe`, every 128-byte line of it belongs to one work item, so nobody can have cached a line of it
+// before its owner signalled; levels with ragged rows take the fence.  All CTAs are co-resident (cooperative
+// launch) and step k+1 depends on step k only, so the waits cannot deadlock; they give up after ~0.5 s anyway
+// (sticky error flag; the results are then wrong, the GPU is not hung).
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned int *p, unsigned int v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+struct ItemBox {   // patch-row coordinates of a work item
+    int b, zr, py, z0, z1;
+};
+__device__ __forceinline__ ItemBox decode_box(unsigned int it, const VGeom &g)
+{
+    unsigned int r, zr, r2, px, py, b;
+    fast_divmod(it, g.dnpx, r, px);
+    fast_divmod(r, g.dnpy, r2, py);
+    fast_divmod(r2, g.dnz, b, zr);
+    ItemBox x;
+    x.b = (int)b; x.zr = (int)zr; x.py = (int)py;
+    x.z0 = (int)zr * g.zrun; x.z1 = min(g.D0, x.z0 + g.zrun);
+    return x;
+}
+
+// max |v_0| of a level from the per-CTA partials (NaN / Inf propagate: the reach then covers the volume)
+__device__ __forceinline__ float level_max(const float *ctamax, int nctas, int lane)
+{
+    float mx = 0.0f;
+    for (int i = lane; i < nctas; i += 32) {
+        const float v = __ldcg(ctamax + i);
+        mx = (v > mx || v != v) ? v : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float v = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = (v > mx || v != v) ? v : mx;
+    }
+    return mx;
+}
+
+// voxels a step can reach when max |v_0| = m0 and the field has doubled `k` times (margins: fp32 rounding of the
+// interpolation weights and of the sample position)
+__device__ __forceinline__ int step_reach(float m0, int k, int cap)
+{
+    const float bound = m0 * (float)(1u << k) * 1.0005f + 0.501f;
+    if (!(bound < (float)cap)) return cap;     // also NaN
+    return (int)bound + 1;
+}
+
+// wait until every row of work items within `reach` voxels of the item has completed `need_steps` steps
+__device__ __forceinline__ void wait_rows(const VLevel &L, const ItemBox &x, int reach, unsigned int need_steps, int lane,
+                                          unsigned int *err)
+{
+    const VGeom &g = L.g;
+    const int zlo = max(x.z0 - reach, 0) / g.zrun, zhi = min(x.z1 - 1 + reach, g.D0 - 1) / g.zrun;
+    const int ylo = max(x.py * VI_PY - reach, 0) / VI_PY, yhi = min(x.py * VI_PY + VI_PY - 1 + reach, g.D1 - 1) / VI_PY;
+    const int ny = yhi - ylo + 1, n = (zhi - zlo + 1) * ny;
+    const unsigned int need = need_steps * (unsigned int)g.npx;
+    const unsigned int *base = L.rowdone + (i64)x.b * g.nzrun * g.npy;
+    for (int i = lane; i < n; i += 32) {
+        const int zr = zlo + i / ny, py = ylo + i % ny;
+        const unsigned int *p = base + zr * g.npy + py;
+        int spins = 0;
+        while (ld_relaxed_u32(p) < need) {
+            __nanosleep(100);
+            if (++spins > (1 << 16) && (ld_relaxed_u32(err) != 0u || spins > (1 << 22))) {
+                atomicExch(err, 1u);
+                break;
+            }
+        }
+    }
+    __syncwarp();
+    if (!L.l1safe) fence_acq_rel_gpu();
+}
+
+__device__ __forceinline__ void signal_row(const VLevel &L, const ItemBox &x, int lane)
+{
+    __syncwarp();
+    if (lane == 0) red_release_add(L.rowdone + ((i64)x.b * L.g.nzrun + x.zr) * L.g.npy + x.py, 1u);
+}
+
 // One forward work item.  L0 = true: the item belongs to level 0 (the bulk of the work), whose geometry is then
 // addressed at constant offsets of the kernel parameter (constant-bank operands) instead of through a run-time
 // level index (one LDC per use).
@@ -386,7 +499,7 @@ vecint_fwd_kernel(const VMulti m, int nsteps, int save, float scale)
                 }
                 continue;
             }
-            grid.sync();
+            grid_barrier(grid, m.n);
             const VLevel &C = m.l[lv + 1];
             const float *lower = (lv + 1 == m.n - 1) ? m.indiv[lv + 1] : C.in;
             const int c1 = C.g.D1, c2 = C.g.D2;
@@ -409,35 +522,79 @@ vecint_fwd_kernel(const VMulti m, int nsteps, int save, float scale)
             }
         }
     } else {
+        __shared__ float vi_red[32];
         for (int lv = 0; lv < m.n; ++lv) {
             const VLevel &L = m.l[lv];
             const unsigned int N = L.g.N, S = L.g.S;
+            float mx = 0.0f;   // max |v_0| of this thread's voxels (NaN sticks)
             for (unsigned int i = tid; i < N; i += nthr) {
                 unsigned int b = i / S, v = i - b * S;
                 const float *f = L.in + (i64)b * 3 * S + v;
-                L.ws[i] = make_float4(__fmul_rn(__ldg(f), scale), __fmul_rn(__ldg(f + S), scale),
-                                      __fmul_rn(__ldg(f + 2 * S), scale), 0.0f);
+                const float4 q = make_float4(__fmul_rn(__ldg(f), scale), __fmul_rn(__ldg(f + S), scale),
+                                             __fmul_rn(__ldg(f + 2 * S), scale), 0.0f);
+                L.ws[i] = q;
+                const float a = fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z));
+                mx = (q.x != q.x || q.y != q.y || q.z != q.z) ? __int_as_float(0x7fc00000) : ((a > mx) ? a : mx);
+            }
+            if (m.dataflow) {
+                // per-CTA partial of the level's max |v_0| and zeroed row counters, published by the grid barrier below
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float v = __shfl_xor_sync(0xffffffffu, mx, o);
+                    mx = (v > mx || v != v) ? v : mx;
+                }
+                __syncthreads();
+                if (lane == 0) vi_red[threadIdx.x >> 5] = mx;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    float t = 0.0f;
+                    for (unsigned int w = 0; w < (blockDim.x >> 5); ++w) {
+                        const float v = vi_red[w];
+                        t = (v > t || v != v) ? v : t;
+                    }
+                    L.ctamax[blockIdx.x] = t;
+                }
+                const unsigned int rows = (unsigned int)(L.g.B * L.g.nzrun * L.g.npy);
+                for (unsigned int i = tid; i < rows; i += nthr) L.rowdone[i] = 0u;
             }
         }
+        if (m.dataflow && tid == 0) *m.err = 0u;
     }
+    const bool flow = m.dataflow != 0;
+    int cached_lv = -1;
+    float cached_max = 0.0f;
     for (int k = 0; k < nsteps; ++k) {
 #ifdef PULPO_VI_NOSYNC   // timing experiment only (wrong results): upper bound of what removing the step barriers buys
         if (k == 0)
 #endif
-        grid.sync();
+        if (k == 0 || !flow) grid_barrier(grid, m.n);
         const bool last = (k == nsteps - 1);
         for (unsigned int it = warp; it < m.items; it += nwarps) {
             int lv = 0;
 #pragma unroll
             for (int j = 1; j < VI_MAXL; ++j) lv += (j < m.n && it >= m.l[j].item0) ? 1 : 0;
+            ItemBox box;
+            if (flow) {
+                const VLevel &L = m.l[lv];
+                box = decode_box(it - L.item0, L.g);
+                if (k > 0) {
+                    if (lv != cached_lv) {
+                        cached_max = level_max(L.ctamax, (int)gridDim.x, lane);
+                        cached_lv = lv;
+                    }
+                    const int cap = max(L.g.D0, max(L.g.D1, L.g.D2));
+                    wait_rows(L, box, step_reach(cached_max, k, cap), (unsigned int)k, lane, m.err);
+                }
+            }
             if (lv == 0)
                 vi_fwd_item<MODE, true>(m, 0, it, lane, k, save, last);
             else
                 vi_fwd_item<MODE, false>(m, lv, it, lane, k, save, last);
+            if (flow && !last) signal_row(m.l[lv], box, lane);
         }
     }
     if (nsteps == 0) {
-        grid.sync();
+        grid_barrier(grid, m.n);
         for (int lv = 0; lv < m.n; ++lv) {
             const VLevel &L = m.l[lv];
             const unsigned int N = L.g.N, S = L.g.S;
@@ -510,6 +667,7 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
 #else
         float4 *Pa = L.scr, *Ya = L.scr + N, *Yb = L.scr + 3 * (i64)N;
 #endif
+        float mx = 0.0f;   // dataflow: max |v_0| over the saved first state (bounds every step's reach)
         for (unsigned int i = tid; i < N; i += nthr) {
             unsigned int b = i / S, v = i - b * S;
             const float *f = L.in + (i64)b * 3 * S + v;
@@ -518,14 +676,44 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
 #ifndef PULPO_VI_BWD_XYZ
             Yb[i] = zero4;
 #endif
+            if (m.dataflow && nsteps > 0) {
+                const float4 q = __ldg(L.ws + i);
+                const float a = fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fabsf(q.z));
+                mx = (q.x != q.x || q.y != q.y || q.z != q.z) ? __int_as_float(0x7fc00000) : ((a > mx) ? a : mx);
+            }
+        }
+        if (m.dataflow) {
+            __shared__ float vi_red[32];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float v = __shfl_xor_sync(0xffffffffu, mx, o);
+                mx = (v > mx || v != v) ? v : mx;
+            }
+            __syncthreads();
+            if (lane == 0) vi_red[threadIdx.x >> 5] = mx;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float t = 0.0f;
+                for (unsigned int w = 0; w < (blockDim.x >> 5); ++w) {
+                    const float v = vi_red[w];
+                    t = (v > t || v != v) ? v : t;
+                }
+                L.ctamax[blockIdx.x] = t;
+            }
+            const unsigned int rows = (unsigned int)(L.g.B * L.g.nzrun * L.g.npy);
+            for (unsigned int i = tid; i < rows; i += nthr) L.rowdone[i] = 0u;
         }
     }
+    if (m.dataflow && tid == 0) *m.err = 0u;
+    const bool flow = m.dataflow != 0;
+    int cached_lv = -1;
+    float cached_max = 0.0f;
     int flip = 0;   // which (P, Y) pair holds the incoming gradient of the current step
     for (int k = nsteps - 1; k >= 0; --k, flip ^= 1) {
 #ifdef PULPO_VI_NOSYNC
         if (k == nsteps - 1)
 #endif
-        grid.sync();
+        if (k == nsteps - 1 || !flow) grid_barrier(grid, m.n);
 #ifdef PULPO_VI_TRACE
         if (threadIdx.x == 0 && blockIdx.x < 148 && k < 32) g_vi_trace[blockIdx.x * 64 + 2 * k] = gtime();
 #endif
@@ -538,6 +726,20 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
             const unsigned int N = g.N, S = g.S;
             const int sy = g.D2, sz = g.D1 * g.D2;
             const VStride vst = make_vstride(sy, sz);
+            ItemBox box;
+            if (flow) {
+                // this step reads the gradient state the previous backward step (forward step k+1) scattered into,
+                // within that step's reach, and scatters into / clears states whose owners must be past it too
+                box = decode_box(it - L.item0, g);
+                if (k < nsteps - 1) {
+                    if (lv != cached_lv) {
+                        cached_max = level_max(L.ctamax, (int)gridDim.x, lane);
+                        cached_lv = lv;
+                    }
+                    wait_rows(L, box, step_reach(cached_max, k + 1, max(g.D0, max(g.D1, g.D2))), (unsigned int)(nsteps - 1 - k), lane,
+                              m.err);
+                }
+            }
 #ifdef PULPO_VI_BWD_XYZ
             // three rotating states: X (incoming gradient), Y (accumulates own + scatter parts, zero at step start),
             // Z (being zeroed for the next step); Pa = X, Yb = Y, Ya = Z in the names below
@@ -724,13 +926,14 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
                 float4 *q = acc + carry_addr;
                 red3(q, up[0]); red3(q + 1, up[1]); red3(q + sy, up[2]); red3(q + sy + 1, up[3]);
             }
+            if (flow && k > 0) signal_row(L, box, lane);
         }
 #ifdef PULPO_VI_TRACE
         __syncthreads();
         if (threadIdx.x == 0 && blockIdx.x < 148 && k < 32) g_vi_trace[blockIdx.x * 64 + 2 * k + 1] = gtime();
 #endif
     }
-    grid.sync();
+    grid_barrier(grid, m.n);
     for (int lv = 0; lv < m.n; ++lv) {
         const VLevel &L = m.l[lv];
         const unsigned int N = L.g.N, S = L.g.S;
@@ -742,7 +945,7 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
         if (m.combine && lv > 0) {
             // adjoint of the combination: the finer level's (complete) gradient flows into this level through
             // 2 * up2^T; fine to coarse, one grid barrier per level
-            grid.sync();
+            grid_barrier(grid, m.n);
             const VLevel &F = m.l[lv - 1];
             const unsigned int Sf = F.g.S;
             const int d0 = L.g.D0, d1 = L.g.D1, d2 = L.g.D2;
@@ -775,6 +978,8 @@ vecint_bwd_kernel(const VMulti m, int nsteps, float scale)
         }
     }
 }
+
+constexpr size_t VI_TAIL_CTAS = 2048;   // per-CTA slots in a workspace tail (dataflow synchronisation)
 
 template <typename K>
 static int coop_ctas(K kernel, int threads, size_t smem = 0)
@@ -829,9 +1034,34 @@ static int launch_coop(K kernel, int threads, VMulti &m, void **args, cudaStream
     i64 grid = (padded + threads - 1) / threads;
     if (grid > ctas) grid = ctas;
     if (grid < 1) grid = 1;
+    if ((size_t)grid > VI_TAIL_CTAS) m.dataflow = 0;
     plan_items(m, (int)grid * (threads / 32));
     cudaError_t e = cudaLaunchCooperativeKernel((void *)kernel, dim3((unsigned int)grid), dim3(threads), args, smem, st);
     return e == cudaSuccess ? launch_status() : PULPO_ERR_CUDA;
+}
+
+// Tail of a level's state workspace (forward) / gradient scratch (backward) used by the dataflow synchronisation:
+// row counters (upper bound: one z run per plane), per-CTA maxima, the error flag.
+static size_t vi_tail_bytes(int B, int D0, int D1)
+{
+    const size_t rows = (size_t)B * D0 * ((D1 + VI_PY - 1) / VI_PY);
+    return 128 + ((rows * 4 + 127) / 128) * 128 + VI_TAIL_CTAS * 4 + 128;
+}
+static void vi_tail_ptrs(VLevel &L, char *tail, int B, int D0, int D1)
+{
+    tail = (char *)(((uintptr_t)tail + 127) & ~(uintptr_t)127);
+    const size_t rows = (size_t)B * D0 * ((D1 + VI_PY - 1) / VI_PY);
+    L.rowdone = (unsigned int *)tail;
+    L.ctamax = (float *)(tail + ((rows * 4 + 127) / 128) * 128);
+}
+static bool vi_dataflow_enabled()
+{
+    // Opt-in ("1"; read per call).  Measured on B200 at config 2 (scripts/vi_ab.py, profiles/r2_vecint_sync.md): the
+    // item-to-item synchronisation is correct (bit-identical forward) but SLOWER than grid barriers -- forward 107 vs
+    // 74 us, backward 188 vs 176 us at 80x96x112 -- because every item pays a MEMBAR.GPU + an L2 round trip of polling
+    // per step (~2-3 us), more than the 1.4 us a grid barrier costs once the steps are balanced.
+    const char *e = getenv("PULPO_VI_DATAFLOW");
+    return e && e[0] == '1';
 }
 
 static int fill_levels(VMulti &m, const pulpo_vecint_level *levels, int nlevels, int B, bool bwd, int nsteps, int save)
@@ -857,9 +1087,27 @@ static int fill_levels(VMulti &m, const pulpo_vecint_level *levels, int nlevels,
                           PULPO_ERR_WORKSPACE);
         }
         m.l[l].in = v.in; m.l[l].out = v.out; m.l[l].ws = (float4 *)v.ws; m.l[l].scr = (float4 *)v.scratch;
+        m.l[l].rowdone = nullptr; m.l[l].ctamax = nullptr; m.l[l].l1safe = 1;
+        const size_t state = (size_t)B * v.D0 * v.D1 * v.D2 * sizeof(float4);
+        if (bwd) {
+#ifdef PULPO_VI_BWD_XYZ
+            vi_tail_ptrs(m.l[l], (char *)v.scratch + 3 * state, B, v.D0, v.D1);   // backward: L1-cached loads touch read-only states only
+#endif
+        } else if (save && nsteps >= 1) {
+            vi_tail_ptrs(m.l[l], (char *)v.ws + (size_t)nsteps * state, B, v.D0, v.D1);
+            m.l[l].l1safe = (v.D2 % VI_PX == 0) && (((uintptr_t)v.ws) % 128 == 0) && (VI_PX * sizeof(float4) == 128);
+        }
         total += (i64)B * v.D0 * v.D1 * v.D2;
     }
     PULPO_REQUIRE(total < (1ll << 31), PULPO_ERR_INVALID_SHAPE);
+    // item-to-item step synchronisation needs every state to be written exactly once (saved steps) and room for the
+    // counters in the workspace tail; otherwise the steps are separated by grid barriers
+    m.dataflow = 0;
+    m.err = nullptr;
+    if (vi_dataflow_enabled() && nsteps >= 2 && m.l[0].rowdone && (bwd || save)) {
+        m.dataflow = 1;
+        m.err = (unsigned int *)((char *)m.l[0].ctamax + VI_TAIL_CTAS * 4);
+    }
     return PULPO_OK;
 }
 
@@ -878,13 +1126,14 @@ extern "C" size_t pulpo_vecint_ws_bytes(int nsteps, int save_steps, int B, int D
 {
     size_t state = (size_t)B * D0 * D1 * D2 * sizeof(float4);
     int n = save_steps ? (nsteps < 1 ? 1 : nsteps) : 2;
-    return state * (size_t)n;
+    // one synchronisation tail per batch item: batches of large volumes run item by item, each on its own slice
+    return state * (size_t)n + (save_steps ? (size_t)B * vi_tail_bytes(1, D0, D1) : 0);
 }
 
 extern "C" size_t pulpo_vecint_bwd_scratch_bytes(int B, int D0, int D1, int D2)
 {
 #ifdef PULPO_VI_BWD_XYZ
-    return (size_t)B * D0 * D1 * D2 * sizeof(float4) * 3;   // three rotating gradient states
+    return (size_t)B * D0 * D1 * D2 * sizeof(float4) * 3 + (size_t)B * vi_tail_bytes(1, D0, D1);   // three rotating gradient states + sync tails
 #else
     return (size_t)B * D0 * D1 * D2 * sizeof(float4) * 4;   // two (P, Y) pairs
 #endif
@@ -963,6 +1212,7 @@ static int vecint_multi_fwd_impl(const pulpo_vecint_level *levels, const float *
             m.indiv[l] = indiv[l];
         }
         m.combine = 1;
+        m.dataflow = 0;   // the in-launch combination has its own grid-wide phases
     }
     float scale = 1.0f / (float)(1u << nsteps);
     void *args[] = {&m, &nsteps, &save_steps, &scale};
@@ -1009,6 +1259,7 @@ static int vecint_multi_bwd_impl(const pulpo_vecint_level *levels, int combine, 
         rc = check_pyramid(levels, nlevels);
         if (rc != PULPO_OK) return rc;
         m.combine = 1;
+        m.dataflow = 0;
     }
     float scale = 1.0f / (float)(1u << nsteps);
     void *args[] = {&m, &nsteps, &scale};

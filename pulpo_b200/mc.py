@@ -145,6 +145,68 @@ def uncertainty_metrics(moved: MCMoments, sqerr: MCSqErr) -> Dict[str, object]:
     return {"var": std ** 2, "mse": sqerr.mse().reshape(std.shape), "ncc": r[0], "var_mean": r[1]}
 
 
+class StreamingStats:
+    """Statistics of ALL tracked maps of an MC loop, updated by ONE graph-capturable launch per sample.
+
+    ``maps``: {name: tensor} -- the STATIC buffers one sample's results land in (e.g. ``plan.moved[0][0]``);
+    ``targets``: {name: fixed image} for the maps whose squared error is streamed too.  ``update()`` enqueues
+    ``pulpo_moments_update_multi`` + ``pulpo_counter_add`` on the current stream (the sample count lives on the
+    device, so the pair can be captured in the same CUDA graph as the sample's forward pass); the host only
+    tallies how many times it ran.  ``states()`` hands the result out as ``MCMoments`` / ``MCSqErr`` objects that
+    ``merge_across_ranks`` and ``uncertainty_metrics`` take."""
+
+    def __init__(self, maps: Dict[str, torch.Tensor], targets: Optional[Dict[str, torch.Tensor]] = None):
+        import ctypes
+        from . import _lib
+        targets = targets or {}
+        self.names = list(maps.keys())
+        self.maps = {n: maps[n] for n in self.names}
+        dev = next(iter(maps.values())).device
+        self.dev = dev
+        self.mean = {n: torch.zeros_like(maps[n]) for n in self.names}
+        self.m2 = {n: torch.zeros_like(maps[n]) for n in self.names}
+        self.acc = {n: torch.zeros_like(maps[n]) for n in self.names if n in targets}
+        self.targets = {n: targets[n].contiguous() for n in self.acc}
+        self.count_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.count = 0
+        arr = (_lib.MomentsMap * len(self.names))()
+        for k, n in enumerate(self.names):
+            t = maps[n]
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                raise RuntimeError("StreamingStats: map %r must be a contiguous fp32 CUDA tensor" % n)
+            if n in self.acc and self.targets[n].numel() != t.numel():
+                raise RuntimeError("StreamingStats: target of %r has %d elements, the map %d" % (n, self.targets[n].numel(), t.numel()))
+            arr[k] = _lib.MomentsMap(t.data_ptr(), self.mean[n].data_ptr(), self.m2[n].data_ptr(),
+                                     self.targets[n].data_ptr() if n in self.acc else None,
+                                     self.acc[n].data_ptr() if n in self.acc else None, t.numel())
+        self._arr, self._vp = arr, ctypes.c_void_p
+
+    def reset(self):
+        from . import _lib
+        _lib.check(_lib.lib().pulpo_counter_add(self._vp(self.count_dev.data_ptr()), 0, 1,
+                                                self._vp(torch.cuda.current_stream(self.dev).cuda_stream)), "counter reset")
+        self.count = 0
+
+    def update(self):
+        """Enqueue the update for the sample currently in the map buffers (graph-capturable; does not touch ``count``)."""
+        from . import _lib
+        lib, st = _lib.lib(), self._vp(torch.cuda.current_stream(self.dev).cuda_stream)
+        _lib.check(lib.pulpo_moments_update_multi(self._arr, len(self.names), self._vp(self.count_dev.data_ptr()), st), "moments_update_multi")
+        _lib.check(lib.pulpo_counter_add(self._vp(self.count_dev.data_ptr()), 1, 0, st), "counter_add")
+
+    def states(self) -> Dict[str, "MCMoments | MCSqErr"]:
+        out: Dict[str, object] = {}
+        for n in self.names:
+            st = MCMoments.__new__(MCMoments)
+            st.ops, st.count, st.mean, st.m2 = _KernelOps, self.count, self.mean[n], self.m2[n]
+            out[n] = st
+            if n in self.acc:
+                sq = MCSqErr.__new__(MCSqErr)
+                sq.ops, sq.count, sq.acc = _KernelOps, self.count, self.acc[n]
+                out[n + ":sqerr"] = sq
+        return out
+
+
 def _check_same_maps(local_meta, group):
     """Every rank must hold the same maps with the same shapes; a rank that drew no sample (empty explicit
     ``sample_ids``) may hold none.  Decided on ALL ranks before any tensor collective, so a mismatch raises

@@ -1089,3 +1089,49 @@ def test_nonfinite_losses_match_torch(PF, bad):
     mr = mub.clone().requires_grad_(True)
     T.kl_diag(mr, sg, z, o).backward()
     assert np.array_equal(np.isnan(m.grad.cpu().numpy()), np.isnan(mr.grad.numpy()))
+
+
+# ----------------------------------------------------------------------------- VecInt step synchronisation
+@pytest.mark.parametrize("shape,B,amp", [((80, 96, 112), 1, 45.0), ((20, 24, 28), 2, 12.0), ((10, 12, 14), 1, 6.0),
+                                         ((16, 24, 32), 2, 200.0), ((9, 11, 13), 1, 3.0)])
+def test_vecint_dataflow_sync_equals_grid_barriers(PF, shape, B, amp, monkeypatch):
+    """The item-to-item (row counter) synchronisation of the integration steps against the grid-barrier path it
+    replaces: forward bit-identical, gradients equal up to the order of the scatter's atomic sums.  Covers the
+    level-0 size, ragged rows (no cache-line ownership -> acquire fence), batches and a field whose reach exceeds
+    the volume (every item waits for every row)."""
+    from pulpo_b200 import synthetic as syn
+    vec = syn.make_field(shape, 31, batch=B, max_abs=amp).cuda()
+    gout = syn.make_field(shape, 32, batch=B, max_abs=1.0).cuda()
+
+    def run():
+        v = vec.clone().requires_grad_(True)      # requires_grad -> saved states -> dataflow path when enabled
+        o = PF.vecint(v, 7)
+        o.backward(gout)
+        torch.cuda.synchronize()
+        return o.detach(), v.grad.detach()
+    monkeypatch.setenv("PULPO_VI_DATAFLOW", "0")
+    o_bar, g_bar = run()
+    monkeypatch.setenv("PULPO_VI_DATAFLOW", "1")
+    for _ in range(3):                            # several launches: the counters are re-armed by every launch
+        o_flow, g_flow = run()
+        assert torch.equal(o_flow, o_bar), "forward differs: max-abs %.3e" % float((o_flow - o_bar).abs().max())
+        assert_grad_close(g_flow.cpu().numpy(), g_bar.cpu().numpy(), "vecint grad (dataflow vs barriers)", rtol=1e-5)
+    with torch.no_grad():
+        assert torch.equal(PF.vecint(vec, 7), o_bar)          # forward-only (two ping-pong states, barriers) agrees too
+
+
+def test_vecint_dataflow_multi_level_plan_equals_barriers(PF, monkeypatch):
+    """All pyramid levels in one cooperative launch (HotPathPlan) with dataflow vs grid barriers."""
+    from pulpo_b200 import synthetic as syn
+    size, total, latent = [64, 96, 112], 4, 3
+    x, y, dfs, mus, sgs = syn.make_hot_path_inputs(size, total, latent, seed=5)
+    dev_in = (x.cuda(), y.cuda(), {l: dfs[l].cuda() for l in dfs}, {l: mus[l].cuda() for l in dfs},
+              {l: sgs[l].cuda() for l in dfs})
+    monkeypatch.setenv("PULPO_VI_DATAFLOW", "0")
+    ref = _run_plan(dev_in, total, latent, size, 1, True, False)
+    monkeypatch.setenv("PULPO_VI_DATAFLOW", "1")
+    new = _run_plan(dev_in, total, latent, size, 1, True, True)
+    assert_loss_close(new.total.item(), ref.total.item(), "total")
+    for l in range(latent):
+        assert torch.equal(new.integ[l], ref.integ[l]), "integrated field %d differs" % l
+        assert_grad_close(new.gdf[l].cpu().numpy(), ref.gdf[l].cpu().numpy(), "gdf %d" % l, rtol=1e-5)
