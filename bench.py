@@ -799,10 +799,12 @@ def run_mc128(args):
     ids = mc.shard_samples(N, rank, world)
     result = {}
 
+    gen = torch.Generator(device=dev)     # one Philox generator, re-seeded per sample (same streams as mc.sample_generator)
+
     def job():
         stats.reset()
         for i in ids:
-            gen = mc.sample_generator(args.seed0, i, dev)
+            gen.manual_seed(int(args.seed0) + int(i))
             for l in range(latent):    # gauss_sampler (src/network_blocks.py:7-8), z = mu + sigma * eps, one kernel per level
                 torch.normal(mu[l], sg[l], generator=gen, out=z[l])
             graph.replay() if graph is not None else one_sample()

@@ -115,3 +115,4 @@ def test_reference_training_step_with_pulpo_b200_modules(df_resolution):
               % (df_resolution, rel, worst, cos, len(g_ref)))
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic = old
+        torch.autograd.set_detect_anomaly(False)     # PULPo.__init__ (src/models.py:50) switched it on process-wide
