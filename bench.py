@@ -770,17 +770,24 @@ def run_mc128(args):
     mu = {l: d_h[l].to(dev) for l in range(latent)}              # posterior mean of the velocity field (stands for the conv output)
     sg = {l: (0.3 * s_h[l]).to(dev) for l in range(latent)}
     plan = HotPathPlan(size, total, latent, batch=1, device=dev, with_reg=False)
-    z = {l: torch.empty_like(mu[l]) for l in range(latent)}      # static sample buffers the graph reads
+    from pulpo_b200 import functional as PF
+    ids = mc.shard_samples(N, rank, world)       # round-robin: sample ids rank, rank + world, ...
+    tracked = ["moved%d" % l for l in range(latent)] + ["final%d" % l for l in range(latent)] + ["indiv%d" % l for l in range(latent)]
+    count_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    sampler = mc.PhiloxSampler(mu, sg, seed=args.seed0, first_id=rank, id_stride=world, count_dev=count_dev)
+    z = sampler.z                                # static sample buffers the graph reads
     for _ in range(2):
         plan.run_forward(x, z)
     torch.cuda.synchronize()
-    tracked = ["moved%d" % l for l in range(latent)] + ["final%d" % l for l in range(latent)] + ["indiv%d" % l for l in range(latent)]
     bufs = {}
     for l in range(latent):
         bufs["moved%d" % l], bufs["final%d" % l], bufs["indiv%d" % l] = plan.moved[l][0], plan.final[l][0], z[l][0]
     stats = mc.StreamingStats(bufs, targets={"moved0": y[0]})
+    stats.count_dev = count_dev                  # sampler and statistics share the device-side sample counter
+    sampler.count_dev = count_dev
 
-    def one_sample():            # everything of a sample but the noise: forward pass + all statistics, one CUDA graph
+    def one_sample():            # a whole MC sample -- noise, forward pass, all statistics -- as one CUDA graph
+        sampler.draw()
         plan.run_forward(x, z)
         stats.update()
     graph, launch_mode = None, "eager"
@@ -794,26 +801,19 @@ def run_mc128(args):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             one_sample()
-        launch_mode = "cuda_graph per sample (forward + statistics)"
-    launches_fwd = plan.launches + 2
-    ids = mc.shard_samples(N, rank, world)
+        launch_mode = "cuda_graph per sample (Philox noise + forward + statistics)"
+    launches_fwd = plan.launches + 3
     result = {}
-
-    gen = torch.Generator(device=dev)     # one Philox generator, re-seeded per sample (same streams as mc.sample_generator)
 
     def job():
         stats.reset()
-        for i in ids:
-            gen.manual_seed(int(args.seed0) + int(i))
-            for l in range(latent):    # gauss_sampler (src/network_blocks.py:7-8), z = mu + sigma * eps, one kernel per level
-                torch.normal(mu[l], sg[l], generator=gen, out=z[l])
+        for _ in ids:
             graph.replay() if graph is not None else one_sample()
             stats.count += 1
-        states = mc.merge_across_ranks(stats.states(), dst=0, device=dev)
+        res = mc.sliced_uncertainty(stats.states(), dst=0, device=dev)
         if rank == 0:
-            m = mc.uncertainty_metrics(states["moved0"], states["moved0:sqerr"])
-            result.update(var=m["var"], mse=m["mse"], ncc=m["ncc"], var_mean=m["var_mean"],
-                          std={k: states[k].std_channel_mean() for k in tracked})
+            r = PF.global_ncc(res["moved0"], res["moved0:mse"], 1.0, 1.0, True)      # ncc(var = std^2, mse), var.mean()
+            result.update(var=res["moved0"] ** 2, mse=res["moved0:mse"], ncc=r[0], var_mean=r[1], std={k: res[k] for k in tracked})
     ms_total, clk = _timed(torch, dist, world, dev, local, rank, max(1, min(args.warmup, 2)), args.steps, job)
     ms_step = ms_total / args.steps
     value = N * nvox / (ms_step * 1e-3) / 1e9
@@ -834,10 +834,7 @@ def run_mc128(args):
     state = {"m": None}
 
     def prof_one():      # one sample + its moment updates, eager, single stream
-        g = mc.sample_generator(args.seed0, 0, dev)
-        for l in range(latent):
-            z[l].normal_(generator=g)
-            z[l].mul_(sg[l]).add_(mu[l])
+        sampler.draw(0)
         plan1.run_forward(x, z)
         if state["m"] is None:
             state["m"] = {k: mc.MCMoments(v.shape, dev) for k, v in (("moved0", plan1.moved[0][0]), ("final0", plan1.final[0][0]))}
@@ -855,8 +852,8 @@ def run_mc128(args):
                "config": {"workload": args.workload, "samples": N, "samples_per_gpu": len(ids), "voxels_per_sample": nvox,
                           "levels": "%d total / %d latent, level_res, 7 integration steps" % (total, latent), "launch": launch_mode,
                           "tracked_maps": tracked + ["moved0:sqerr"],
-                          "parallelism": "samples dealt round-robin to %d GPU(s); binomial-tree reduce of (count, mean, M2) to rank 0 "
-                                         "(NCCL send/recv), reduce(SUM) of the squared errors" % world,
+                          "parallelism": "samples dealt round-robin to %d GPU(s); all_to_all of voxel slices of (mean, M2, squared errors), "
+                                         "per-slice Chan merge, gather of the std / MSE maps to rank 0 (NCCL)" % world,
                           "l2": "per-sample working set ~0.9 GB >> 126 MB L2; no explicit flush"},
                "e2e": {"value": N * nvox / (ms_e2e / e2e_steps * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": 2 * nvox * 4,
                        "d2h_bytes_per_step": nvox * 4, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,

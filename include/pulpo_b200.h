@@ -291,6 +291,21 @@ int pulpo_moments_update_multi(const pulpo_moments_map *maps, int nmaps, const i
                                pulpo_stream_t stream);
 int pulpo_counter_add(int *counter_dev, int value, int reset, pulpo_stream_t stream);
 
+/* ---- a13 for the MC loop: gauss_sampler (src/network_blocks.py:7-8) of ALL levels of one deformation sample ----
+ * z = mu + sigma * (var * eps), eps ~ N(0,1) from Philox4x32-10 + Box-Muller keyed by (seed, sample id) and indexed by
+ * (level, element): sample i has the same noise on whatever rank draws it (the sharding contract of config 3).
+ * sample id = first_id + id_stride * (*count_dev) (count_dev nullable = 0): with the running sample count on the
+ * device one captured launch serves the whole loop of evaluate.py:227-235.  eps_out nullable (noise dump for tests).
+ * `levels` is a HOST array, <= 8. */
+typedef struct pulpo_gauss_level {
+    const float *mu, *sigma;
+    float *z, *eps_out;
+    long long n;
+} pulpo_gauss_level;
+int pulpo_gauss_sample_multi(const pulpo_gauss_level *levels, int nlevels, unsigned long long seed,
+                             const int *count_dev, int first_id, int id_stride, float var,
+                             pulpo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,11 @@ class KlLevel(ctypes.Structure):
     _fields_ = [("mu", _vp), ("sigma", _vp), ("gmu", _vp), ("gsigma", _vp), ("out", _vp), ("n", _ll), ("weight", _f)]
 
 
+class GaussLevel(ctypes.Structure):
+    """pulpo_gauss_level (include/pulpo_b200.h)."""
+    _fields_ = [("mu", _vp), ("sigma", _vp), ("z", _vp), ("eps_out", _vp), ("n", _ll)]
+
+
 class MomentsMap(ctypes.Structure):
     """pulpo_moments_map (include/pulpo_b200.h)."""
     _fields_ = [("x", _vp), ("mean", _vp), ("m2", _vp), ("target", _vp), ("sqerr_acc", _vp), ("n", _ll)]
@@ -79,6 +84,7 @@ SIGNATURES = {
     "pulpo_moments_update": (_i, [_vp, _vp, _vp, _i, _ll, _vp]),
     "pulpo_moments_merge": (_i, [_vp, _vp, _i, _vp, _vp, _i, _ll, _vp]),
     "pulpo_moments_std": (_i, [_vp, _vp, _i, _ll, _vp]),
+    "pulpo_gauss_sample_multi": (_i, [ctypes.POINTER(GaussLevel), _i, ctypes.c_ulonglong, _vp, _i, _i, _f, _vp]),
     "pulpo_moments_update_multi": (_i, [ctypes.POINTER(MomentsMap), _i, _vp, _vp]),
     "pulpo_counter_add": (_i, [_vp, _i, _i, _vp]),
     "pulpo_loss_total": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp]),

@@ -509,6 +509,61 @@ __global__ void counter_add_kernel(int *ctr, int v, int reset)
     if (threadIdx.x == 0 && blockIdx.x == 0) *ctr = reset ? v : *ctr + v;
 }
 
+// ---- MC sampling: z = mu + sigma * eps (gauss_sampler, src/network_blocks.py:7-8) for every level of one MC
+// deformation sample in ONE graph-capturable launch.  eps comes from a counter-based generator (Philox4x32-10 +
+// Box-Muller) keyed by (seed, sample id) and indexed by (level, element), so sample i is the same bits on whatever
+// rank draws it; the sample id is first_id + id_stride * (*count_dev): the MC loop's running count lives on the
+// device (pulpo_counter_add), so the captured launch serves every sample of the loop at evaluate.py:227-235.
+constexpr int GS_MAXL = 8;
+struct GaussLevels {
+    int n;
+    pulpo_gauss_level l[GS_MAXL];
+};
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float2 box_muller(unsigned int a, unsigned int b)
+{
+    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);    // (0, 1)
+    const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    __sincosf(6.283185307179586f * u2, &s, &c);
+    return make_float2(r * c, r * s);
+}
+__global__ void __launch_bounds__(256)
+gauss_sample_multi_kernel(const GaussLevels lv, unsigned long long seed, const int *__restrict__ count_dev, int first_id,
+                          int id_stride, float var)
+{
+    const unsigned int sample = (unsigned int)(first_id + id_stride * (count_dev ? *count_dev : 0));
+    const uint2 key = make_uint2((unsigned int)seed, (unsigned int)(seed >> 32));
+    for (int k = 0; k < lv.n; ++k) {
+        const pulpo_gauss_level &L = lv.l[k];
+        const i64 quads = (L.n + 3) / 4;
+        for (i64 q = blockIdx.x * (i64)blockDim.x + threadIdx.x; q < quads; q += (i64)gridDim.x * blockDim.x) {
+            const uint4 r = philox4x32_10(make_uint4((unsigned int)q, (unsigned int)(q >> 32), sample, (unsigned int)k), key);
+            const float2 e0 = box_muller(r.x, r.y), e1 = box_muller(r.z, r.w);
+            const float e[4] = {e0.x, e0.y, e1.x, e1.y};
+            const i64 i0 = 4 * q;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (i0 + t < L.n) {
+                    const float eps = __fmul_rn(var, e[t]);
+                    if (L.eps_out) L.eps_out[i0 + t] = eps;
+                    L.z[i0 + t] = __fadd_rn(L.mu[i0 + t], __fmul_rn(L.sigma[i0 + t], eps));
+                }
+        }
+    }
+}
+
 }  // namespace pulpo
 
 using namespace pulpo;
@@ -718,6 +773,25 @@ extern "C" int pulpo_counter_add(int *counter_dev, int value, int reset, pulpo_s
 {
     PULPO_REQUIRE(counter_dev, PULPO_ERR_NULL_POINTER);
     counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter_dev, value, reset);
+    return launch_status();
+}
+
+extern "C" int pulpo_gauss_sample_multi(const pulpo_gauss_level *levels, int nlevels, unsigned long long seed,
+                                        const int *count_dev, int first_id, int id_stride, float var, pulpo_stream_t stream)
+{
+    PULPO_REQUIRE(levels, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(nlevels >= 1 && nlevels <= GS_MAXL, PULPO_ERR_INVALID_SHAPE);
+    GaussLevels g;
+    g.n = nlevels;
+    long long biggest = 0;
+    for (int k = 0; k < nlevels; ++k) {
+        PULPO_REQUIRE(levels[k].mu && levels[k].sigma && levels[k].z, PULPO_ERR_NULL_POINTER);
+        PULPO_REQUIRE(levels[k].n > 0, PULPO_ERR_INVALID_SHAPE);
+        g.l[k] = levels[k];
+        if (levels[k].n > biggest) biggest = levels[k].n;
+    }
+    gauss_sample_multi_kernel<<<grid_for((biggest + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(g, seed, count_dev, first_id,
+                                                                                                 id_stride, var);
     return launch_status();
 }
 

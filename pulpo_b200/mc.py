@@ -207,6 +207,129 @@ class StreamingStats:
         return out
 
 
+class PhiloxSampler:
+    """gauss_sampler (src/network_blocks.py:7-8) of all levels of an MC sample as ONE graph-capturable launch:
+    ``z[l] = mu[l] + sigma[l] * eps`` with eps from a counter-based Philox stream keyed by ``(seed, sample id)``, so
+    sample *i* is the same noise on whatever rank draws it.  The sample id is ``first_id + id_stride * count`` where
+    ``count`` is the device-side sample counter of a ``StreamingStats`` (or 0): captured together with the forward pass
+    and the statistics update, a single graph replay runs a whole sample without any host-side RNG call."""
+
+    def __init__(self, mu: Dict[int, torch.Tensor], sigma: Dict[int, torch.Tensor], seed: int = 0, first_id: int = 0,
+                 id_stride: int = 1, count_dev: Optional[torch.Tensor] = None, dump_noise: bool = False):
+        import ctypes
+        from . import _lib
+        self.levels = sorted(mu.keys())
+        self.mu = {l: mu[l].contiguous() for l in self.levels}
+        self.sigma = {l: sigma[l].contiguous() for l in self.levels}
+        self.z = {l: torch.empty_like(self.mu[l]) for l in self.levels}
+        self.eps = {l: torch.empty_like(self.mu[l]) for l in self.levels} if dump_noise else None
+        self.dev = self.mu[self.levels[0]].device
+        self.seed, self.first_id, self.id_stride = int(seed), int(first_id), int(id_stride)
+        self.count_dev = count_dev
+        arr = (_lib.GaussLevel * len(self.levels))()
+        for k, l in enumerate(self.levels):
+            if not (self.mu[l].is_cuda and self.mu[l].dtype == torch.float32 and self.sigma[l].shape == self.mu[l].shape):
+                raise RuntimeError("PhiloxSampler: mu / sigma of level %d must be fp32 CUDA tensors of one shape" % l)
+            arr[k] = _lib.GaussLevel(self.mu[l].data_ptr(), self.sigma[l].data_ptr(), self.z[l].data_ptr(),
+                                     self.eps[l].data_ptr() if dump_noise else None, self.mu[l].numel())
+        self._arr, self._vp = arr, ctypes.c_void_p
+
+    def draw(self, sample_id: Optional[int] = None):
+        """Enqueue the sampling of the next sample (device counter) or of an explicit ``sample_id`` (not capturable)."""
+        from . import _lib
+        st = self._vp(torch.cuda.current_stream(self.dev).cuda_stream)
+        if sample_id is None:
+            cnt = self._vp(self.count_dev.data_ptr()) if self.count_dev is not None else None
+            first, stride = self.first_id, self.id_stride
+        else:
+            cnt, first, stride = None, int(sample_id), 0
+        _lib.check(_lib.lib().pulpo_gauss_sample_multi(self._arr, len(self.levels), self.seed, cnt, first, stride, 1.0, st),
+                   "gauss_sample_multi")
+        return self.z
+
+
+def sliced_uncertainty(states: Dict[str, "MCMoments | MCSqErr"], group=None, dst: int = 0, device=None):
+    """Multi-GPU reduction of MC statistics straight to the maps ``Evaluate.predict / uncertainty`` report
+    (evaluate.py:243-251, 1534-1545), sized for NVSwitch: every rank owns 1/W of the voxels.
+
+    1. one ``all_to_all``: rank r receives voxel slice r of every rank's ``(mean, M2)`` (and squared-error sums) --
+       each rank sends its state once, all links busy at the same time (a tree reduce to one rank serialises
+       log2(W) hops of the full state);
+    2. each rank Chan-merges the W partial slices in rank order (deterministic) and turns them into what is reported:
+       per-voxel unbiased std averaged over channels, and the MSE;
+    3. one ``gather`` of those result slices (1 float per voxel per map, 6x less than (mean, M2) of a 3-channel field)
+       to rank ``dst``.
+    Returns on ``dst``: ``{name: std_channel_mean [*S]}`` plus ``{name + ":mse": [*S]}`` for the squared-error states;
+    ``None`` on the other ranks."""
+    import torch.distributed as dist
+    names = sorted(n for n in states if not isinstance(states[n], MCSqErr))
+    sq_names = sorted(n for n in states if isinstance(states[n], MCSqErr))
+    if device is None:
+        device = states[names[0]].mean.device
+    ops = states[names[0]].ops
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    W = dist.get_world_size(group) if multi else 1
+    rank = dist.get_rank(group) if multi else 0
+    if not multi:
+        out = {n: states[n].std_channel_mean() for n in names}
+        out.update({n.replace(":sqerr", ":mse"): states[n].mse() for n in sq_names})
+        return out
+    # layout of one rank's packed state: for every map [C, nvox] -> W slices of `chunk` voxels (zero padded)
+    meta, total = [], 0
+    for n in names:
+        C, nvox = states[n].mean.shape[0], states[n].mean[0].numel()
+        chunk = (nvox + W - 1) // W
+        meta.append((n, C, nvox, chunk, total, 2 * C * chunk))
+        total += 2 * C * chunk
+    for n in sq_names:
+        C, nvox = states[n].acc.shape[0], states[n].acc[0].numel()
+        chunk = (nvox + W - 1) // W
+        meta.append((n, C, nvox, chunk, total, C * chunk))
+        total += C * chunk
+    send = torch.zeros(W, total, dtype=torch.float32, device=device)
+    for n, C, nvox, chunk, off, sz in meta:
+        st = states[n]
+        parts = [st.acc.reshape(C, nvox)] if isinstance(st, MCSqErr) else [st.mean.reshape(C, nvox), st.m2.reshape(C, nvox)]
+        packed = torch.zeros(len(parts), C, W * chunk, dtype=torch.float32, device=device)
+        for k, p in enumerate(parts):
+            packed[k, :, :nvox] = p
+        # [parts, C, W, chunk] -> [W, parts * C * chunk]
+        send[:, off:off + sz] = packed.reshape(len(parts), C, W, chunk).permute(2, 0, 1, 3).reshape(W, sz)
+    counts = torch.tensor([states[names[0]].count], dtype=torch.int64, device=device)
+    all_counts = [torch.empty_like(counts) for _ in range(W)]
+    dist.all_gather(all_counts, counts, group=group)
+    all_counts = [int(c.item()) for c in all_counts]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    # merge this rank's slice of every map over the W partial states, in rank order
+    res_parts, res_meta = [], []
+    for n, C, nvox, chunk, off, sz in meta:
+        if n in sq_names:
+            acc = recv[:, off:off + sz].sum(dim=0) / float(sum(all_counts))
+            res = acc.reshape(C, chunk).mean(dim=0) if C > 1 else acc.reshape(chunk)
+        else:
+            m = MCMoments((C, chunk), device, ops=ops)
+            for r in range(W):
+                blk = recv[r, off:off + sz].reshape(2, C, chunk)
+                m.merge_state(blk[0], blk[1], all_counts[r])
+            res = m.std_channel_mean()
+        res_parts.append(res.reshape(-1))
+        res_meta.append((n, nvox, chunk))
+    mine = torch.cat(res_parts)
+    gathered = [torch.empty_like(mine) for _ in range(W)] if rank == dst else None
+    dist.gather(mine, gathered, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+    if rank != dst:
+        return None
+    out, pos = {}, 0
+    for n, nvox, chunk in res_meta:
+        full = torch.cat([g[pos:pos + chunk] for g in gathered])[:nvox]
+        st = states[n]
+        shape = tuple((st.acc if isinstance(st, MCSqErr) else st.mean).shape[1:])
+        out[n.replace(":sqerr", ":mse")] = full.reshape(shape)
+        pos += chunk
+    return out
+
+
 def _check_same_maps(local_meta, group):
     """Every rank must hold the same maps with the same shapes; a rank that drew no sample (empty explicit
     ``sample_ids``) may hold none.  Decided on ALL ranks before any tensor collective, so a mismatch raises

@@ -1136,3 +1136,72 @@ def test_vecint_dataflow_multi_level_plan_equals_barriers(PF, monkeypatch):
     for l in range(latent):
         assert torch.equal(new.integ[l], ref.integ[l]), "integrated field %d differs" % l
         assert_grad_close(new.gdf[l].cpu().numpy(), ref.gdf[l].cpu().numpy(), "gdf %d" % l, rtol=1e-5)
+
+
+# ----------------------------------------------------------------------------- MC sampling in one launch (config 3)
+def test_philox_sampler_is_sharding_invariant_and_standard_normal(PF):
+    """gauss_sampler (src/network_blocks.py:7-8) for all levels of an MC sample in one graph-capturable launch:
+    z = mu + sigma * eps exactly; eps depends on (seed, sample id, level, element) only -- the same sample id gives
+    the same bits whether it is addressed explicitly or through the device-side counter of another 'rank' -- and is
+    standard normal."""
+    from pulpo_b200 import mc
+    g = torch.Generator(device="cuda").manual_seed(1)
+    mu = {l: torch.randn(1, 3, 20 >> l, 24 >> l, 28 >> l, device="cuda", generator=g) for l in range(3)}
+    sg = {l: torch.rand(1, 3, 20 >> l, 24 >> l, 28 >> l, device="cuda", generator=g) + 0.1 for l in range(3)}
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    a = mc.PhiloxSampler(mu, sg, seed=9, first_id=1, id_stride=4, count_dev=cnt, dump_noise=True)   # "rank 1 of 4"
+    b = mc.PhiloxSampler(mu, sg, seed=9, dump_noise=True)
+    cnt.fill_(2)                                     # third sample of that rank -> sample id 1 + 4 * 2 = 9
+    za = {l: t.clone() for l, t in a.draw().items()}
+    zb = {l: t.clone() for l, t in b.draw(9).items()}      # draw() returns the sampler's static buffers
+    for l in mu:
+        assert torch.equal(za[l], zb[l]), "level %d: sample 9 differs between counter and explicit addressing" % l
+        assert torch.equal(zb[l], mu[l] + sg[l] * b.eps[l])
+    z8 = {l: t.clone() for l, t in b.draw(8).items()}
+    assert not torch.equal(z8[0], zb[0])
+    assert not torch.equal(mc.PhiloxSampler(mu, sg, seed=10).draw(9)[0], zb[0])
+    big = {0: torch.zeros(1, 3, 64, 64, 64, device="cuda")}
+    s = mc.PhiloxSampler(big, {0: torch.ones_like(big[0])}, seed=3)
+    e = s.draw(0)[0].double()
+    n = e.numel()
+    assert abs(float(e.mean())) < 5 / n ** 0.5 and abs(float(e.var()) - 1.0) < 5 * (2.0 / n) ** 0.5
+    assert abs(float((e ** 3).mean())) < 0.02 and abs(float((e ** 4).mean()) - 3.0) < 0.05
+    assert float(e.abs().max()) < 6.5
+    e2 = s.draw(1)[0].double()
+    assert abs(float((e * e2).mean())) < 5 / n ** 0.5          # different samples are uncorrelated
+
+
+def test_streaming_stats_graph_matches_mcmoments(PF):
+    """StreamingStats (all maps + squared errors in one launch, device-side sample count, CUDA-graph replayed)
+    against the per-map MCMoments / MCSqErr updates."""
+    from pulpo_b200 import mc
+    g = torch.Generator(device="cuda").manual_seed(2)
+    bufs = {"a": torch.empty(3, 6, 7, 8, device="cuda"), "b": torch.empty(1, 9, 5, 4, device="cuda")}
+    tgt = torch.rand(1, 9, 5, 4, device="cuda", generator=g)
+    st = mc.StreamingStats(bufs, targets={"b": tgt})
+    ref = {k: mc.MCMoments(v.shape, "cuda") for k, v in bufs.items()}
+    sq = mc.MCSqErr(bufs["b"].shape, "cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        st.update()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        st.update()
+    st.reset()
+    for i in range(7):
+        for k in bufs:
+            bufs[k].copy_(torch.randn(bufs[k].shape, device="cuda", generator=g) * (i + 1))
+            ref[k].update(bufs[k])
+        sq.update(bufs["b"], tgt)
+        gr.replay()
+        st.count += 1
+    out = st.states()
+    for k in bufs:
+        assert out[k].count == 7
+        assert torch.equal(out[k].mean, ref[k].mean) and torch.equal(out[k].m2, ref[k].m2)
+    assert torch.equal(out["b:sqerr"].acc, sq.acc)
+    one = mc.sliced_uncertainty(out)
+    assert torch.equal(one["a"], ref["a"].std_channel_mean()) and torch.equal(one["b:mse"], sq.mse())

@@ -156,3 +156,40 @@ def test_merge_shape_mismatch_raises_on_all_ranks(tmp_path):
     port = _free_port()
     mp.spawn(_worker_mismatch, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert all(open(os.path.join(str(tmp_path), "ok%d" % r)).read() == "True" for r in range(2))
+
+
+
+def _worker_sliced(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        states = mc.mc_uncertainty(_sample, N_SAMPLES, seed0=123, device=torch.device("cpu"), ops=TorchCpuOps, dst=0,
+                                   sample_ids=mc.shard_samples(N_SAMPLES, rank, world), targets={"moved0": _target()})
+        # mc_uncertainty already merged onto rank 0; for the sliced reduction start again from the per-rank partial states
+        local = {}
+        for i in mc.shard_samples(N_SAMPLES, rank, world):
+            maps = _sample(i, mc.sample_generator(123, i, "cpu"))
+            for n, t in maps.items():
+                local.setdefault(n, mc.MCMoments(t.shape, "cpu", ops=TorchCpuOps)).update(t)
+            local.setdefault("moved0:sqerr", mc.MCSqErr(maps["moved0"].shape, "cpu", ops=TorchCpuOps)).update(maps["moved0"], _target())
+        res = mc.sliced_uncertainty(local, dst=0, device=torch.device("cpu"))
+        if rank == 0:
+            torch.save(res, os.path.join(out_dir, "sliced.pt"))
+        else:
+            assert res is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_sliced_all_to_all_reduction_three_ranks(tmp_path):
+    """all_to_all of voxel slices + per-slice Chan merge + gather of the std maps == stack-based std / MSE
+    (3 ranks: the slice size does not divide the voxel count)."""
+    port = _free_port()
+    mp.spawn(_worker_sliced, args=(3, port, str(tmp_path)), nprocs=3, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "sliced.pt"))
+    stack = torch.stack([_sample(i, mc.sample_generator(123, i, "cpu"))["final0"] for i in range(N_SAMPLES)])
+    moved = torch.stack([_sample(i, mc.sample_generator(123, i, "cpu"))["moved0"] for i in range(N_SAMPLES)])
+    torch.testing.assert_close(got["final0"], stack.std(dim=0).mean(dim=0), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(got["moved0"], moved.std(dim=0).mean(dim=0), rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(got["moved0:mse"], ((moved - _target()) ** 2).mean(dim=0)[0], rtol=1e-5, atol=1e-8)
