@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/pulpo_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -17,6 +19,14 @@ namespace pulpo {
 typedef long long i64;
 
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
+
+// NVTX range around every C-ABI entry point (the reference has no tracing hooks; Nsight shows one range
+// per call).  Header-only NVTX v3: a no-op costing a few nanoseconds when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define PULPO_NVTX(name) ::pulpo::NvtxRange pulpo_nvtx_range_(name)
 
 #define PULPO_REQUIRE(cond, code) \
     do {                          \
@@ -137,24 +147,27 @@ __device__ __forceinline__ Tap make_tap(float vf, float d, const AxisConst &a, f
 //   * n + 1 with n = 2 * (q - 0.5):  n is exact (a power-of-two scaling), so RN(n + 1) == fma(q - 0.5, 2, 1);
 //   * (t - 1) * 0.5 with t = RN((n + 1) * S):  halving commutes with rounding (t - 1 is never subnormal: it is 0
 //     or at least one ulp of a value near 1), so RN(t - 1) / 2 == fma(t, 0.5, -0.5).
-struct AxisConst2 {   // AxisConst with every constant duplicated into both halves of a register pair
-    float2 S, nSm1, rcp;
-    float Sm1, tmax, gmul, kf;
+struct AxisConst2 {   // AxisConst as register pairs: the same axis twice (two voxels) or two axes of one voxel
+    float2 S, nSm1, rcp, Sm1, tmax, gmul, kf;
 };
 
 // S: size of the axis the displacement field lives on (normalisation, src/network_blocks.py:106-107); Simg: size of
 // the sampled image along that axis (grid_sample's unnormalise, clamp and gather).  They differ when a level-sized
 // field resamples a full-resolution image (evaluate.py:198,240,246).
-__host__ __device__ inline AxisConst2 make_axis2(int S, int Simg)
+__host__ __device__ inline AxisConst2 make_axis_pair(int Sx, int Simgx, int Sy, int Simgy)
 {
-    const AxisConst a = make_axis(S), i = make_axis(Simg);
+    const AxisConst ax = make_axis(Sx), ix = make_axis(Simgx), ay = make_axis(Sy), iy = make_axis(Simgy);
     AxisConst2 r;
-    r.S.x = r.S.y = i.S;
-    r.nSm1.x = r.nSm1.y = -a.Sm1;
-    r.rcp.x = r.rcp.y = a.rcp;
-    r.Sm1 = i.Sm1; r.tmax = i.tmax; r.gmul = i.gmul; r.kf = i.S / a.Sm1;
+    r.S.x = ix.S; r.S.y = iy.S;
+    r.nSm1.x = -ax.Sm1; r.nSm1.y = -ay.Sm1;
+    r.rcp.x = ax.rcp; r.rcp.y = ay.rcp;
+    r.Sm1.x = ix.Sm1; r.Sm1.y = iy.Sm1;
+    r.tmax.x = ix.tmax; r.tmax.y = iy.tmax;
+    r.gmul.x = ix.gmul; r.gmul.y = iy.gmul;
+    r.kf.x = ix.S / ax.Sm1; r.kf.y = iy.S / ay.Sm1;
     return r;
 }
+__host__ __device__ inline AxisConst2 make_axis2(int S, int Simg) { return make_axis_pair(S, Simg, S, Simg); }
 __host__ __device__ inline AxisConst2 make_axis2(int S) { return make_axis2(S, S); }
 
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
@@ -183,7 +196,7 @@ template <int MODE>
 __device__ __forceinline__ float2 sample_pos2(float2 vf, float2 d, const AxisConst2 &a)
 {
     float2 loc = __fadd2_rn(vf, d);
-    if (MODE == PULPO_COORD_FAST) return __ffma2_rn(loc, splat2(a.kf), splat2(-0.5f));
+    if (MODE == PULPO_COORD_FAST) return __ffma2_rn(loc, a.kf, splat2(-0.5f));
     float2 q;
     if (MODE == PULPO_COORD_CPU_EXACT) {
         loc.x = tame(loc.x); loc.y = tame(loc.y);
@@ -218,10 +231,10 @@ __device__ __forceinline__ Tap2 make_tap2(float2 vf, float2 d, const AxisConst2 
     Tap2 tp;
     tp.u = sample_pos2<MODE>(vf, d, a);
     float2 p;
-    p.x = clip_pos(tp.u.x, a.Sm1); p.y = clip_pos(tp.u.y, a.Sm1);
+    p.x = clip_pos(tp.u.x, a.Sm1.x); p.y = clip_pos(tp.u.y, a.Sm1.y);
     const float2 t = __fadd2_rz(p, splat2(8388608.0f));
     float2 tc;
-    tc.x = fminf(t.x, a.tmax); tc.y = fminf(t.y, a.tmax);
+    tc.x = fminf(t.x, a.tmax.x); tc.y = fminf(t.y, a.tmax.y);
     const float2 fl = __fadd2_rn(tc, splat2(-8388608.0f));
     tp.bits0 = __float_as_int(tc.x); tp.bits1 = __float_as_int(tc.y);
     tp.fl0 = __float_as_int(t.x) - kTapBias; tp.fl1 = __float_as_int(t.y) - kTapBias;

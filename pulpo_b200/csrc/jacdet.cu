@@ -202,6 +202,7 @@ using namespace pulpo;
 extern "C" int pulpo_jacdet_fwd(const float *df, float *det, int normalize, int B, int D0, int D1, int D2,
                                 pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_jacdet_fwd");
     PULPO_REQUIRE(df && det, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
     JGeom g;
@@ -219,6 +220,7 @@ extern "C" size_t pulpo_jacdet_bwd_ws_bytes(int B, int D0, int D1, int D2)
 extern "C" int pulpo_jacdet_bwd(const float *gdet, const float *df, float *gdf, void *ws, size_t ws_bytes, int normalize,
                                 int B, int D0, int D1, int D2, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_jacdet_bwd");
     PULPO_REQUIRE(gdet && df && gdf && ws, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(ws_bytes >= pulpo_jacdet_bwd_ws_bytes(B, D0, D1, D2), PULPO_ERR_WORKSPACE);
@@ -236,6 +238,7 @@ extern "C" size_t pulpo_std_ws_bytes(void) { return 32 + sizeof(double) * 2 * kS
 extern "C" int pulpo_std_fwd(const float *x, float lamb, float *out, void *ws, size_t ws_bytes, long long n,
                              pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_std_fwd");
     PULPO_REQUIRE(x && out && ws, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(n >= 2, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(ws_bytes >= pulpo_std_ws_bytes(), PULPO_ERR_WORKSPACE);
@@ -248,6 +251,7 @@ extern "C" int pulpo_std_fwd(const float *x, float lamb, float *out, void *ws, s
 extern "C" int pulpo_std_bwd(const float *gloss, const float *x, const void *ws, float lamb, float *gx, long long n,
                              pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_std_bwd");
     PULPO_REQUIRE(x && ws && gx, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(n >= 2, PULPO_ERR_INVALID_SHAPE);
     std_bwd_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(gloss, x, (const StdWs *)ws, lamb, gx, n);

@@ -574,6 +574,7 @@ extern "C" int pulpo_kl_diag_fwd(const float *mu0, const float *sigma0, const fl
                                  float eps, float weight, float *out, void *ws, size_t ws_bytes, int B, long long n,
                                  pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_kl_diag_fwd");
     PULPO_REQUIRE(mu0 && sigma0 && out && ws, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && n > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(ws_bytes >= kReduceWsBytes, PULPO_ERR_WORKSPACE);
@@ -589,6 +590,7 @@ extern "C" int pulpo_gauss_sample_kl_fwd(const float *mu, const float *sigma, co
                                         const float *sigma1, float var, float eps, float weight, float *z, float *out,
                                         void *ws, size_t ws_bytes, int B, long long n, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_gauss_sample_kl_fwd");
     PULPO_REQUIRE(mu && sigma && noise && z && out && ws, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && n > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(ws_bytes >= kReduceWsBytes, PULPO_ERR_WORKSPACE);
@@ -607,6 +609,7 @@ extern "C" int pulpo_gauss_sample_kl_bwd(const float *gz, const float *gloss, in
                                         float var, float eps, float weight, float *gmu, float *gsigma, int B,
                                         long long n, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_gauss_sample_kl_bwd");
     PULPO_REQUIRE(mu && sigma && noise && gmu && gsigma, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && n > 0, PULPO_ERR_INVALID_SHAPE);
     const i64 total = (i64)B * n;
@@ -620,6 +623,7 @@ extern "C" size_t pulpo_kl_multi_ws_bytes(void) { return 16 + sizeof(double) * K
 extern "C" int pulpo_kl_n01_multi(const pulpo_kl_level *levels, int nlevels, float eps, int B, void *ws, size_t ws_bytes,
                                   pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_kl_n01_multi");
     PULPO_REQUIRE(levels && ws, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(nlevels >= 1 && nlevels <= KL_MAXL && B > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(ws_bytes >= pulpo_kl_multi_ws_bytes(), PULPO_ERR_WORKSPACE);
@@ -647,6 +651,7 @@ extern "C" int pulpo_kl_diag_bwd(const float *gloss, const float *mu0, const flo
                                  const float *sigma1, float eps, float weight, float *gmu0, float *gsigma0, int B,
                                  long long n, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_kl_diag_bwd");
     PULPO_REQUIRE(mu0 && sigma0 && gmu0 && gsigma0, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && n > 0, PULPO_ERR_INVALID_SHAPE);
     const i64 total = (i64)B * n;
@@ -658,6 +663,7 @@ extern "C" int pulpo_kl_diag_bwd(const float *gloss, const float *mu0, const flo
 extern "C" int pulpo_l2reg_fwd(const float *f, float lamb, float *out, void *ws, size_t ws_bytes, int B, int C,
                                int D0, int D1, int D2, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_l2reg_fwd");
     PULPO_REQUIRE(f && out && ws, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(ws_bytes >= kReduceWsBytes, PULPO_ERR_WORKSPACE);
@@ -676,6 +682,7 @@ extern "C" int pulpo_l2reg_fwd(const float *f, float lamb, float *out, void *ws,
 extern "C" int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, float *gf, int accumulate, int B,
                                int C, int D0, int D1, int D2, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_l2reg_bwd");
     PULPO_REQUIRE(f && gf, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2, PULPO_ERR_INVALID_SHAPE);
     const i64 total = (i64)B * C * D0 * D1 * D2;
@@ -695,6 +702,7 @@ extern "C" int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, f
 extern "C" int pulpo_moments_update(const float *x, float *mean, float *m2, int count, long long n,
                                     pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_moments_update");
     PULPO_REQUIRE(x && mean && m2, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(count >= 1 && n > 0, PULPO_ERR_INVALID_SHAPE);
     moments_update_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, mean, m2, 1.0f / (float)count,
@@ -705,6 +713,7 @@ extern "C" int pulpo_moments_update(const float *x, float *mean, float *m2, int 
 extern "C" int pulpo_moments_merge(float *mean_a, float *m2_a, int count_a, const float *mean_b, const float *m2_b,
                                    int count_b, long long n, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_moments_merge");
     PULPO_REQUIRE(mean_a && m2_a && mean_b && m2_b, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(count_a >= 0 && count_b >= 0 && count_a + count_b > 0 && n > 0, PULPO_ERR_INVALID_SHAPE);
     const float tot = (float)(count_a + count_b);
@@ -715,6 +724,7 @@ extern "C" int pulpo_moments_merge(float *mean_a, float *m2_a, int count_a, cons
 
 extern "C" int pulpo_moments_std(const float *m2, float *std_out, int count, long long n, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_moments_std");
     PULPO_REQUIRE(m2 && std_out, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(count >= 2 && n > 0, PULPO_ERR_INVALID_SHAPE);
     moments_std_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(m2, std_out, 1.0f / (float)(count - 1), n);
@@ -723,6 +733,7 @@ extern "C" int pulpo_moments_std(const float *m2, float *std_out, int count, lon
 
 extern "C" int pulpo_sqerr_update(const float *x, const float *y, float *acc, int first, long long n, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_sqerr_update");
     PULPO_REQUIRE(x && y && acc, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(n > 0, PULPO_ERR_INVALID_SHAPE);
     sqerr_update_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, acc, first, n);
@@ -734,6 +745,7 @@ extern "C" size_t pulpo_global_ncc_ws_bytes(void) { return sizeof(GnccWs); }
 extern "C" int pulpo_global_ncc(const float *a, const float *v, float scale_a, float scale_v, int square_a, long long n,
                                 float *out2, void *ws, size_t ws_bytes, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_global_ncc");
     PULPO_REQUIRE(a && v && out2 && ws, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(n > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(ws_bytes >= sizeof(GnccWs), PULPO_ERR_WORKSPACE);
@@ -746,6 +758,7 @@ extern "C" int pulpo_global_ncc(const float *a, const float *v, float scale_a, f
 extern "C" int pulpo_loss_total(const float *losses, int rows, int cols, float *total, float *running, int accumulate,
                                 pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_loss_total");
     PULPO_REQUIRE(losses && (total || running), PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(rows > 0 && cols > 0 && rows * cols <= 4096, PULPO_ERR_INVALID_SHAPE);
     loss_total_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(losses, rows, cols, total, running, accumulate);
@@ -754,6 +767,7 @@ extern "C" int pulpo_loss_total(const float *losses, int rows, int cols, float *
 
 extern "C" int pulpo_moments_update_multi(const pulpo_moments_map *maps, int nmaps, const int *count_dev, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_moments_update_multi");
     PULPO_REQUIRE(maps && count_dev, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(nmaps >= 1 && nmaps <= MM_MAXMAPS, PULPO_ERR_INVALID_SHAPE);
     MomentsMaps mm;
@@ -771,6 +785,7 @@ extern "C" int pulpo_moments_update_multi(const pulpo_moments_map *maps, int nma
 
 extern "C" int pulpo_counter_add(int *counter_dev, int value, int reset, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_counter_add");
     PULPO_REQUIRE(counter_dev, PULPO_ERR_NULL_POINTER);
     counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter_dev, value, reset);
     return launch_status();
@@ -779,6 +794,7 @@ extern "C" int pulpo_counter_add(int *counter_dev, int value, int reset, pulpo_s
 extern "C" int pulpo_gauss_sample_multi(const pulpo_gauss_level *levels, int nlevels, unsigned long long seed,
                                         const int *count_dev, int first_id, int id_stride, float var, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_gauss_sample_multi");
     PULPO_REQUIRE(levels, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(nlevels >= 1 && nlevels <= GS_MAXL, PULPO_ERR_INVALID_SHAPE);
     GaussLevels g;

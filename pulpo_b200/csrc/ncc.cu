@@ -293,6 +293,7 @@ extern "C" int pulpo_ncc_fwd(const float *pred, const float *target, float *loss
                              size_t ws_bytes, int win, float gamma, int B, int C, int D0, int D1, int D2,
                              pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_ncc_fwd");
     PULPO_REQUIRE(pred && target && loss && ws, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE((i64)D0 * D1 * D2 < (1ll << 31), PULPO_ERR_INVALID_SHAPE);
@@ -327,6 +328,7 @@ extern "C" int pulpo_ncc_bwd(const float *abc, const float *pred, const float *t
                              float *gpred, int win, float gamma, int B, int C, int D0, int D1, int D2,
                              pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_ncc_bwd");
     PULPO_REQUIRE(abc && pred && target && gpred, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE((i64)D0 * D1 * D2 < (1ll << 31), PULPO_ERR_INVALID_SHAPE);

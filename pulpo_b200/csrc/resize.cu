@@ -560,6 +560,7 @@ using namespace pulpo;
 extern "C" int pulpo_resize_up_fwd(const float *x, const float *addend, float *out, int factor, float scale, int B,
                                    int C, int d0, int d1, int d2, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_resize_up_fwd");
     PULPO_REQUIRE(x && out, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && d0 > 0 && d1 > 0 && d2 > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(factor >= 2 && factor <= 64, PULPO_ERR_UNSUPPORTED);
@@ -608,6 +609,7 @@ extern "C" int pulpo_resize_up_fwd(const float *x, const float *addend, float *o
 extern "C" int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, float scale, int accumulate, int B,
                                    int C, int d0, int d1, int d2, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_resize_up_bwd");
     PULPO_REQUIRE(gout && gx, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && d0 > 0 && d1 > 0 && d2 > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(factor >= 2 && factor <= 64, PULPO_ERR_UNSUPPORTED);
@@ -657,6 +659,7 @@ extern "C" int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, flo
 extern "C" int pulpo_interp_size_fwd(const float *x, float *out, int B, int C, int i0, int i1, int i2, int o0,
                                      int o1, int o2, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_interp_size_fwd");
     PULPO_REQUIRE(x && out, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && i0 > 0 && i1 > 0 && i2 > 0 && o0 > 0 && o1 > 0 && o2 > 0,
                   PULPO_ERR_INVALID_SHAPE);
@@ -670,6 +673,7 @@ extern "C" int pulpo_interp_size_fwd(const float *x, float *out, int B, int C, i
 extern "C" int pulpo_avgpool2_fwd(const float *x, float *out, int B, int C, int D0, int D1, int D2,
                                   pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_avgpool2_fwd");
     PULPO_REQUIRE(x && out, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
     i64 total = (i64)B * C * ((D0 + 1) / 2) * ((D1 + 1) / 2) * ((D2 + 1) / 2);
@@ -680,6 +684,7 @@ extern "C" int pulpo_avgpool2_fwd(const float *x, float *out, int B, int C, int 
 extern "C" int pulpo_avgpool2_pyramid_fwd(const float *x, float *const *outs, int nlevels, int B, int C, int D0, int D1,
                                           int D2, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_avgpool2_pyramid_fwd");
     PULPO_REQUIRE(x && outs, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 > 0 && D1 > 0 && D2 > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(nlevels >= 1 && nlevels <= POOL_MAXL, PULPO_ERR_INVALID_SHAPE);

@@ -427,9 +427,9 @@ warp3d_bwd_kernel(const float *__restrict__ gout, const float *__restrict__ img,
     for (int jp = 0; jp < WR / 2; ++jp) {
         const Foot2 &k = ft[jp];
         // zero gradient wherever the border clamp is active (p <= 0 or p >= S-1)
-        const float2 mz = pair((k.uz.x > 0.0f && k.uz.x < g.a0.Sm1) ? g.a0.gmul : 0.0f, (k.uz.y > 0.0f && k.uz.y < g.a0.Sm1) ? g.a0.gmul : 0.0f);
-        const float2 my = pair((k.uy.x > 0.0f && k.uy.x < g.a1.Sm1) ? g.a1.gmul : 0.0f, (k.uy.y > 0.0f && k.uy.y < g.a1.Sm1) ? g.a1.gmul : 0.0f);
-        const float2 mx = pair((k.ux.x > 0.0f && k.ux.x < g.a2.Sm1) ? g.a2.gmul : 0.0f, (k.ux.y > 0.0f && k.ux.y < g.a2.Sm1) ? g.a2.gmul : 0.0f);
+        const float2 mz = pair((k.uz.x > 0.0f && k.uz.x < g.a0.Sm1.x) ? g.a0.gmul.x : 0.0f, (k.uz.y > 0.0f && k.uz.y < g.a0.Sm1.x) ? g.a0.gmul.x : 0.0f);
+        const float2 my = pair((k.uy.x > 0.0f && k.uy.x < g.a1.Sm1.x) ? g.a1.gmul.x : 0.0f, (k.uy.y > 0.0f && k.uy.y < g.a1.Sm1.x) ? g.a1.gmul.x : 0.0f);
+        const float2 mx = pair((k.ux.x > 0.0f && k.ux.x < g.a2.Sm1.x) ? g.a2.gmul.x : 0.0f, (k.ux.y > 0.0f && k.ux.y < g.a2.Sm1.x) ? g.a2.gmul.x : 0.0f);
         const float2 z2 = __fmul2_rn(__fmul2_rn(mz, rz2[jp]), splat2(kz));
         const float2 y2 = __fmul2_rn(__fmul2_rn(my, ry2[jp]), splat2(ky));
         const float2 x2 = __fmul2_rn(__fmul2_rn(mx, rx2[jp]), splat2(kx));
@@ -544,6 +544,7 @@ using namespace pulpo;
 extern "C" int pulpo_warp3d_fwd(const float *img, const float *df, float *out, int32_t *idx_dbg, int B, int C,
                                 int D0, int D1, int D2, int coord_mode, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_warp3d_fwd");
     PULPO_REQUIRE(img && df && out, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(coord_mode == 0 || coord_mode == 1, PULPO_ERR_UNSUPPORTED);
@@ -554,6 +555,7 @@ extern "C" int pulpo_warp3d_fwd(const float *img, const float *df, float *out, i
 extern "C" int pulpo_warp3d_bwd(const float *gout, const float *img, const float *df, float *gimg, float *gdf,
                                 int B, int C, int D0, int D1, int D2, int coord_mode, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_warp3d_bwd");
     PULPO_REQUIRE(gout && img && df, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(gimg || gdf, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2, PULPO_ERR_INVALID_SHAPE);
@@ -565,6 +567,7 @@ extern "C" int pulpo_warp3d_bwd(const float *gout, const float *img, const float
 extern "C" int pulpo_warp3d_fwd_img(const float *img, const float *df, float *out, int32_t *idx_dbg, int B, int C,
                                     int D0, int D1, int D2, int I0, int I1, int I2, int coord_mode, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_warp3d_fwd_img");
     PULPO_REQUIRE(img && df && out, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2 && I0 >= 2 && I1 >= 2 && I2 >= 2, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(coord_mode == 0 || coord_mode == 1, PULPO_ERR_UNSUPPORTED);
@@ -576,6 +579,7 @@ extern "C" int pulpo_warp3d_bwd_img(const float *gout, const float *img, const f
                                     int B, int C, int D0, int D1, int D2, int I0, int I1, int I2, int coord_mode,
                                     pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_warp3d_bwd_img");
     PULPO_REQUIRE(gout && img && df, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(gimg || gdf, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2 && I0 >= 2 && I1 >= 2 && I2 >= 2, PULPO_ERR_INVALID_SHAPE);
@@ -588,6 +592,7 @@ extern "C" int pulpo_warp3d_l2reg_fwd(const float *img, const float *df, float *
                                       void *ws, size_t ws_bytes, int B, int C, int D0, int D1, int D2,
                                       int coord_mode, pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_warp3d_l2reg_fwd");
     PULPO_REQUIRE(img && df && out && reg_out && ws, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(coord_mode == 0 || coord_mode == 1, PULPO_ERR_UNSUPPORTED);
@@ -600,6 +605,7 @@ extern "C" int pulpo_warp3d_l2reg_bwd(const float *gout, const float *img, const
                                       const float *reg_gloss, int B, int C, int D0, int D1, int D2, int coord_mode,
                                       pulpo_stream_t stream)
 {
+    PULPO_NVTX("pulpo_warp3d_l2reg_bwd");
     PULPO_REQUIRE(gout && img && df && gdf, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(coord_mode == 0 || coord_mode == 1, PULPO_ERR_UNSUPPORTED);

@@ -163,9 +163,24 @@ class StreamingStats:
         self.maps = {n: maps[n] for n in self.names}
         dev = next(iter(maps.values())).device
         self.dev = dev
-        self.mean = {n: torch.zeros_like(maps[n]) for n in self.names}
-        self.m2 = {n: torch.zeros_like(maps[n]) for n in self.names}
-        self.acc = {n: torch.zeros_like(maps[n]) for n in self.names if n in targets}
+        # one flat buffer per statistic (padded so that any world size up to 16 splits it evenly): the multi-GPU
+        # reduction exchanges contiguous slices of these without any packing pass
+        self.offsets, off = {}, 0
+        for n in self.names:
+            self.offsets[n] = (off, maps[n].numel())
+            off += maps[n].numel()
+        self.total = off
+        pad = -(-off // 5040) * 5040
+        self.flat = torch.zeros(2, pad, dtype=torch.float32, device=dev)           # [mean | M2]
+        self.mean = {n: self.flat[0, o:o + k].view(maps[n].shape) for n, (o, k) in self.offsets.items()}
+        self.m2 = {n: self.flat[1, o:o + k].view(maps[n].shape) for n, (o, k) in self.offsets.items()}
+        self.acc_offsets, off = {}, 0
+        for n in self.names:
+            if n in targets:
+                self.acc_offsets[n] = (off, maps[n].numel())
+                off += maps[n].numel()
+        self.acc_flat = torch.zeros(max(-(-off // 5040) * 5040, 5040), dtype=torch.float32, device=dev)
+        self.acc = {n: self.acc_flat[o:o + k].view(maps[n].shape) for n, (o, k) in self.acc_offsets.items()}
         self.targets = {n: targets[n].contiguous() for n in self.acc}
         self.count_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.count = 0
@@ -193,6 +208,14 @@ class StreamingStats:
         lib, st = _lib.lib(), self._vp(torch.cuda.current_stream(self.dev).cuda_stream)
         _lib.check(lib.pulpo_moments_update_multi(self._arr, len(self.names), self._vp(self.count_dev.data_ptr()), st), "moments_update_multi")
         _lib.check(lib.pulpo_counter_add(self._vp(self.count_dev.data_ptr()), 1, 0, st), "counter_add")
+
+    def reduce_to_maps(self, counts: List[int], group=None, dst: int = 0):
+        """See ``reduce_flat_stats``: ``{name: std_channel_mean}`` + ``{name + ":mse"}`` on rank ``dst``."""
+        shapes = {n: tuple(self.maps[n].shape) for n in self.names}
+        if getattr(self, "_recv", None) is None:
+            self._recv = torch.empty_like(self.flat)       # receive buffer of the all_to_all, kept across jobs
+        return reduce_flat_stats(self.flat, self.acc_flat, self.offsets, self.acc_offsets, shapes, counts, _KernelOps,
+                                 group=group, dst=dst, recv=self._recv)
 
     def states(self) -> Dict[str, "MCMoments | MCSqErr"]:
         out: Dict[str, object] = {}
@@ -246,6 +269,66 @@ class PhiloxSampler:
         _lib.check(_lib.lib().pulpo_gauss_sample_multi(self._arr, len(self.levels), self.seed, cnt, first, stride, 1.0, st),
                    "gauss_sample_multi")
         return self.z
+
+
+def reduce_flat_stats(flat, acc_flat, offsets, acc_offsets, shapes, counts, ops, group=None, dst: int = 0, recv=None):
+    """Multi-GPU reduction of flat MC statistics straight to the reported maps (evaluate.py:243-251, 1538), sized for
+    NVSwitch.  ``flat``: [2, T] (means | M2s) of all tracked maps back to back, ``acc_flat``: [TA] squared-error sums,
+    both padded so that the world size divides them; ``counts[r]`` = samples rank r ran (known on the host).
+
+    Every rank owns 1/W of the flat state: two ``all_to_all`` (means, M2s) hand rank r slice r of every rank's state --
+    each rank sends its state once, all links busy at once, no packing pass -- and a ``reduce_scatter`` sums the
+    squared errors; the rank Chan-merges its W partial slices in rank order (deterministic), turns them into the
+    unbiased std / the MSE, and ONE ``gather`` brings those result slices to ``dst``, which forms the channel means."""
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    W = dist.get_world_size(group) if multi else 1
+    rank = dist.get_rank(group) if multi else 0
+    N = int(sum(counts))
+    T, TA = flat.shape[1], acc_flat.numel()
+    dev = flat.device
+    if T % W or TA % W:
+        raise RuntimeError("reduce_flat_stats: world size %d does not divide the padded state (%d, %d)" % (W, T, TA))
+    ch, cha = T // W, TA // W
+    if multi:
+        if recv is None:
+            recv = torch.empty_like(flat)
+        dist.all_to_all_single(recv[0], flat[0], group=group)
+        dist.all_to_all_single(recv[1], flat[1], group=group)
+        acc = torch.empty(cha, dtype=torch.float32, device=dev)
+        try:
+            dist.reduce_scatter_tensor(acc, acc_flat, group=group)
+        except (RuntimeError, NotImplementedError):          # gloo (CPU tests): no reduce_scatter
+            tmp = acc_flat.clone()
+            dist.all_reduce(tmp, group=group)
+            acc = tmp[rank * cha:(rank + 1) * cha]
+        mean, m2, seen = recv[0, :ch], recv[1, :ch], int(counts[0])     # rank 0's partial slice, merged into in place
+        for r in range(1, W):
+            if counts[r] > 0:
+                if seen == 0:
+                    mean.copy_(recv[0, r * ch:(r + 1) * ch]); m2.copy_(recv[1, r * ch:(r + 1) * ch])
+                else:
+                    ops.merge(mean, m2, seen, recv[0, r * ch:(r + 1) * ch], recv[1, r * ch:(r + 1) * ch], int(counts[r]))
+                seen += int(counts[r])
+    else:
+        m2, acc = flat[1], acc_flat
+    mine = torch.cat([ops.std(m2.contiguous(), N), acc * (1.0 / N)])
+    if multi:
+        gathered = torch.empty(W, ch + cha, dtype=torch.float32, device=dev) if rank == dst else None
+        dist.gather(mine, list(gathered.unbind(0)) if rank == dst else None,
+                    dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+        if rank != dst:
+            return None
+        std_flat = gathered[:, :ch].reshape(-1)
+        mse_flat = gathered[:, ch:].reshape(-1)
+    else:
+        std_flat, mse_flat = mine[:T], mine[T:]
+    out = {}
+    for n, (o, k) in offsets.items():
+        out[n] = std_flat[o:o + k].view(shapes[n]).mean(dim=0)
+    for n, (o, k) in acc_offsets.items():
+        out[n + ":mse"] = mse_flat[o:o + k].view(shapes[n])[0]
+    return out
 
 
 def sliced_uncertainty(states: Dict[str, "MCMoments | MCSqErr"], group=None, dst: int = 0, device=None):

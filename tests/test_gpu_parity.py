@@ -1205,3 +1205,6 @@ def test_streaming_stats_graph_matches_mcmoments(PF):
     assert torch.equal(out["b:sqerr"].acc, sq.acc)
     one = mc.sliced_uncertainty(out)
     assert torch.equal(one["a"], ref["a"].std_channel_mean()) and torch.equal(one["b:mse"], sq.mse())
+    flat = st.reduce_to_maps([7])                 # the flat (multi-GPU) reduction path at world size 1
+    torch.testing.assert_close(flat["a"], ref["a"].std_channel_mean(), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(flat["b:mse"], sq.mse()[0], rtol=1e-6, atol=1e-9)

@@ -193,3 +193,50 @@ def test_sliced_all_to_all_reduction_three_ranks(tmp_path):
     torch.testing.assert_close(got["final0"], stack.std(dim=0).mean(dim=0), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(got["moved0"], moved.std(dim=0).mean(dim=0), rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(got["moved0:mse"], ((moved - _target()) ** 2).mean(dim=0)[0], rtol=1e-5, atol=1e-8)
+
+
+
+def _worker_flat(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # flat per-rank statistics as StreamingStats lays them out: [mean | M2] of both maps back to back, padded
+        shapes = {"final0": SHAPE, "moved0": (1,) + SHAPE[1:]}
+        offsets, off = {}, 0
+        for n, sh in shapes.items():
+            k = int(torch.tensor(sh).prod())
+            offsets[n] = (off, k)
+            off += k
+        pad = -(-off // 5040) * 5040
+        flat = torch.zeros(2, pad)
+        acc_flat = torch.zeros(5040)
+        acc_offsets = {"moved0": (0, offsets["moved0"][1])}
+        ids = mc.shard_samples(N_SAMPLES, rank, world)
+        for c, i in enumerate(ids):
+            maps = _sample(i, mc.sample_generator(123, i, "cpu"))
+            for n, (o, k) in offsets.items():
+                TorchCpuOps.update(maps[n].reshape(-1), flat[0, o:o + k], flat[1, o:o + k], c + 1)
+            TorchCpuOps.sqerr(maps["moved0"].reshape(-1), _target().reshape(-1), acc_flat[:acc_offsets["moved0"][1]], c == 0)
+        counts = [len(mc.shard_samples(N_SAMPLES, r, world)) for r in range(world)]
+        res = mc.reduce_flat_stats(flat, acc_flat, offsets, acc_offsets, shapes, counts, TorchCpuOps, dst=0)
+        if rank == 0:
+            torch.save(res, os.path.join(out_dir, "flat.pt"))
+        else:
+            assert res is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.timeout(180)
+def test_flat_all_to_all_reduction(tmp_path, world):
+    """reduce_flat_stats (what StreamingStats.reduce_to_maps runs on the GPUs): all_to_all of 1/W slices, Chan merge
+    per slice, gather of std / MSE -- against the stack-based numbers of evaluate.py:243-251, 1538."""
+    port = _free_port()
+    mp.spawn(_worker_flat, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "flat.pt"))
+    stack = torch.stack([_sample(i, mc.sample_generator(123, i, "cpu"))["final0"] for i in range(N_SAMPLES)])
+    moved = torch.stack([_sample(i, mc.sample_generator(123, i, "cpu"))["moved0"] for i in range(N_SAMPLES)])
+    torch.testing.assert_close(got["final0"], stack.std(dim=0).mean(dim=0), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(got["moved0"], moved.std(dim=0).mean(dim=0), rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(got["moved0:mse"], ((moved - _target()) ** 2).mean(dim=0)[0], rtol=1e-5, atol=1e-8)
