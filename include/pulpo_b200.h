@@ -306,6 +306,12 @@ int pulpo_gauss_sample_multi(const pulpo_gauss_level *levels, int nlevels, unsig
                              const int *count_dev, int first_id, int id_stride, float var,
                              pulpo_stream_t stream);
 
+/* Multi-GPU reduction of the MC statistics (config 3): after the all_to_all a rank holds `nparts` partial
+ * (mean, M2) slices of `chunk` elements back to back (part r at r * chunk, counts[r] samples, HOST array,
+ * nparts <= 16); one pass Chan-merges them in part order and writes the unbiased std of the union. */
+int pulpo_moments_merge_std(const float *mean_parts, const float *m2_parts, const int *counts,
+                            int nparts, long long chunk, float *std_out, pulpo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

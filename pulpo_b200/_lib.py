@@ -85,6 +85,7 @@ SIGNATURES = {
     "pulpo_moments_merge": (_i, [_vp, _vp, _i, _vp, _vp, _i, _ll, _vp]),
     "pulpo_moments_std": (_i, [_vp, _vp, _i, _ll, _vp]),
     "pulpo_gauss_sample_multi": (_i, [ctypes.POINTER(GaussLevel), _i, ctypes.c_ulonglong, _vp, _i, _i, _f, _vp]),
+    "pulpo_moments_merge_std": (_i, [_vp, _vp, ctypes.POINTER(ctypes.c_int), _i, _ll, _vp, _vp]),
     "pulpo_moments_update_multi": (_i, [ctypes.POINTER(MomentsMap), _i, _vp, _vp]),
     "pulpo_counter_add": (_i, [_vp, _i, _i, _vp]),
     "pulpo_loss_total": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp]),

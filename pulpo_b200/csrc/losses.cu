@@ -564,6 +564,39 @@ gauss_sample_multi_kernel(const GaussLevels lv, unsigned long long seed, const i
     }
 }
 
+// Chan merge of W partial (mean, M2) slices in rank order and the unbiased std of the result in one pass (the reduction
+// of MC statistics after the all_to_all: part r of a statistic sits at r * chunk).  Sequential merge in registers: same
+// arithmetic and order as W - 1 calls of moments_merge_kernel followed by moments_std_kernel.
+constexpr int MS_MAXW = 16;
+struct MergeCounts {
+    int w;
+    int n[MS_MAXW];
+};
+__global__ void __launch_bounds__(256)
+moments_merge_std_kernel(const float *__restrict__ mean_parts, const float *__restrict__ m2_parts, const MergeCounts c, i64 chunk,
+                         float inv_nm1, float *__restrict__ std_out)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < chunk; i += (i64)gridDim.x * blockDim.x) {
+        float mean = 0.0f, m2 = 0.0f;
+        int seen = 0;
+        for (int r = 0; r < c.w; ++r) {
+            const int nb = c.n[r];
+            if (nb == 0) continue;
+            const float mb = mean_parts[r * chunk + i], qb = m2_parts[r * chunk + i];
+            if (seen == 0) {
+                mean = mb; m2 = qb;
+            } else {
+                const float tot = (float)(seen + nb);
+                const float d = mb - mean;
+                mean += d * ((float)nb / tot);
+                m2 += qb + d * d * ((float)seen * (float)nb / tot);
+            }
+            seen += nb;
+        }
+        std_out[i] = sqrtf(m2 * inv_nm1);
+    }
+}
+
 }  // namespace pulpo
 
 using namespace pulpo;
@@ -808,6 +841,26 @@ extern "C" int pulpo_gauss_sample_multi(const pulpo_gauss_level *levels, int nle
     }
     gauss_sample_multi_kernel<<<grid_for((biggest + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(g, seed, count_dev, first_id,
                                                                                                  id_stride, var);
+    return launch_status();
+}
+
+extern "C" int pulpo_moments_merge_std(const float *mean_parts, const float *m2_parts, const int *counts, int nparts,
+                                       long long chunk, float *std_out, pulpo_stream_t stream)
+{
+    PULPO_NVTX("pulpo_moments_merge_std");
+    PULPO_REQUIRE(mean_parts && m2_parts && counts && std_out, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(nparts >= 1 && nparts <= MS_MAXW && chunk > 0, PULPO_ERR_INVALID_SHAPE);
+    MergeCounts c;
+    c.w = nparts;
+    long long total = 0;
+    for (int r = 0; r < nparts; ++r) {
+        PULPO_REQUIRE(counts[r] >= 0, PULPO_ERR_INVALID_SHAPE);
+        c.n[r] = counts[r];
+        total += counts[r];
+    }
+    PULPO_REQUIRE(total >= 2, PULPO_ERR_INVALID_SHAPE);
+    moments_merge_std_kernel<<<grid_for(chunk, 256, 8), 256, 0, (cudaStream_t)stream>>>(mean_parts, m2_parts, c, chunk,
+                                                                                       1.0f / (float)(total - 1), std_out);
     return launch_status();
 }
 

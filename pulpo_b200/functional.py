@@ -562,3 +562,13 @@ def global_ncc(a, v, scale_a=1.0, scale_v=1.0, square_a=False):
     check(lib.pulpo_global_ncc(_ptr(a), _ptr(v), float(scale_a), float(scale_v), int(bool(square_a)), a.numel(), _ptr(out),
                                _ptr(ws), ws.numel(), _stream()), "global_ncc")
     return out
+
+
+def moments_merge_std(mean_parts, m2_parts, counts, chunk, out):
+    """Chan merge of len(counts) partial (mean, M2) slices of ``chunk`` elements (part r at r * chunk) in part order
+    and the unbiased std of the union, written to ``out`` -- one launch (multi-GPU MC reduction)."""
+    import ctypes
+    arr = (ctypes.c_int * len(counts))(*[int(c) for c in counts])
+    check(_lib.lib().pulpo_moments_merge_std(_ptr(mean_parts), _ptr(m2_parts), arr, len(counts), int(chunk), _ptr(out), _stream()),
+          "moments_merge_std")
+    return out

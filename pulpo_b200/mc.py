@@ -52,6 +52,10 @@ class _KernelOps:
         PF.sqerr_update(x, y, acc, first)
 
     @staticmethod
+    def merge_std(mean_parts, m2_parts, counts, chunk, out):
+        return PF.moments_merge_std(mean_parts, m2_parts, counts, chunk, out)
+
+    @staticmethod
     def global_ncc(a, v, scale_a, scale_v, square_a):
         return PF.global_ncc(a, v, scale_a, scale_v, square_a)
 
@@ -302,17 +306,22 @@ def reduce_flat_stats(flat, acc_flat, offsets, acc_offsets, shapes, counts, ops,
             tmp = acc_flat.clone()
             dist.all_reduce(tmp, group=group)
             acc = tmp[rank * cha:(rank + 1) * cha]
-        mean, m2, seen = recv[0, :ch], recv[1, :ch], int(counts[0])     # rank 0's partial slice, merged into in place
-        for r in range(1, W):
-            if counts[r] > 0:
-                if seen == 0:
-                    mean.copy_(recv[0, r * ch:(r + 1) * ch]); m2.copy_(recv[1, r * ch:(r + 1) * ch])
-                else:
-                    ops.merge(mean, m2, seen, recv[0, r * ch:(r + 1) * ch], recv[1, r * ch:(r + 1) * ch], int(counts[r]))
-                seen += int(counts[r])
+        mine = torch.empty(ch + cha, dtype=torch.float32, device=dev)
+        if hasattr(ops, "merge_std"):          # one pass: Chan merge of the W partial slices in rank order + unbiased std
+            ops.merge_std(recv[0], recv[1], [int(c) for c in counts], ch, mine[:ch])
+        else:
+            mean, m2, seen = recv[0, :ch], recv[1, :ch], int(counts[0])     # rank 0's partial slice, merged into in place
+            for r in range(1, W):
+                if counts[r] > 0:
+                    if seen == 0:
+                        mean.copy_(recv[0, r * ch:(r + 1) * ch]); m2.copy_(recv[1, r * ch:(r + 1) * ch])
+                    else:
+                        ops.merge(mean, m2, seen, recv[0, r * ch:(r + 1) * ch], recv[1, r * ch:(r + 1) * ch], int(counts[r]))
+                    seen += int(counts[r])
+            mine[:ch] = ops.std(m2.contiguous(), N)
+        torch.mul(acc, 1.0 / N, out=mine[ch:])
     else:
-        m2, acc = flat[1], acc_flat
-    mine = torch.cat([ops.std(m2.contiguous(), N), acc * (1.0 / N)])
+        mine = torch.cat([ops.std(flat[1].contiguous(), N), acc_flat * (1.0 / N)])
     if multi:
         gathered = torch.empty(W, ch + cha, dtype=torch.float32, device=dev) if rank == dst else None
         dist.gather(mine, list(gathered.unbind(0)) if rank == dst else None,

@@ -1208,3 +1208,24 @@ def test_streaming_stats_graph_matches_mcmoments(PF):
     flat = st.reduce_to_maps([7])                 # the flat (multi-GPU) reduction path at world size 1
     torch.testing.assert_close(flat["a"], ref["a"].std_channel_mean(), rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(flat["b:mse"], sq.mse()[0], rtol=1e-6, atol=1e-9)
+
+
+def test_moments_merge_std_kernel_equals_sequential_chan_merges(PF):
+    """The one-pass W-way merge + std of the multi-GPU MC reduction == W - 1 pairwise Chan merges then std
+    (same arithmetic, same order), including a part that saw no samples."""
+    from pulpo_b200 import mc
+    g = torch.Generator(device="cuda").manual_seed(8)
+    chunk, counts = 5003, [3, 0, 4, 2]
+    parts = []
+    for c in counts:
+        st = mc.MCMoments((chunk,), "cuda")
+        for _ in range(c):
+            st.update(torch.randn(chunk, device="cuda", generator=g) * 2.0 + 1.0)
+        parts.append(st)
+    mean_parts = torch.cat([p.mean for p in parts]); m2_parts = torch.cat([p.m2 for p in parts])
+    out = torch.empty(chunk, device="cuda")
+    PF.moments_merge_std(mean_parts, m2_parts, counts, chunk, out)
+    ref = mc.MCMoments((chunk,), "cuda")
+    for p in parts:
+        ref.merge_state(p.mean, p.m2, p.count)
+    assert torch.equal(out, ref.std())
