@@ -24,6 +24,8 @@
 //     window core, 128-bit LDS of two (I,J) pairs), keeps the W-plane z window of its two outputs as
 //     a register ring, and writes 64-bit results.
 // Algorithmic bytes: fwd 8 B/voxel (+12 when saving a,b,c), bwd 12 B/voxel (+12 reading a,b,c).
+#include <type_traits>
+
 #include <cuda.h>   // CUtensorMap and its enums; cuTensorMapEncodeTiled is looked up at run time
 
 #include "ncc_common.cuh"
@@ -39,6 +41,20 @@ constexpr int NT_PADL = 4;        // the box starts at x0 - 4: TMA needs a 16-by
 constexpr int NT_STAGES = 3;
 constexpr int NT_RY = 4;          // output rows per pass-1 work item
 constexpr int NT_YC = NT_TX + 2 * NT_PADL;   // columns of the y-summed arrays (pitch: 40 float2 = 320 B)
+
+// compile-time loop with early exit: f(integral_constant<int, I>) for I = 0 .. N-1 until it returns false
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for_impl(F &f)
+{
+    if constexpr (I < N) {
+        if (f(std::integral_constant<int, I>{})) static_for_impl<I + 1, N>(f);
+    }
+}
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    static_for_impl<0, N>(f);
+}
 
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
 
@@ -184,6 +200,9 @@ ncc_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
             rC[s][0] = rC[s][1] = 0.0f;
         }
 
+        if constexpr (FWD) {
+        // forward: pass 1 and pass 2 of a plane back to back across the plane barrier (its two 45-register z rings leave
+        // no room to overlap the passes of consecutive planes: the pipelined order below spills, 96 -> 110 us)
         for (int p0 = 0; p0 < nplanes; p0 += W) {
 #pragma unroll
             for (int s = 0; s < W; ++s) {
@@ -324,6 +343,174 @@ ncc_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                     }
                 }
             }
+        }
+        } else {
+        // backward: software-pipelined across the plane barrier (79 -> 70 us at 160x192x224)
+        // Pass 2 (x sums into ring slot SLOT) + z window + epilogue of plane `pl`, from the y sums in buffer pl & 1.
+        // Called one barrier interval AFTER the plane's pass 1: in every interval a thread runs pass 1 of plane pl and
+        // pass 2 of plane pl - 1, two independent instruction streams, instead of the two passes of one plane back to
+        // back across the barrier -- the kernel is bound by the length of the per-plane dependency chain (measured:
+        // skipping the arithmetic of all-zero planes changed nothing), not by throughput.
+        constexpr bool PIPE = true;
+        auto pass2 = [&](auto slot_c, const int pl, const float2 Iv, const float2 Jv) {
+            constexpr int SLOT = decltype(slot_c)::value;
+            float *ybuf = ys + (pl & 1) * L::YS_FLOATS;
+            const float2 *YA = reinterpret_cast<const float2 *>(ybuf);
+            const float2 *YB = reinterpret_cast<const float2 *>(ybuf + L::YA_FLOATS);
+            const float *YC = ybuf + L::YA_FLOATS * (FWD ? 2 : 1);
+            const int zout = z_start + pl - 2 * R;
+            {
+                float2 PA[NP], PB[NP];
+                float PC[NP];
+                const int cb = ty * NT_YC + 2 * xp + XOFF;   // first y-summed column of this thread's windows
+                if ((XOFF & 1) == 0) {
+#pragma unroll
+                    for (int t = 0; t < NP / 2; ++t) {
+                        const float4 qa = *reinterpret_cast<const float4 *>(YA + cb + 2 * t);
+                        PA[2 * t] = make_float2(qa.x, qa.y); PA[2 * t + 1] = make_float2(qa.z, qa.w);
+                        if (FWD) {
+                            const float4 qb = *reinterpret_cast<const float4 *>(YB + cb + 2 * t);
+                            PB[2 * t] = make_float2(qb.x, qb.y); PB[2 * t + 1] = make_float2(qb.z, qb.w);
+                        }
+                        const float2 qc = *reinterpret_cast<const float2 *>(YC + cb + 2 * t);
+                        PC[2 * t] = qc.x; PC[2 * t + 1] = qc.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < NP; ++t) {
+                        PA[t] = YA[cb + t];
+                        if (FWD) PB[t] = YB[cb + t];
+                        PC[t] = YC[cb + t];
+                    }
+                }
+                float2 coreA = PA[1];
+                float coreC = PC[1];
+#pragma unroll
+                for (int t = 2; t < W; ++t) {
+                    coreA = add2(coreA, PA[t]);
+                    coreC = add2(coreC, PC[t]);
+                }
+                rA[SLOT][0] = add2(PA[0], coreA);
+                rA[SLOT][1] = add2(coreA, PA[W]);
+                rC[SLOT][0] = add2(PC[0], coreC);
+                rC[SLOT][1] = add2(coreC, PC[W]);
+                if (FWD) {
+                    float2 coreB = PB[1];
+#pragma unroll
+                    for (int t = 2; t < W; ++t) coreB = add2(coreB, PB[t]);
+                    rB[FWD ? SLOT : 0][0] = add2(PB[0], coreB);
+                    rB[FWD ? SLOT : 0][1] = add2(coreB, PB[W]);
+                }
+            }
+            // ---------------- z window + epilogue
+            if (pl >= 2 * R && live) {
+                const i64 off = obase + (i64)zout * sz;
+                float ra[2], rb[2], rc[2];
+#pragma unroll
+                for (int o = 0; o < 2; ++o) {
+                    float2 sA = rA[0][o], sB = FWD ? rB[0][o] : make_float2(0.f, 0.f);
+                    float sC = rC[0][o];
+#pragma unroll
+                    for (int u = 1; u < W; ++u) {
+                        sA = add2(sA, rA[u][o]);
+                        if (FWD) sB = add2(sB, rB[u % (FWD ? W : 1)][o]);
+                        sC = add2(sC, rC[u][o]);
+                    }
+                    if (FWD) {
+                        if (p.o0) {
+                            const NccPoint r = ncc_point<true>(sA.x, sA.y, sB.x, sB.y, sC, p.Wf, p.rcpW);
+                            cc_acc += r.cc;
+                            ra[o] = r.a; rb[o] = r.b; rc[o] = r.c;
+                        } else {
+                            cc_acc += ncc_point<false>(sA.x, sA.y, sB.x, sB.y, sC, p.Wf, p.rcpW).cc;
+                        }
+                    } else {
+                        const float iv = o ? Iv.y : Iv.x, jv = o ? Jv.y : Jv.x;
+                        ra[o] = gk * (iv * sA.x + sA.y + 2.0f * jv * sC);
+                    }
+                }
+                if (FWD) {
+                    if (p.o0) {
+                        *reinterpret_cast<float2 *>(p.o0 + off) = make_float2(ra[0], ra[1]);
+                        *reinterpret_cast<float2 *>(p.o1 + off) = make_float2(rb[0], rb[1]);
+                        *reinterpret_cast<float2 *>(p.o2 + off) = make_float2(rc[0], rc[1]);
+                    }
+                } else {
+                    *reinterpret_cast<float2 *>(p.o0 + off) = make_float2(ra[0], ra[1]);
+                }
+            }
+        };
+
+        float2 Iv_prev = make_float2(0.f, 0.f), Jv_prev = Iv_prev;   // backward epilogue operands of the plane whose pass 2 is pending
+        for (int p0 = 0; p0 <= nplanes; p0 += W) {
+            static_for<W>([&](auto s_c) -> bool {      // ring slot s is a compile-time constant: the rings stay in registers
+                constexpr int s = decltype(s_c)::value;
+                const int pl = p0 + s;
+                if (pl > nplanes) return false;
+                const bool have = pl < nplanes;       // the last turn only drains pass 2 of the final plane
+                const unsigned int st = (gp + pl) % NT_STAGES, par = ((gp + pl) / NT_STAGES) & 1u;
+                float *ybuf = ys + (pl & 1) * L::YS_FLOATS;
+                float2 *YA = reinterpret_cast<float2 *>(ybuf);
+                float2 *YB = reinterpret_cast<float2 *>(ybuf + L::YA_FLOATS);
+                float *YC = ybuf + L::YA_FLOATS * (FWD ? 2 : 1);
+                const int zout = z_start + pl - 2 * R;
+                // backward epilogue operands: requested now, used one interval later
+                float2 Iv = make_float2(0.f, 0.f), Jv = Iv;
+                if (!FWD && have && pl >= 2 * R && live) {
+                    Iv = __ldg(reinterpret_cast<const float2 *>(p.I + obase + (i64)zout * sz));
+                    Jv = __ldg(reinterpret_cast<const float2 *>(p.J + obase + (i64)zout * sz));
+                }
+                if (have) mbar_wait(bar_s + 8 * st, par);
+                // ---------------- pass 1: y sums of the staged plane (products formed in registers).  Scalar loads
+                // let (I, J) land in one register pair, so everything downstream is packed FADD2 / FMUL2.
+                if (has_item && have) {
+                    const float *r0 = raw + st * NIN * L::RAW_FLOATS + (NT_RY * yrg) * NT_BOXW + XOFF + yc;
+                    float2 a[NVY], b[NVY];
+                    float c[NVY];
+#pragma unroll
+                    for (int j = 0; j < NVY; ++j) {
+                        a[j] = make_float2(r0[j * NT_BOXW], r0[L::RAW_FLOATS + j * NT_BOXW]);
+                        if (FWD) {
+                            b[j] = __fmul2_rn(a[j], a[j]);
+                            c[j] = __fmul_rn(a[j].x, a[j].y);
+                        } else {
+                            b[j] = make_float2(0.f, 0.f);
+                            c[j] = r0[2 * L::RAW_FLOATS + j * NT_BOXW];
+                        }
+                    }
+                    float2 oA[4], oB[4];
+                    float oC[4];
+                    xsum4<W>(a, oA);
+                    if (FWD) xsum4<W>(b, oB);
+                    xsum4<W>(c, oC);
+#pragma unroll
+                    for (int o = 0; o < NT_RY; ++o) {
+                        const int idx = (NT_RY * yrg + o) * NT_YC + XOFF + yc;
+                        YA[idx] = oA[o];
+                        if (FWD) YB[idx] = oB[o];
+                        YC[idx] = oC[o];
+                    }
+                }
+                // ---------------- pass 2 + epilogue of the PREVIOUS plane (its y sums were published by the last barrier)
+                if (PIPE) {
+                    if (pl > 0) pass2(std::integral_constant<int, (s + W - 1) % W>{}, pl - 1, Iv_prev, Jv_prev);
+                    Iv_prev = Iv; Jv_prev = Jv;
+                }
+                __syncthreads();
+                // the staged plane has been consumed by every thread: refill its slot
+                if (tid == 0 && have && pl + NT_STAGES < nplanes) {
+                    const unsigned int bar = bar_s + 8 * st, dst = raw_s + st * NIN * L::RAW_FLOATS * 4;
+                    const int zin = z_start - R + pl + NT_STAGES;
+                    mbar_expect_tx(bar, STAGE_BYTES);
+                    tma_load_box(dst, &tm0, bar, x0 - NT_PADL, y0 - R, zin, bc);
+                    tma_load_box(dst + L::RAW_FLOATS * 4, &tm1, bar, x0 - NT_PADL, y0 - R, zin, bc);
+                    if (!FWD) tma_load_box(dst + 2 * L::RAW_FLOATS * 4, &tm2, bar, x0 - NT_PADL, y0 - R, zin, bc);
+                }
+                // not pipelined: the two passes of the same plane, back to back across the barrier
+                if (!PIPE && have) pass2(std::integral_constant<int, s>{}, pl, Iv, Jv);
+                return true;
+            });
+        }
         }
         gp += (unsigned int)nplanes;
     }
