@@ -57,7 +57,9 @@ int pulpo_warp3d_fwd(const float *img, const float *df, float *out, int32_t *idx
                      int B, int C, int D0, int D1, int D2, int coord_mode, pulpo_stream_t stream);
 
 /* grid_sampler_3d_backward + the autograd chain of network_blocks.py:103-117.
- * gimg (nullable): ACCUMULATED into with vector/scalar red.global.add -> caller zeroes it.
+ * gimg (nullable): ACCUMULATED into with red.global.add.f32 -> caller zeroes it.  The contributions of
+ *   neighbouring lanes whose footprints share a corner column are combined by warp shuffle first (about 4
+ *   instead of 8 reductions per voxel and channel, no intra-warp address collisions for a smooth field).
  * gdf (nullable): overwritten; zero where the border clamp is active. */
 int pulpo_warp3d_bwd(const float *gout, const float *img, const float *df, float *gimg, float *gdf,
                      int B, int C, int D0, int D1, int D2, int coord_mode, pulpo_stream_t stream);
@@ -117,8 +119,12 @@ typedef struct pulpo_vecint_level {
     size_t scratch_bytes; /* bwd only */
     int D0, D1, D2;
 } pulpo_vecint_level;
-/* Batches of large volumes (>= 2^19 voxels per item over all levels) run one item after the other so that one
- * item's states stay L2-resident; small volumes share one launch. */
+/* Batches of large volumes (>= 2^19 voxels per item summed over the levels of the call) run one item after the
+ * other so that one item's states stay L2-resident; small volumes share one launch.  The layout of the saved states
+ * inside `ws` follows that decision ([B][steps][S] vs [steps][B][S]) and is opaque: the backward MUST be called with
+ * the same (B, nsteps, level set) as the forward that filled `ws` -- pulpo_vecint_fwd with pulpo_vecint_bwd,
+ * pulpo_vecint_multi_fwd with pulpo_vecint_multi_bwd over the same levels[] (what _VecInt and HotPathPlan do).
+ * Mixing them for B > 1 reads the states of the wrong item. */
 int pulpo_vecint_multi_fwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int save_steps,
                            int B, int coord_mode, pulpo_stream_t stream);
 int pulpo_vecint_multi_bwd(const pulpo_vecint_level *levels, int nlevels, int nsteps, int B,
