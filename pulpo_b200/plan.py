@@ -121,7 +121,12 @@ class HotPathPlan:
         self.pool_pyramid = bool(pool_pyramid) and 1 <= npool <= 4 and all(s % edge == 0 for s in self.full)
         self.aux_early = bool(aux_early)
         self.multi_stream = multi_stream
-        self.streams = [torch.cuda.Stream(device=dev) for _ in range(L + 1)] if multi_stream else None
+        # level 0 carries the critical path: its stream gets the highest priority, so that its persistent kernels are not
+        # kept waiting for CTA slots by the small kernels of the coarser levels / the aux stream (PULPO_PLAN_PRIO=0: off)
+        import os
+        prio = os.environ.get("PULPO_PLAN_PRIO", "1") != "0"
+        self.streams = [torch.cuda.Stream(device=dev, priority=(-1 if (prio and l == 0) else 0)) for l in range(L + 1)] \
+            if multi_stream else None
         self.launches = 0
 
     # ------------------------------------------------------------------------------------------
