@@ -355,7 +355,7 @@ def run_ours(args):
     nvox = size[0] * size[1] * size[2]
     B = args.batch
     plan_kw = dict(fuse_reg=bool(args.fuse_reg), fuse_combine=bool(args.fuse_combine), pool_pyramid=bool(args.pool_pyramid),
-                   aux_early=bool(args.aux_early))
+                   aux_early=bool(args.aux_early), dpos=bool(args.dpos))
     x_h, y_h, d_h, m_h, s_h = syn.make_hot_path_inputs(size, total, latent, seed=rank, batch=B,
                                                        field_sigma_vox=args.field_sigma_vox, max_abs=args.field_max_abs)
     host = [x_h, y_h] + [d_h[l] for l in range(latent)] + [m_h[l] for l in range(latent)] + [s_h[l] for l in range(latent)]
@@ -910,6 +910,7 @@ def main():
     ap.add_argument("--engine", default="plan", choices=["plan", "autograd"],
                     help="plan: pre-planned multi-stream C-ABI sequence; autograd: the drop-in nn.Modules")
     ap.add_argument("--fuse-reg", type=int, default=1, help="plan engine: L2_reg fused into the warp kernels (1) or separate kernels (0)")
+    ap.add_argument("--dpos", type=int, default=1, help="plan engine: the warp forward stores d out / d df and the backward is a streaming product inside the regulariser's pass (1) or the gather-form warp backward (0)")
     ap.add_argument("--fuse-combine", type=int, default=0, help="plan engine: pyramid combination inside the integration launches (1) or separate launches (0)")
     ap.add_argument("--pool-pyramid", type=int, default=1, help="plan engine: moving-image pyramid in one launch (1) or one launch per level (0)")
     ap.add_argument("--aux-early", type=int, default=0, help="plan engine: pyramid + KL start with the step (1) or after the integration (0)")

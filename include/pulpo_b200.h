@@ -76,6 +76,18 @@ int pulpo_warp3d_bwd_img(const float *gout, const float *img, const float *df, f
                          float *gdf, int B, int C, int D0, int D1, int D2, int I0, int I1, int I2,
                          int coord_mode, pulpo_stream_t stream);
 
+/* a2 with the backward's gather half prepared by the forward (one image channel, the hot path's level warps,
+ * src/components/pulpo.py:317).  dpos [B,3,D0,D1,D2] = d out / d df: the spatial gradient of the interpolant at the
+ * sample point, masked where the border clamp is active and scaled by the autograd chain of
+ * network_blocks.py:103-117 -- exactly what pulpo_warp3d_bwd multiplies gout with.  The backward is then the
+ * streaming product gdf (+)= gout * dpos (pulpo_warp3d_bwd_dpos, gout [B,1,...], gdf [B,3,...]), or the same product
+ * inside the regulariser's pass over the field (pulpo_l2reg_fwd_bwd): no second position chain and no second round
+ * of corner gathers in the backward. */
+int pulpo_warp3d_fwd_dpos(const float *img, const float *df, float *out, float *dpos, int B, int D0, int D1,
+                          int D2, int coord_mode, pulpo_stream_t stream);
+int pulpo_warp3d_bwd_dpos(const float *gout, const float *dpos, float *gdf, int accumulate, int B, int D0,
+                          int D1, int D2, pulpo_stream_t stream);
+
 /* a2 fused with f-1 (L2_reg, src/losses.py:208-222): the warp and the regulariser read the same
  * full-resolution field in the same step (src/models.py:160-162).  reg_out (device scalar) =
  * L2_reg(df, lamb); ws: pulpo_reduce_ws_bytes() bytes, zeroed once by the caller. */
@@ -231,6 +243,14 @@ int pulpo_l2reg_fwd(const float *f, float lamb, float *out, void *ws, size_t ws_
 /* accumulate != 0: gf += ... (lets the caller fold this gradient into the warp's gdf) */
 int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, float *gf, int accumulate,
                     int B, int C, int D0, int D1, int D2, pulpo_stream_t stream);
+
+/* value and gradient in one pass (the plan's form: weights folded, no upstream scalar): out = L2_reg(f, lamb),
+ * gf (+)= d out / d f  [+ gout * dpos].  gout [B,1,D0,D1,D2] and dpos [B,C,D0,D1,D2] (both or neither): the warp's
+ * gather-half backward (pulpo_warp3d_fwd_dpos) rides in the same pass, so the field gradient is written once.
+ * ws: pulpo_reduce_ws_bytes() bytes, zeroed once by the caller. */
+int pulpo_l2reg_fwd_bwd(const float *f, float lamb, float *out, const float *gout, const float *dpos,
+                        float *gf, int accumulate, void *ws, size_t ws_bytes, int B, int C, int D0, int D1,
+                        int D2, pulpo_stream_t stream);
 
 /* ---- f-2: jacobian_det(deformation_field, normalize) / JDetStd   src/losses.py:147-204 (3-D branch) ----
  * det: [B,D0,D1,D2] (the reference returns jacobian[:,0,0]-shaped maps).  Replication-padded central

@@ -48,6 +48,8 @@ SIGNATURES = {
     "pulpo_warp3d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_warp3d_fwd_img": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_warp3d_bwd_img": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_warp3d_fwd_dpos": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_warp3d_bwd_dpos": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "pulpo_warp3d_l2reg_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_warp3d_l2reg_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_vecint_ws_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
@@ -75,6 +77,7 @@ SIGNATURES = {
     "pulpo_kl_n01_multi": (_i, [ctypes.POINTER(KlLevel), _i, _f, _i, _vp, _sz, _vp]),
     "pulpo_l2reg_fwd": (_i, [_vp, _f, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "pulpo_l2reg_bwd": (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_l2reg_fwd_bwd": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _i, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "pulpo_jacdet_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "pulpo_jacdet_bwd_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "pulpo_jacdet_bwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),

@@ -344,6 +344,181 @@ l2reg_bwd_v4_kernel(const float *__restrict__ gloss, const float *__restrict__ f
     *o = make_float4(r[0], r[1], r[2], r[3]);
 }
 
+// Value AND gradient of L2_reg in one pass over the field (the hot-path plan's form: the loss weights are folded into
+// the kernels, so the gradient does not wait for an upstream scalar).  Same per-voxel arithmetic as the two kernels
+// above; every thread owns 4 consecutive voxels of a row, the five neighbour quads come through L2 (read-once
+// streaming loads), persistent grid so that the value can use the deterministic two-stage reduction.
+// PROD: gf additionally receives gout * dpos -- the gather half of the warp's backward when its forward stored dpos
+// (warp3d.cu, pulpo_warp3d_fwd_dpos); gout has one channel per batch item, f / dpos / gf have C.
+template <bool ACC, bool PROD>
+__global__ void __launch_bounds__(256)
+l2reg_fwd_bwd_v4_kernel(const float *__restrict__ f, float *__restrict__ gf, float kk, float *out, ReduceWs *ws,
+                        double scale, const float *__restrict__ gout, const float *__restrict__ dpos, int C,
+                        const RowGeom g)
+{
+    __shared__ double red[32];
+    const int sy = g.D2, sz = g.D1 * g.D2;
+    float vacc = 0.0f;
+    for (unsigned int gid = blockIdx.x * 256u + threadIdx.x; gid < g.groups; gid += gridDim.x * 256u) {
+        unsigned int row, xg, zb, y, bc, z;
+        fast_divmod(gid, g.dXG, row, xg);
+        fast_divmod(row, g.dD1, zb, y);
+        fast_divmod(zb, g.dD0, bc, z);
+        const float *p = f + (i64)gid * 4;
+        const float4 c4 = ld_stream4(p);
+        const bool zin = z > 0, yin = y > 0, zn = (int)z + 1 < g.D0, yn = (int)y + 1 < g.D1;
+        float4 pz = make_float4(0.f, 0.f, 0.f, 0.f), py = pz, nz = pz, ny = pz, go = pz, dp = pz;
+        if (PROD) {
+            const unsigned int b = bc / (unsigned int)C;
+            const i64 S4 = (i64)g.D0 * g.D1 * g.XG;                 // quads per channel
+            go = ld_stream4(gout + ((i64)gid - (i64)(bc - b) * S4) * 4);
+            dp = ld_stream4(dpos + (i64)gid * 4);
+        }
+        if (zin) pz = ld_stream4(p - sz);
+        if (yin) py = ld_stream4(p - sy);
+        if (zn) nz = ld_stream4(p + sz);
+        if (yn) ny = ld_stream4(p + sy);
+        const float c[6] = {xg ? __ldg(p - 1) : 0.0f, c4.x, c4.y, c4.z, c4.w, (int)xg + 1 < g.XG ? __ldg(p + 4) : 0.0f};
+        const float pzv[4] = {pz.x, pz.y, pz.z, pz.w}, pyv[4] = {py.x, py.y, py.z, py.w};
+        const float nzv[4] = {nz.x, nz.y, nz.z, nz.w}, nyv[4] = {ny.x, ny.y, ny.z, ny.w};
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = 4 * (int)xg + j;
+            const bool xin = x > 0, xn = x + 1 < g.D2;
+            const float cc = c[j + 1];
+            float a = 0.0f;
+            if (xin && yin && zin) {
+                const float dz = cc - pzv[j], dy = cc - pyv[j], dx = cc - c[j];
+                a += dz + dy + dx;
+                vacc += dz * dz; vacc += dy * dy; vacc += dx * dx;
+            }
+            if (zn && yin && xin) a -= nzv[j] - cc;
+            if (yn && zin && xin) a -= nyv[j] - cc;
+            if (xn && zin && yin) a -= c[j + 2] - cc;
+            r[j] = kk * a;
+        }
+        if (PROD) {
+            r[0] += go.x * dp.x; r[1] += go.y * dp.y; r[2] += go.z * dp.z; r[3] += go.w * dp.w;
+        }
+        float4 *o = reinterpret_cast<float4 *>(gf + (i64)gid * 4);
+        if (ACC) {
+            const float4 old = *o;
+            r[0] += old.x; r[1] += old.y; r[2] += old.z; r[3] += old.w;
+        }
+        *o = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    double bt = block_sum((double)vacc, red);
+    grid_reduce_finish(bt, ws, out, scale, red);
+}
+
+// z-marching form of the kernel above (the default when the volume has >= 8 planes).  The one-plane-per-thread version
+// pulls five neighbour quads of the field through L2 for every quad it produces (~660 MB of L2 traffic for 275 MB of
+// HBM bytes at 160x192x224: L2-bound).  Here a thread owns one quad column and walks a run of planes: the quads of the
+// previous and the next plane are carried in registers, the y neighbours of a plane come from L1 (the rows above and
+// below belong to threads of the same CTA at the same plane), and everything plane z + 1 needs is requested before
+// plane z is computed.
+struct L2MarchGeom {
+    int BC, D0, D1, D2, XG, zrun, nzrun, C;
+    unsigned int items;     // BC * nzrun * D1 * XG
+    FastDiv dXG, dD1, dnz, dC;
+};
+
+struct L2Plane {
+    float4 c, py, ny, go, dp, old;
+    float xl, xr;
+};
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+template <bool ACC, bool PROD>
+__device__ __forceinline__ void l2_plane_load(L2Plane &p, const float *fq, const float *goq, const float *dpq,
+                                              const float *gfq, int sy, bool full, bool yin, bool yn, bool xl_ok, bool xr_ok)
+{
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    p.c = ldg4(fq);
+    p.py = (full && yin) ? ldg4(fq - sy) : z4;
+    p.ny = (full && yn) ? ldg4(fq + sy) : z4;
+    p.xl = (full && xl_ok) ? __ldg(fq - 1) : 0.0f;
+    p.xr = (full && xr_ok) ? __ldg(fq + 4) : 0.0f;
+    if (PROD) {
+        p.go = full ? ld_stream4(goq) : z4;
+        p.dp = full ? ld_stream4(dpq) : z4;
+    }
+    if (ACC) p.old = full ? ld_stream4(gfq) : z4;
+}
+
+template <bool ACC, bool PROD>
+__global__ void __launch_bounds__(256, 3)
+l2reg_fwd_bwd_march_kernel(const float *__restrict__ f, float *__restrict__ gf, float kk, float *out, ReduceWs *ws,
+                           double scale, const float *__restrict__ gout, const float *__restrict__ dpos,
+                           const L2MarchGeom g)
+{
+    __shared__ double red[32];
+    const int sy = g.D2;
+    const i64 sz = (i64)g.D1 * g.D2, S = (i64)g.D0 * sz;
+    float vacc = 0.0f;
+    for (unsigned int it = blockIdx.x * 256u + threadIdx.x; it < g.items; it += gridDim.x * 256u) {
+        // item order: x quad, row, CHANNEL, z run, batch item -- the C channels of a (z run, batch item) are in flight
+        // together, so the one-channel gout they share is read from HBM once and from L2 afterwards
+        unsigned int row, xg, r2, y, r3, ch, b, zr;
+        fast_divmod(it, g.dXG, row, xg);
+        fast_divmod(row, g.dD1, r2, y);
+        fast_divmod(r2, g.dC, r3, ch);
+        fast_divmod(r3, g.dnz, b, zr);
+        const unsigned int bc = b * (unsigned int)g.C + ch;
+        const int z0 = (int)zr * g.zrun, z1 = min(g.D0, z0 + g.zrun);
+        const bool yin = y > 0, yn = (int)y + 1 < g.D1, xl_ok = xg > 0, xr_ok = (int)xg + 1 < g.XG;
+        const i64 q0 = (i64)bc * S + (i64)z0 * sz + (i64)y * g.D2 + 4 * (i64)xg;     // this thread's quad at plane z0
+        const i64 qg = q0 - (i64)(bc - b) * S;                                       // the same quad of gout [B,1,...]
+        const float *fq = f + q0, *goq = PROD ? gout + qg : nullptr, *dpq = PROD ? dpos + q0 : nullptr;
+        float *gfq = gf + q0;
+        float4 prev = z0 > 0 ? ldg4(fq - sz) : make_float4(0.f, 0.f, 0.f, 0.f);
+        L2Plane cur;
+        l2_plane_load<ACC, PROD>(cur, fq, goq, dpq, gfq, sy, true, yin, yn, xl_ok, xr_ok);
+        for (int z = z0; z < z1; ++z) {
+            L2Plane nxt;
+            const bool zn = z + 1 < g.D0, zin = z > 0;
+            if (zn)
+                l2_plane_load<ACC, PROD>(nxt, fq + sz, PROD ? goq + sz : nullptr, PROD ? dpq + sz : nullptr, gfq + sz, sy,
+                                         z + 1 < z1, yin, yn, xl_ok, xr_ok);
+            else
+                nxt.c = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float c[6] = {cur.xl, cur.c.x, cur.c.y, cur.c.z, cur.c.w, cur.xr};
+            const float pzv[4] = {prev.x, prev.y, prev.z, prev.w}, pyv[4] = {cur.py.x, cur.py.y, cur.py.z, cur.py.w};
+            const float nzv[4] = {nxt.c.x, nxt.c.y, nxt.c.z, nxt.c.w}, nyv[4] = {cur.ny.x, cur.ny.y, cur.ny.z, cur.ny.w};
+            float r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x = 4 * (int)xg + j;
+                const bool xin = x > 0, xn = x + 1 < g.D2;
+                const float cc = c[j + 1];
+                float a = 0.0f;
+                if (xin && yin && zin) {
+                    const float dz = cc - pzv[j], dy = cc - pyv[j], dx = cc - c[j];
+                    a += dz + dy + dx;
+                    vacc += dz * dz; vacc += dy * dy; vacc += dx * dx;
+                }
+                if (zn && yin && xin) a -= nzv[j] - cc;
+                if (yn && zin && xin) a -= nyv[j] - cc;
+                if (xn && zin && yin) a -= c[j + 2] - cc;
+                r[j] = kk * a;
+            }
+            if (PROD) {
+                r[0] += cur.go.x * cur.dp.x; r[1] += cur.go.y * cur.dp.y; r[2] += cur.go.z * cur.dp.z; r[3] += cur.go.w * cur.dp.w;
+            }
+            if (ACC) { r[0] += cur.old.x; r[1] += cur.old.y; r[2] += cur.old.z; r[3] += cur.old.w; }
+            *reinterpret_cast<float4 *>(gfq) = make_float4(r[0], r[1], r[2], r[3]);
+            prev = cur.c;
+            cur = nxt;
+            fq += sz; gfq += sz;
+            if (PROD) { goq += sz; dpq += sz; }
+        }
+    }
+    double bt = block_sum((double)vacc, red);
+    grid_reduce_finish(bt, ws, out, scale, red);
+}
+
 // Welford: count = number of samples including x
 __global__ void __launch_bounds__(256)
 moments_update_kernel(const float *__restrict__ x, float *__restrict__ mean, float *__restrict__ m2, float inv_count,
@@ -729,6 +904,71 @@ extern "C" int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, f
             l2reg_bwd_v4_kernel<false><<<(g.groups + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gloss, f, gf, kk, g);
     else
         l2reg_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(gloss, f, gf, kk, B * C, D0, D1, D2, accumulate);
+    return launch_status();
+}
+
+// generic product for the fallback path of pulpo_l2reg_fwd_bwd
+__global__ void __launch_bounds__(256)
+prod_acc_kernel(const float *__restrict__ gout, const float *__restrict__ dpos, float *__restrict__ gf, i64 S, int C, i64 total)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+        const i64 bc = i / S, b = bc / C;
+        gf[i] += gout[i - (bc - b) * S] * dpos[i];
+    }
+}
+
+extern "C" int pulpo_l2reg_fwd_bwd(const float *f, float lamb, float *out, const float *gout, const float *dpos,
+                                   float *gf, int accumulate, void *ws, size_t ws_bytes, int B, int C, int D0, int D1,
+                                   int D2, pulpo_stream_t stream)
+{
+    PULPO_NVTX("pulpo_l2reg_fwd_bwd");
+    PULPO_REQUIRE(f && out && gf && ws, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE((gout == nullptr) == (dpos == nullptr), PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && C > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(ws_bytes >= kReduceWsBytes, PULPO_ERR_WORKSPACE);
+    const i64 total = (i64)B * C * D0 * D1 * D2;
+    const double cnt = (double)B * C * (D0 - 1) * (double)(D1 - 1) * (D2 - 1);
+    const double scale = (double)lamb * D0 * D1 * D2 / cnt;
+    const float kk = (float)(2.0 * scale);
+    cudaStream_t st = (cudaStream_t)stream;
+    RowGeom g;
+    const bool vec_ok = make_rowgeom(g, B * C, D0, D1, D2) && aligned16(f) && aligned16(gf) &&
+                        (!gout || (aligned16(gout) && aligned16(dpos)));
+    if (vec_ok && D0 >= 8) {
+        L2MarchGeom m;
+        m.BC = B * C; m.D0 = D0; m.D1 = D1; m.D2 = D2; m.XG = D2 / 4; m.C = C;
+        const i64 columns = (i64)m.BC * D1 * m.XG;
+        i64 nz = (2ll * kSMs * 768 + columns - 1) / columns;      // ~2 runs per resident thread
+        if (nz > D0 / 4) nz = D0 / 4;
+        if (nz < 1) nz = 1;
+        m.zrun = (int)((D0 + nz - 1) / nz);
+        m.nzrun = (D0 + m.zrun - 1) / m.zrun;
+        m.items = (unsigned int)(columns * m.nzrun);
+        m.dXG = make_fastdiv(m.XG); m.dD1 = make_fastdiv(D1); m.dnz = make_fastdiv(m.nzrun); m.dC = make_fastdiv(C);
+        const int grid = grid_for(m.items, 256, 3);
+        ReduceWs *w = (ReduceWs *)ws;
+        if (gout) {
+            if (accumulate) l2reg_fwd_bwd_march_kernel<true, true><<<grid, 256, 0, st>>>(f, gf, kk, out, w, scale, gout, dpos, m);
+            else l2reg_fwd_bwd_march_kernel<false, true><<<grid, 256, 0, st>>>(f, gf, kk, out, w, scale, gout, dpos, m);
+        } else {
+            if (accumulate) l2reg_fwd_bwd_march_kernel<true, false><<<grid, 256, 0, st>>>(f, gf, kk, out, w, scale, nullptr, nullptr, m);
+            else l2reg_fwd_bwd_march_kernel<false, false><<<grid, 256, 0, st>>>(f, gf, kk, out, w, scale, nullptr, nullptr, m);
+        }
+    } else if (vec_ok) {
+        const int grid = grid_for(g.groups, 256, 8);
+        ReduceWs *w = (ReduceWs *)ws;
+        if (gout) {
+            if (accumulate) l2reg_fwd_bwd_v4_kernel<true, true><<<grid, 256, 0, st>>>(f, gf, kk, out, w, scale, gout, dpos, C, g);
+            else l2reg_fwd_bwd_v4_kernel<false, true><<<grid, 256, 0, st>>>(f, gf, kk, out, w, scale, gout, dpos, C, g);
+        } else {
+            if (accumulate) l2reg_fwd_bwd_v4_kernel<true, false><<<grid, 256, 0, st>>>(f, gf, kk, out, w, scale, nullptr, nullptr, C, g);
+            else l2reg_fwd_bwd_v4_kernel<false, false><<<grid, 256, 0, st>>>(f, gf, kk, out, w, scale, nullptr, nullptr, C, g);
+        }
+    } else {   // rows that are not a multiple of 4 voxels: the generic kernels
+        l2reg_fwd_kernel<<<grid_for(total, 256, 4), 256, 0, st>>>(f, out, (ReduceWs *)ws, scale, B * C, D0, D1, D2);
+        l2reg_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(nullptr, f, gf, kk, B * C, D0, D1, D2, accumulate);
+        if (gout) prod_acc_kernel<<<grid_for(total, 256), 256, 0, st>>>(gout, dpos, gf, (i64)D0 * D1 * D2, C, total);
+    }
     return launch_status();
 }
 

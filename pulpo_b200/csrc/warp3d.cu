@@ -31,6 +31,9 @@ namespace pulpo {
 #ifndef PULPO_WARP_BWD_CTAS
 #define PULPO_WARP_BWD_CTAS 2
 #endif
+#ifndef PULPO_WARP_FWDG_CTAS
+#define PULPO_WARP_FWDG_CTAS 2   // forward that also stores the interpolant's spatial gradient (dpos)
+#endif
 constexpr int WR = PULPO_WARP_WR;
 
 struct WarpGeom {
@@ -214,10 +217,37 @@ __device__ __forceinline__ float l2_fwd_terms(const float *f, const float (&c)[W
     return acc;
 }
 
-template <int MODE, bool IDX, bool REG>
-__global__ void __launch_bounds__(256, PULPO_WARP_FWD_CTAS)
+// Spatial gradient of the interpolant at the two sample points of a pair, masked and scaled exactly like the gather
+// half of the backward (zero wherever the border clamp is active; S_img/2 of the unnormalise times 2/(S-1) of the
+// normalise): d out / d df along z, y, x.  With one image channel the whole gather half of the backward is
+// gdf = gout * dpos, so a forward that stores dpos (GRAD) turns the backward into a streaming product (see
+// warp3d_bwd_dpos_kernel and resize.cu's fused adjoint) -- no second position chain, no second round of gathers.
+__device__ __forceinline__ void foot_grad2(const C8 &a, const C8 &b, const Foot2 &k, const WarpGeom &g, float2 &gz,
+                                           float2 &gy, float2 &gx)
+{
+    const float2 c000 = pair(a.c000, b.c000), c001 = pair(a.c001, b.c001), c010 = pair(a.c010, b.c010),
+                 c011 = pair(a.c011, b.c011), c100 = pair(a.c100, b.c100), c101 = pair(a.c101, b.c101),
+                 c110 = pair(a.c110, b.c110), c111 = pair(a.c111, b.c111);
+    const float2 sx = lerp_diff2(sub2(c001, c000), sub2(c011, c010), sub2(c101, c100), sub2(c111, c110), k.wy0, k.wy1,
+                                 k.wz0, k.wz1);
+    const float2 sy_ = lerp_diff2(sub2(c010, c000), sub2(c011, c001), sub2(c110, c100), sub2(c111, c101), k.wx0, k.wx1,
+                                  k.wz0, k.wz1);
+    const float2 sz_ = lerp_diff2(sub2(c100, c000), sub2(c101, c001), sub2(c110, c010), sub2(c111, c011), k.wx0, k.wx1,
+                                  k.wy0, k.wy1);
+    const float kz = 2.0f * g.a0.rcp.x, ky = 2.0f * g.a1.rcp.x, kx = 2.0f * g.a2.rcp.x;
+    const float2 mz = pair((k.uz.x > 0.0f && k.uz.x < g.a0.Sm1.x) ? g.a0.gmul.x : 0.0f, (k.uz.y > 0.0f && k.uz.y < g.a0.Sm1.x) ? g.a0.gmul.x : 0.0f);
+    const float2 my = pair((k.uy.x > 0.0f && k.uy.x < g.a1.Sm1.x) ? g.a1.gmul.x : 0.0f, (k.uy.y > 0.0f && k.uy.y < g.a1.Sm1.x) ? g.a1.gmul.x : 0.0f);
+    const float2 mx = pair((k.ux.x > 0.0f && k.ux.x < g.a2.Sm1.x) ? g.a2.gmul.x : 0.0f, (k.ux.y > 0.0f && k.ux.y < g.a2.Sm1.x) ? g.a2.gmul.x : 0.0f);
+    gz = __fmul2_rn(__fmul2_rn(mz, sz_), splat2(kz));
+    gy = __fmul2_rn(__fmul2_rn(my, sy_), splat2(ky));
+    gx = __fmul2_rn(__fmul2_rn(mx, sx), splat2(kx));
+}
+
+template <int MODE, bool IDX, bool REG, bool GRAD>
+__global__ void __launch_bounds__(256, GRAD ? PULPO_WARP_FWDG_CTAS : PULPO_WARP_FWD_CTAS)
 warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, float *__restrict__ out,
-                  int32_t *__restrict__ idx, float *reg_out, ReduceWs *ws, double reg_scale, const WarpGeom g)
+                  int32_t *__restrict__ idx, float *reg_out, ReduceWs *ws, double reg_scale, float *__restrict__ dpos,
+                  const WarpGeom g)
 {
     __shared__ double red[32];
     const unsigned int nwarps = gridDim.x * 8u;
@@ -273,6 +303,13 @@ warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, f
                 const float2 res = interp8x2(q[2 * jp], q[2 * jp + 1], ft[jp]);
                 if (ok[2 * jp]) o[(2 * jp) * sy] = res.x;
                 if (ok[2 * jp + 1]) o[(2 * jp + 1) * sy] = res.y;
+                if (GRAD) {   // C == 1 (checked by the entry point)
+                    float2 gz, gy, gx;
+                    foot_grad2(q[2 * jp], q[2 * jp + 1], ft[jp], g, gz, gy, gx);
+                    float *d = dpos + (i64)t.b * 3 * S + v0 + (2 * jp) * sy;
+                    if (ok[2 * jp]) { d[0] = gz.x; d[S] = gy.x; d[2 * S] = gx.x; }
+                    if (ok[2 * jp + 1]) { d[sy] = gz.y; d[S + sy] = gy.y; d[2 * S + sy] = gx.y; }
+                }
             }
         }
     }
@@ -494,18 +531,21 @@ static unsigned int persistent_grid(unsigned int items, int per_sm)
 
 template <int MODE>
 static int launch_fwd(const float *img, const float *df, float *out, int32_t *idx, float *reg_out, ReduceWs *ws,
-                      double reg_scale, int B, int C, int D0, int D1, int D2, int I0, int I1, int I2, cudaStream_t st)
+                      double reg_scale, int B, int C, int D0, int D1, int D2, int I0, int I1, int I2, cudaStream_t st,
+                      float *dpos = nullptr)
 {
     WarpGeom g;
     int rc = make_geom(g, B, C, D0, D1, D2, I0, I1, I2);
     if (rc != PULPO_OK) return rc;
-    const unsigned int grid = persistent_grid(g.items, PULPO_WARP_FWD_CTAS);
-    if (idx)
-        warp3d_fwd_kernel<MODE, true, false><<<grid, 256, 0, st>>>(img, df, out, idx, nullptr, nullptr, 0.0, g);
+    const unsigned int grid = persistent_grid(g.items, dpos ? PULPO_WARP_FWDG_CTAS : PULPO_WARP_FWD_CTAS);
+    if (dpos)
+        warp3d_fwd_kernel<MODE, false, false, true><<<grid, 256, 0, st>>>(img, df, out, nullptr, nullptr, nullptr, 0.0, dpos, g);
+    else if (idx)
+        warp3d_fwd_kernel<MODE, true, false, false><<<grid, 256, 0, st>>>(img, df, out, idx, nullptr, nullptr, 0.0, nullptr, g);
     else if (reg_out)
-        warp3d_fwd_kernel<MODE, false, true><<<grid, 256, 0, st>>>(img, df, out, nullptr, reg_out, ws, reg_scale, g);
+        warp3d_fwd_kernel<MODE, false, true, false><<<grid, 256, 0, st>>>(img, df, out, nullptr, reg_out, ws, reg_scale, nullptr, g);
     else
-        warp3d_fwd_kernel<MODE, false, false><<<grid, 256, 0, st>>>(img, df, out, nullptr, nullptr, nullptr, 0.0, g);
+        warp3d_fwd_kernel<MODE, false, false, false><<<grid, 256, 0, st>>>(img, df, out, nullptr, nullptr, nullptr, 0.0, nullptr, g);
     return launch_status();
 }
 
@@ -531,12 +571,39 @@ static int launch_bwd(const float *gout, const float *img, const float *df, floa
 
 static int warp_fwd_dispatch(const float *img, const float *df, float *out, int32_t *idx, float *reg_out, void *ws,
                              double reg_scale, int B, int C, int D0, int D1, int D2, int coord_mode, cudaStream_t st,
-                             int I0 = 0, int I1 = 0, int I2 = 0)
+                             int I0 = 0, int I1 = 0, int I2 = 0, float *dpos = nullptr)
 {
     ReduceWs *w = (ReduceWs *)ws;
     if (coord_mode == PULPO_COORD_CPU_EXACT)
-        return launch_fwd<0>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, I0, I1, I2, st);
-    return launch_fwd<1>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, I0, I1, I2, st);
+        return launch_fwd<0>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, I0, I1, I2, st, dpos);
+    return launch_fwd<1>(img, df, out, idx, reg_out, w, reg_scale, B, C, D0, D1, D2, I0, I1, I2, st, dpos);
+}
+
+// gdf (+)= gout * dpos: the gather half of the backward once the forward has stored dpos (one image channel).
+// Pure streaming, 128-bit when the volume allows.
+template <bool ACC, typename V>
+__global__ void __launch_bounds__(256)
+warp3d_bwd_dpos_kernel(const V *__restrict__ gout, const V *__restrict__ dpos, V *__restrict__ gdf, unsigned int Sv,
+                       unsigned int total)   // Sv: vectors per channel; total = B * Sv
+{
+    for (unsigned int i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+        const unsigned int b = i / Sv, v = i - b * Sv;
+        const V go = gout[i];
+        const size_t o = (size_t)b * 3 * Sv + v;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const V d = dpos[o + (size_t)c * Sv];
+            V r;
+            if constexpr (sizeof(V) == 16) {
+                r.x = go.x * d.x; r.y = go.y * d.y; r.z = go.z * d.z; r.w = go.w * d.w;
+                if (ACC) { const V old = gdf[o + (size_t)c * Sv]; r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w; }
+            } else {
+                r = go * d;
+                if (ACC) r += gdf[o + (size_t)c * Sv];
+            }
+            gdf[o + (size_t)c * Sv] = r;
+        }
+    }
 }
 
 static int warp_bwd_dispatch(const float *gout, const float *img, const float *df, float *gimg, float *gdf,
@@ -580,6 +647,44 @@ extern "C" int pulpo_warp3d_bwd(const float *gout, const float *img, const float
     PULPO_REQUIRE(coord_mode == 0 || coord_mode == 1, PULPO_ERR_UNSUPPORTED);
     return warp_bwd_dispatch(gout, img, df, gimg, gdf, nullptr, 0.0f, false, B, C, D0, D1, D2, coord_mode,
                              (cudaStream_t)stream);
+}
+
+extern "C" int pulpo_warp3d_fwd_dpos(const float *img, const float *df, float *out, float *dpos, int B, int D0, int D1,
+                                     int D2, int coord_mode, pulpo_stream_t stream)
+{
+    PULPO_NVTX("pulpo_warp3d_fwd_dpos");
+    PULPO_REQUIRE(img && df && out && dpos, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && D0 >= 2 && D1 >= 2 && D2 >= 2, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(coord_mode == 0 || coord_mode == 1, PULPO_ERR_UNSUPPORTED);
+    return warp_fwd_dispatch(img, df, out, nullptr, nullptr, nullptr, 0.0, B, 1, D0, D1, D2, coord_mode,
+                             (cudaStream_t)stream, 0, 0, 0, dpos);
+}
+
+extern "C" int pulpo_warp3d_bwd_dpos(const float *gout, const float *dpos, float *gdf, int accumulate, int B, int D0,
+                                     int D1, int D2, pulpo_stream_t stream)
+{
+    PULPO_NVTX("pulpo_warp3d_bwd_dpos");
+    PULPO_REQUIRE(gout && dpos && gdf, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && D0 >= 1 && D1 >= 1 && D2 >= 1, PULPO_ERR_INVALID_SHAPE);
+    const i64 S = (i64)D0 * D1 * D2;
+    PULPO_REQUIRE(S * B < (1ll << 31), PULPO_ERR_INVALID_SHAPE);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (S % 4 == 0 && aligned16(gout) && aligned16(dpos) && aligned16(gdf)) {
+        const unsigned int Sv = (unsigned int)(S / 4), total = Sv * (unsigned int)B;
+        const int grid = grid_for(total, 256, 8);
+        if (accumulate)
+            warp3d_bwd_dpos_kernel<true, float4><<<grid, 256, 0, st>>>((const float4 *)gout, (const float4 *)dpos, (float4 *)gdf, Sv, total);
+        else
+            warp3d_bwd_dpos_kernel<false, float4><<<grid, 256, 0, st>>>((const float4 *)gout, (const float4 *)dpos, (float4 *)gdf, Sv, total);
+    } else {
+        const unsigned int Sv = (unsigned int)S, total = Sv * (unsigned int)B;
+        const int grid = grid_for(total, 256, 8);
+        if (accumulate)
+            warp3d_bwd_dpos_kernel<true, float><<<grid, 256, 0, st>>>(gout, dpos, gdf, Sv, total);
+        else
+            warp3d_bwd_dpos_kernel<false, float><<<grid, 256, 0, st>>>(gout, dpos, gdf, Sv, total);
+    }
+    return launch_status();
 }
 
 extern "C" int pulpo_warp3d_fwd_img(const float *img, const float *df, float *out, int32_t *idx_dbg, int B, int C,

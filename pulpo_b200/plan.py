@@ -43,13 +43,19 @@ def _p(t, byte_offset=0):
 class HotPathPlan:
     def __init__(self, input_size, total_levels, latent_levels, batch=1, beta=0.1, gamma=0.05, lamb=0.025,
                  with_reg=True, nsteps=7, coord_mode=CPU_EXACT, device=None, multi_stream=True, fuse_reg=True,
-                 vecint_mode=CPU_EXACT, fuse_combine=False, pool_pyramid=True, aux_early=False, df_resolution="level_res"):
+                 vecint_mode=CPU_EXACT, fuse_combine=False, pool_pyramid=True, aux_early=False, df_resolution="level_res",
+                 dpos=True):
         self.L = L = latent_levels
         self.B = B = batch
         self.lk = lk = total_levels - latent_levels
         self.nsteps, self.mode, self.with_reg = nsteps, coord_mode, with_reg
         self.vi_mode = vecint_mode   # CPU_EXACT: bit-identical fields; FAST is within 1e-4 but buys little (L1-pipe bound)
         self.fuse_reg = bool(fuse_reg and with_reg)   # L2_reg rides in the warp kernels (same field, same step)
+        # dpos: the level warps' forward also stores d out / d df (the interpolant's spatial gradient at the sample
+        # point, masked and scaled), so their backward is the streaming product gmoved * dpos -- formed inside the
+        # regulariser's value + gradient pass over the same field when there is one.  False: the gather-form warp
+        # backward (second position chain, second round of corner gathers), regulariser inside the warp kernels.
+        self.dpos = bool(dpos) and (self.fuse_reg or not with_reg)
         # pyramid combination (and its adjoint) inside the integration launches: fewer launches (25 instead of 31) but
         # measured slower (0.936 vs 0.916 ms at config 2): the in-kernel phases run on the cooperative grid's 113 k / 75 k
         # threads and are latency-bound, while the separate small launches overlap with the aux stream's work
@@ -102,6 +108,7 @@ class HotPathPlan:
             self.vi_scr[l] = buf(lib.pulpo_vecint_bwd_scratch_bytes(B, *d) // 4)
         self.abc = {l: buf(3, B, 1, *self.outsz[l]) for l in range(L)}
         self.gmoved = {l: buf(B, 1, *self.outsz[l]) for l in range(L)}
+        self.dposb = {l: buf(B, 3, *self.outsz[l]) for l in range(L)} if self.dpos else {}
         self.gfinal = {l: buf(B, 3, *self.outsz[l]) for l in range(L)}
         self.ginteg = {l: (buf(B, 3, *self.insz[l]) if self.outsz[l] != self.insz[l] else self.gfinal[l]) for l in range(L)}
         self.gdf = {l: buf(B, 3, *self.insz[l]) for l in range(L)}
@@ -241,7 +248,10 @@ class HotPathPlan:
             # warp the (pooled) moving image
             if ms and l in ev_lx:
                 s.wait_event(ev_lx[l])
-            if self.fuse_reg:
+            if self.dpos:
+                call(lib.pulpo_warp3d_fwd_dpos, _p(lx[l]), _p(self.final[l]), _p(self.moved[l]), _p(self.dposb[l]), B, *dout,
+                     mode, hs)
+            elif self.fuse_reg:
                 call(lib.pulpo_warp3d_l2reg_fwd, _p(lx[l]), _p(self.final[l]), _p(self.moved[l]), self.lamb_eff[l],
                      self._loss_ptr(2, l), _p(self.ws_l2[l]), self.ws_l2[l].numel(), B, 1, *dout, mode, hs)
             else:
@@ -257,7 +267,13 @@ class HotPathPlan:
                  wsn.numel(), self.win[l], self.gamma_eff[l], B, 1, *dout, hs)
             call(lib.pulpo_ncc_bwd, _p(self.abc[l]), _p(self.moved[l]), _p(yt), None, _p(self.gmoved[l]),
                  self.win[l], self.gamma_eff[l], B, 1, *dout, hs)
-            if self.fuse_reg:
+            if self.dpos and self.with_reg:
+                # L2_reg value + gradient and the warp's backward (gmoved * dpos) in one pass over the final field
+                call(lib.pulpo_l2reg_fwd_bwd, _p(self.final[l]), self.lamb_eff[l], self._loss_ptr(2, l), _p(self.gmoved[l]),
+                     _p(self.dposb[l]), _p(self.gfinal[l]), 0, _p(self.ws_l2[l]), self.ws_l2[l].numel(), B, 3, *dout, hs)
+            elif self.dpos:
+                call(lib.pulpo_warp3d_bwd_dpos, _p(self.gmoved[l]), _p(self.dposb[l]), _p(self.gfinal[l]), 0, B, *dout, hs)
+            elif self.fuse_reg:
                 call(lib.pulpo_warp3d_l2reg_bwd, _p(self.gmoved[l]), _p(lx[l]), _p(self.final[l]), _p(self.gfinal[l]),
                      self.lamb_eff[l], None, B, 1, *dout, mode, hs)
             else:

@@ -25,6 +25,13 @@ def algo_bytes(name, args):
     if name == "pulpo_warp3d_l2reg_bwd":    # gout, img, df, gdf, lamb, reg_gloss, B, C, D0, D1, D2
         B, C, n = a[6], a[7], a[8] * a[9] * a[10]
         return B * n * (4 * C + 12 + 4 * C + 12)
+    if name == "pulpo_warp3d_fwd_dpos":     # img, df, out, dpos, B, D0, D1, D2  (dpos is scratch, not algorithmic)
+        return a[4] * a[5] * a[6] * a[7] * (12 + 8)
+    if name == "pulpo_warp3d_bwd_dpos":     # gout, dpos, gdf, accumulate, B, D0, D1, D2: the warp backward's bytes
+        return a[4] * a[5] * a[6] * a[7] * (4 + 12 + 4 + 12)
+    if name == "pulpo_l2reg_fwd_bwd":       # f, lamb, out, gout, dpos, gf, accumulate, ws, bytes, B, C, D0, D1, D2
+        n = a[9] * a[11] * a[12] * a[13]
+        return n * (4 + 12 + 4 + 12) if a[3] else n * a[10] * 8   # with the product: same bytes as warp3d_l2reg_bwd
     if name == "pulpo_vecint_fwd":          # vec, out, ws, ws_bytes, nsteps, save, B, D0, D1, D2
         return a[4] * 24 * a[6] * a[7] * a[8] * a[9]
     if name == "pulpo_vecint_bwd":          # gout, saved, gvec, scratch, bytes, nsteps, B, D0..

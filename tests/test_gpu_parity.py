@@ -628,7 +628,7 @@ def _run_plan(g_or_inputs, total, latent, size, B, multi_stream=True, graph=Fals
 @pytest.mark.parametrize("multi_stream,graph,fuse_reg,kw", [
     (False, False, True, {}), (True, False, False, {}), (True, True, True, {}),
     (True, True, True, {"fuse_combine": True, "pool_pyramid": False, "aux_early": True}),
-    (False, False, True, {"fuse_combine": True})])
+    (False, False, True, {"fuse_combine": True}), (True, True, True, {"dpos": False}), (False, False, True, {"dpos": False})])
 def test_plan_golden(PF, multi_stream, graph, fuse_reg, kw):
     g = load_golden("hot_path_3lvl")
     total, latent = int(g["total_levels"]), int(g["latent_levels"])
@@ -649,6 +649,67 @@ def test_plan_golden(PF, multi_stream, graph, fuse_reg, kw):
         assert_grad_close(plan.gdf[l].cpu().numpy(), g["gdf%d" % l], "gdf %d" % l)
         assert_grad_close(plan.gmu[l].cpu().numpy(), g["gmu%d" % l], "gmu %d" % l)
         assert_grad_close(plan.gsigma[l].cpu().numpy(), g["gsigma%d" % l], "gsigma %d" % l)
+
+
+def test_warp_dpos_forward_and_streaming_backward_match_gather_backward(PF):
+    """pulpo_warp3d_fwd_dpos: same moved image bit for bit, and dpos such that gout * dpos is the gather-form backward's
+    field gradient (pulpo_warp3d_bwd); pulpo_warp3d_bwd_dpos and pulpo_l2reg_fwd_bwd (product inside the regulariser's
+    pass) against the separate kernels.  Ragged and vectorisable shapes, clamped borders (large displacements)."""
+    import ctypes
+    from pulpo_b200 import _lib, synthetic as syn
+    L = _lib.lib()
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for shape, seed, B, amp in [((12, 20, 28), 1, 2, 2.5), ((9, 11, 13), 2, 1, 6.0), ((40, 48, 56), 3, 1, 30.0), ((16, 24, 32), 4, 3, 0.3)]:
+        D0, D1, D2 = shape
+        f = syn.make_field(shape, seed, batch=B, max_abs=amp).cuda()
+        img = torch.rand(B, 1, *shape, device="cuda")
+        gout = torch.randn(B, 1, *shape, device="cuda")
+        out_ref = PF.warp(f, img)
+        fr = f.clone().requires_grad_(True)
+        PF.warp(fr, img).backward(gout)
+        out, dpos = torch.empty_like(img), torch.full((B, 3, *shape), float("nan"), device="cuda")
+        _lib.check(L.pulpo_warp3d_fwd_dpos(vp(img), vp(f), vp(out), vp(dpos), B, D0, D1, D2, 0, st))
+        assert torch.equal(out, out_ref)
+        assert bool(torch.isfinite(dpos).all())
+        assert_grad_close((gout * dpos).cpu().numpy(), fr.grad.cpu().numpy(), "gout * dpos")
+        gdf = torch.full_like(f, 7.0)
+        _lib.check(L.pulpo_warp3d_bwd_dpos(vp(gout), vp(dpos), vp(gdf), 0, B, D0, D1, D2, st))
+        assert torch.equal(gdf, gout * dpos)
+        _lib.check(L.pulpo_warp3d_bwd_dpos(vp(gout), vp(dpos), vp(gdf), 1, B, D0, D1, D2, st))
+        assert_grad_close(gdf.cpu().numpy(), (2 * gout * dpos).cpu().numpy(), "accumulate")
+        # regulariser value + gradient (+ product) in one pass
+        freg = f.clone().requires_grad_(True)
+        reg_ref = PF.l2_reg(freg, 0.025)
+        reg_ref.backward()
+        ws = torch.zeros(L.pulpo_reduce_ws_bytes(), dtype=torch.uint8, device="cuda")
+        reg = torch.zeros((), device="cuda")
+        for with_prod in (False, True, True):   # repeated: the workspace resets itself
+            g2 = torch.full_like(f, 3.0)
+            _lib.check(L.pulpo_l2reg_fwd_bwd(vp(f), 0.025, vp(reg), vp(gout) if with_prod else None,
+                                             vp(dpos) if with_prod else None, vp(g2), 0, vp(ws), ws.numel(), B, 3, D0, D1, D2, st))
+            assert_loss_close(reg.item(), reg_ref.item(), "fused l2reg value")
+            want = freg.grad + (gout * dpos if with_prod else 0)
+            assert_grad_close(g2.cpu().numpy(), want.cpu().numpy(), "fused l2reg grad (+ product)")
+        g3 = torch.ones_like(f)
+        _lib.check(L.pulpo_l2reg_fwd_bwd(vp(f), 0.025, vp(reg), vp(gout), vp(dpos), vp(g3), 1, vp(ws), ws.numel(), B, 3, D0, D1, D2, st))
+        assert_grad_close(g3.cpu().numpy(), (freg.grad + gout * dpos + 1).cpu().numpy(), "fused l2reg grad, accumulate")
+
+
+def test_plan_without_regulariser_dpos_equals_gather_backward(PF):
+    """with_reg=False: the stored-dpos backward (pulpo_warp3d_bwd_dpos) against the gather-form warp backward."""
+    from pulpo_b200 import synthetic as syn
+    size, total, latent = [32, 48, 64], 4, 3
+    x, y, dfs, mus, sgs = syn.make_hot_path_inputs(size, total, latent, seed=5)
+    dev_in = (x.cuda(), y.cuda(), {l: dfs[l].cuda() for l in dfs}, {l: mus[l].cuda() for l in dfs},
+              {l: sgs[l].cuda() for l in dfs})
+    a = _run_plan(dev_in, total, latent, size, 1, True, True, with_reg=False, dpos=True)
+    b = _run_plan(dev_in, total, latent, size, 1, True, False, with_reg=False, dpos=False)
+    assert a.dpos and not b.dpos
+    assert_loss_close(a.total.item(), b.total.item(), "total")
+    for l in range(latent):
+        assert torch.equal(a.moved[l], b.moved[l])
+        assert_grad_close(a.gdf[l].cpu().numpy(), b.gdf[l].cpu().numpy(), "gdf %d" % l)
 
 
 def test_plan_full_size_config2_vs_torch_oracle(PF):
