@@ -387,6 +387,10 @@ __device__ __forceinline__ float ld_stream(const float *p)
     return r;
 }
 
+// request a line into L2 ahead of its use (no register, no shared memory: for z-marching kernels whose next planes'
+// addresses are known long before the loads that need them)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // sm_90+ vector reduction: one 16-byte red instead of four scalar atomics
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
 {

@@ -448,8 +448,14 @@ __device__ __forceinline__ void l2_plane_load(L2Plane &p, const float *fq, const
     if (ACC) p.old = full ? ld_stream4(gfq) : z4;
 }
 
+#ifndef PULPO_L2M_CTAS
+#define PULPO_L2M_CTAS 3
+#endif
+#ifndef PULPO_L2M_PF
+#define PULPO_L2M_PF 1      // planes ahead of the register prefetch that are requested into L2 (0: off)
+#endif
 template <bool ACC, bool PROD>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, PULPO_L2M_CTAS)
 l2reg_fwd_bwd_march_kernel(const float *__restrict__ f, float *__restrict__ gf, float kk, float *out, ReduceWs *ws,
                            double scale, const float *__restrict__ gout, const float *__restrict__ dpos,
                            const L2MarchGeom g)
@@ -479,6 +485,10 @@ l2reg_fwd_bwd_march_kernel(const float *__restrict__ f, float *__restrict__ gf, 
         for (int z = z0; z < z1; ++z) {
             L2Plane nxt;
             const bool zn = z + 1 < g.D0, zin = z > 0;
+            if (PULPO_L2M_PF > 0 && z + 1 + PULPO_L2M_PF < z1) {
+                prefetch_l2(fq + (1 + PULPO_L2M_PF) * sz);
+                if (PROD) { prefetch_l2(goq + (1 + PULPO_L2M_PF) * sz); prefetch_l2(dpq + (1 + PULPO_L2M_PF) * sz); }
+            }
             if (zn)
                 l2_plane_load<ACC, PROD>(nxt, fq + sz, PROD ? goq + sz : nullptr, PROD ? dpq + sz : nullptr, gfq + sz, sy,
                                          z + 1 < z1, yin, yn, xl_ok, xr_ok);
@@ -488,21 +498,44 @@ l2reg_fwd_bwd_march_kernel(const float *__restrict__ f, float *__restrict__ gf, 
             const float pzv[4] = {prev.x, prev.y, prev.z, prev.w}, pyv[4] = {cur.py.x, cur.py.y, cur.py.z, cur.py.w};
             const float nzv[4] = {nxt.c.x, nxt.c.y, nxt.c.z, nxt.c.w}, nyv[4] = {cur.ny.x, cur.ny.y, cur.ny.z, cur.ny.w};
             float r[4];
+            if (zin && zn && yin && yn) {
+                // interior plane and row (almost every iteration): only the two x faces need masks -- no predicates
+                const float mi0 = xl_ok ? 1.0f : 0.0f, mn3 = xr_ok ? 1.0f : 0.0f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int x = 4 * (int)xg + j;
-                const bool xin = x > 0, xn = x + 1 < g.D2;
-                const float cc = c[j + 1];
-                float a = 0.0f;
-                if (xin && yin && zin) {
+                for (int j = 0; j < 4; ++j) {
+                    const float cc = c[j + 1];
                     const float dz = cc - pzv[j], dy = cc - pyv[j], dx = cc - c[j];
-                    a += dz + dy + dx;
-                    vacc += dz * dz; vacc += dy * dy; vacc += dx * dx;
+                    const float own = (dz + dy + dx) - (nzv[j] - cc) - (nyv[j] - cc);
+                    const float sq = dz * dz + dy * dy + dx * dx;
+                    const float fwd = c[j + 2] - cc;
+                    if (j == 0) {          // x == 0 (first quad of the row) lies outside the crop
+                        vacc += mi0 * sq;
+                        r[j] = kk * (mi0 * own - fwd);
+                    } else if (j == 3) {   // x == D2 - 1 (last quad) has no forward x neighbour
+                        vacc += sq;
+                        r[j] = kk * (own - mn3 * fwd);
+                    } else {
+                        vacc += sq;
+                        r[j] = kk * (own - fwd);
+                    }
                 }
-                if (zn && yin && xin) a -= nzv[j] - cc;
-                if (yn && zin && xin) a -= nyv[j] - cc;
-                if (xn && zin && yin) a -= c[j + 2] - cc;
-                r[j] = kk * a;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int x = 4 * (int)xg + j;
+                    const bool xin = x > 0, xn = x + 1 < g.D2;
+                    const float cc = c[j + 1];
+                    float a = 0.0f;
+                    if (xin && yin && zin) {
+                        const float dz = cc - pzv[j], dy = cc - pyv[j], dx = cc - c[j];
+                        a += dz + dy + dx;
+                        vacc += dz * dz; vacc += dy * dy; vacc += dx * dx;
+                    }
+                    if (zn && yin && xin) a -= nzv[j] - cc;
+                    if (yn && zin && xin) a -= nyv[j] - cc;
+                    if (xn && zin && yin) a -= c[j + 2] - cc;
+                    r[j] = kk * a;
+                }
             }
             if (PROD) {
                 r[0] += cur.go.x * cur.dp.x; r[1] += cur.go.y * cur.dp.y; r[2] += cur.go.z * cur.dp.z; r[3] += cur.go.w * cur.dp.w;
@@ -945,7 +978,7 @@ extern "C" int pulpo_l2reg_fwd_bwd(const float *f, float lamb, float *out, const
         m.nzrun = (D0 + m.zrun - 1) / m.zrun;
         m.items = (unsigned int)(columns * m.nzrun);
         m.dXG = make_fastdiv(m.XG); m.dD1 = make_fastdiv(D1); m.dnz = make_fastdiv(m.nzrun); m.dC = make_fastdiv(C);
-        const int grid = grid_for(m.items, 256, 3);
+        const int grid = grid_for(m.items, 256, PULPO_L2M_CTAS);
         ReduceWs *w = (ReduceWs *)ws;
         if (gout) {
             if (accumulate) l2reg_fwd_bwd_march_kernel<true, true><<<grid, 256, 0, st>>>(f, gf, kk, out, w, scale, gout, dpos, m);

@@ -351,6 +351,9 @@ up2_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gx, float sca
 // is the z-adjoint of four consecutive T's, two of which are carried in registers from the previous
 // plane.  Gradient rows are read 1.5x instead of 4x, all loads are full cache lines.
 constexpr int UB_RY = 2;       // input rows per thread
+#ifndef PULPO_UP2B_PF
+#define PULPO_UP2B_PF 1        // request the next iteration's gradient planes into L2 while this one is computed
+#endif
 struct Up2MGeom {
     int BC, d0, d1, d2;
     int nxb, nyb, zrun, nzrun;
@@ -442,6 +445,18 @@ up2_bwd_march_kernel(const float *__restrict__ gout, float *__restrict__ gx, flo
         T4 ta = (z0 > 0) ? up2_plane_adjoint(ra, lane, wx, wy) : zero;
         T4 tb = up2_plane_adjoint(rb, lane, wx, wy);
         for (int z = z0; z < z1; ++z) {
+#if PULPO_UP2B_PF
+            if (xok && z + 1 < z1) {   // the next iteration's two gradient planes -> L2 (one request per row and lane quad)
+#pragma unroll
+                for (int b = 0; b < UB_RY + 4; ++b) {
+                    int oy = 2 * y0 - 1 + b;
+                    oy = oy < 0 ? 0 : (oy > o1 - 1 ? o1 - 1 : oy);
+                    const float *row = gb + (i64)(2 * z + 3) * plane + (i64)oy * o2 + 2 * x0;
+                    prefetch_l2(row);
+                    if (z + 2 < d0) prefetch_l2(row + plane);
+                }
+            }
+#endif
             up2_plane_load(ra, gb + (i64)(2 * z + 1) * plane, o1, o2, y0, x0, xok, lane);
             if (z + 1 < d0) up2_plane_load(rb, gb + (i64)(2 * z + 2) * plane, o1, o2, y0, x0, xok, lane);
             const T4 tc = up2_plane_adjoint(ra, lane, wx, wy);

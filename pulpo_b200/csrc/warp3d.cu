@@ -34,6 +34,9 @@ namespace pulpo {
 #ifndef PULPO_WARP_FWDG_CTAS
 #define PULPO_WARP_FWDG_CTAS 2   // forward that also stores the interpolant's spatial gradient (dpos)
 #endif
+#ifndef PULPO_WARP_PF
+#define PULPO_WARP_PF 1   // L2 prefetch of the next item's field rows
+#endif
 constexpr int WR = PULPO_WARP_WR;
 
 struct WarpGeom {
@@ -263,6 +266,15 @@ warp3d_fwd_kernel(const float *__restrict__ img, const float *__restrict__ df, f
 #pragma unroll
         for (int j = 0; j < WR; ++j) ok[j] = t.xok && (t.y0 + j < g.D1);
         const float *f = df + (i64)t.b * 3 * S + v0;
+#if PULPO_WARP_PF
+        if (w + nwarps < g.items && lane < 3 * WR) {
+            // the field rows of this warp's NEXT item -> L2 (one 128-byte line per lane: channel lane / WR, row lane % WR),
+            // so the first of the item's two dependent memory round trips is an L2 hit
+            const WItem n = decode_witem(w + nwarps, 0, g);
+            const i64 nv = (i64)n.b * 3 * S + ((i64)n.z * g.D1 + n.y0) * g.D2 + n.x;
+            if (n.y0 + lane % WR < g.D1) prefetch_l2(df + nv + (i64)(lane / WR) * S + (lane % WR) * sy);
+        }
+#endif
         float dz[WR], dy[WR], dx[WR];
         load_rows<!REG>(f, sy, ok, dz);
         load_rows<!REG>(f + S, sy, ok, dy);
