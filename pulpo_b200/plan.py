@@ -44,7 +44,7 @@ class HotPathPlan:
     def __init__(self, input_size, total_levels, latent_levels, batch=1, beta=0.1, gamma=0.05, lamb=0.025,
                  with_reg=True, nsteps=7, coord_mode=CPU_EXACT, device=None, multi_stream=True, fuse_reg=True,
                  vecint_mode=CPU_EXACT, fuse_combine=False, pool_pyramid=True, aux_early=False, df_resolution="level_res",
-                 dpos=True):
+                 dpos=True, aux_after="up2"):
         self.L = L = latent_levels
         self.B = B = batch
         self.lk = lk = total_levels - latent_levels
@@ -127,6 +127,11 @@ class HotPathPlan:
         edge = 4 if npool == 1 else (1 << npool)
         self.pool_pyramid = bool(pool_pyramid) and 1 <= npool <= 4 and all(s % edge == 0 for s in self.full)
         self.aux_early = bool(aux_early)
+        # when the aux stream's work (moving-image pyramid, KL) may start if not with the step: after the integration
+        # ("integ"), after level 0's output resize ("up2") or after level 0's warp ("warp")
+        if aux_after not in ("integ", "up2", "warp"):
+            raise ValueError("aux_after must be 'integ', 'up2' or 'warp'")
+        self.aux_after = aux_after
         self.multi_stream = multi_stream
         # level 0 carries the critical path: its stream gets the highest priority, so that its persistent kernels are not
         # kept waiting for CTA slots by the small kernels of the coarser levels / the aux stream (PULPO_PLAN_PRIO=0: off)
@@ -228,12 +233,20 @@ class HotPathPlan:
             call(lib.pulpo_vecint_multi_fwd, lv_arr, L, self.nsteps, 1, B, self.vi_mode, H(cur))
         ev_int = torch.cuda.Event()
         ev_int.record(cur)
-        if not self.aux_early:
+        if not self.aux_early and self.aux_after == "integ":
             ev_kl = aux_work(ev_int)
 
         # ---- per level: resize, warp, losses and their backward, on the level's stream
         ev_done = {}
-        for l in range(L - 1, -1, -1):
+        late_aux = (not self.aux_early) and self.aux_after != "integ"
+        order = ([0] + list(range(L - 1, 0, -1))) if late_aux else list(range(L - 1, -1, -1))   # level 0 first: the aux work hangs off it
+
+        def aux_after_level0(s):
+            ev = torch.cuda.Event()
+            ev.record(s)
+            return aux_work(ev)
+
+        for l in order:
             s = lv[l]
             if ms:
                 s.wait_event(start)
@@ -245,6 +258,8 @@ class HotPathPlan:
             if dout != din:
                 call(lib.pulpo_resize_up_fwd, _p(self.integ[l]), None, _p(self.final[l]), self.ofac[l], float(self.ofac[l]),
                      B, 3, *din, hs)
+            if late_aux and l == 0 and self.aux_after == "up2":
+                ev_kl = aux_after_level0(s)
             # warp the (pooled) moving image
             if ms and l in ev_lx:
                 s.wait_event(ev_lx[l])
@@ -256,6 +271,8 @@ class HotPathPlan:
                      self._loss_ptr(2, l), _p(self.ws_l2[l]), self.ws_l2[l].numel(), B, 1, *dout, mode, hs)
             else:
                 call(lib.pulpo_warp3d_fwd, _p(lx[l]), _p(self.final[l]), _p(self.moved[l]), None, B, 1, *dout, mode, hs)
+            if late_aux and l == 0 and self.aux_after == "warp":
+                ev_kl = aux_after_level0(s)
             # NCC against the resized fixed image (losses.py:313-318), backward immediately
             if dout != self.full:
                 call(lib.pulpo_interp_size_fwd, _p(y), _p(self.yt[l]), B, 1, *self.full, *dout, hs)

@@ -628,7 +628,8 @@ def _run_plan(g_or_inputs, total, latent, size, B, multi_stream=True, graph=Fals
 @pytest.mark.parametrize("multi_stream,graph,fuse_reg,kw", [
     (False, False, True, {}), (True, False, False, {}), (True, True, True, {}),
     (True, True, True, {"fuse_combine": True, "pool_pyramid": False, "aux_early": True}),
-    (False, False, True, {"fuse_combine": True}), (True, True, True, {"dpos": False}), (False, False, True, {"dpos": False})])
+    (False, False, True, {"fuse_combine": True}), (True, True, True, {"dpos": False}), (False, False, True, {"dpos": False}),
+    (True, True, True, {"aux_after": "up2"}), (True, True, True, {"aux_after": "warp"}), (False, False, True, {"aux_after": "warp"})])
 def test_plan_golden(PF, multi_stream, graph, fuse_reg, kw):
     g = load_golden("hot_path_3lvl")
     total, latent = int(g["total_levels"]), int(g["latent_levels"])
