@@ -352,7 +352,7 @@ up2_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gx, float sca
 // plane.  Gradient rows are read 1.5x instead of 4x, all loads are full cache lines.
 constexpr int UB_RY = 2;       // input rows per thread
 #ifndef PULPO_UP2B_PF
-#define PULPO_UP2B_PF 1        // request the next iteration's gradient planes into L2 while this one is computed
+#define PULPO_UP2B_PF 0        // request the next iteration's gradient planes into L2 while this one is computed
 #endif
 struct Up2MGeom {
     int BC, d0, d1, d2;
@@ -368,7 +368,8 @@ struct T4 {
 // the six gradient rows one plane contributes to this thread's 2 rows x 2 columns
 struct PlaneRaw {
     float4 c[UB_RY + 4];              // gradients 2*x0 .. 2*x0+3 of rows 2*y0-1 .. 2*y0+4
-    float el[UB_RY + 4], er[UB_RY + 4];   // gradients 2*x0-1 / 2*x0+4 for the warp's edge lanes
+    float e[UB_RY + 4];               // the warp's edge lanes only: gradient 2*x0-1 (lane 0) / 2*x0+4 (lane 31) -- one register
+                                      // for both (the kernel is register-bound: separate arrays spilled 250 bytes)
 };
 
 // All loads of a plane are issued back to back (six independent 128-bit loads + the edge lanes'
@@ -384,31 +385,33 @@ __device__ __forceinline__ void up2_plane_load(PlaneRaw &p, const float *__restr
         oy = oy < 0 ? 0 : (oy > o1 - 1 ? o1 - 1 : oy);   // out-of-range rows carry weight 0
         const float *row = plane + (i64)oy * o2;
         p.c[b] = xok ? ld_stream4(row + 2 * x0) : make_float4(0.f, 0.f, 0.f, 0.f);
-        p.el[b] = need_l ? __ldg(row + 2 * x0 - 1) : 0.0f;
-        p.er[b] = need_r ? __ldg(row + 2 * x0 + 4) : 0.0f;
+        p.e[b] = (need_l || need_r) ? __ldg(row + 2 * x0 + (need_l ? -1 : 4)) : 0.0f;
     }
 }
 
-// x/y adjoint of one gradient plane for this thread's 2 rows x 2 columns
-__device__ __forceinline__ T4 up2_plane_adjoint(const PlaneRaw &p, int lane, const float (&wx)[2][4],
-                                                const float (&wy)[UB_RY][4])
+// x/y adjoint of one gradient plane for this thread's 2 rows x 2 columns.  Constant weights (.25, .75, .75, .25) on
+// every tap: at a face the out-of-range tap is the replicated edge gradient (.25 g + .75 g = g, the adjoint of ATen's
+// edge clamp), so there are no per-thread weight tables (16 registers and a select per tap in a kernel that spilled).
+// xfirst / xlast: this thread's first / second column is the first / last input of the row.
+__device__ __forceinline__ T4 up2_plane_adjoint(const PlaneRaw &p, int lane, bool xfirst, bool xlast)
 {
     float tx[UB_RY + 4][2];
 #pragma unroll
     for (int b = 0; b < UB_RY + 4; ++b) {
         float left = __shfl_up_sync(0xffffffffu, p.c[b].w, 1), right = __shfl_down_sync(0xffffffffu, p.c[b].x, 1);
-        if (lane == 0) left = p.el[b];
-        if (lane == 31) right = p.er[b];
-        tx[b][0] = wx[0][0] * left + wx[0][1] * p.c[b].x + wx[0][2] * p.c[b].y + wx[0][3] * p.c[b].z;
-        tx[b][1] = wx[1][0] * p.c[b].y + wx[1][1] * p.c[b].z + wx[1][2] * p.c[b].w + wx[1][3] * right;
+        if (lane == 0) left = p.e[b];
+        if (lane == 31) right = p.e[b];
+        if (xfirst) left = p.c[b].x;
+        if (xlast) right = p.c[b].w;
+        tx[b][0] = 0.25f * (left + p.c[b].z) + 0.75f * (p.c[b].x + p.c[b].y);
+        tx[b][1] = 0.25f * (p.c[b].y + right) + 0.75f * (p.c[b].z + p.c[b].w);
     }
     T4 t;
 #pragma unroll
     for (int r = 0; r < UB_RY; ++r)
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
-            t.v[r][q] = wy[r][0] * tx[2 * r][q] + wy[r][1] * tx[2 * r + 1][q] + wy[r][2] * tx[2 * r + 2][q] +
-                        wy[r][3] * tx[2 * r + 3][q];
+        for (int q = 0; q < 2; ++q)   // rows 2r .. 2r+3 of the six: clamped row indices replicate the edge rows
+            t.v[r][q] = 0.25f * (tx[2 * r][q] + tx[2 * r + 3][q]) + 0.75f * (tx[2 * r + 1][q] + tx[2 * r + 2][q]);
     return t;
 }
 
@@ -418,8 +421,7 @@ up2_bwd_march_kernel(const float *__restrict__ gout, float *__restrict__ gx, flo
 {
     const unsigned int nwarps = gridDim.x * 8u;
     const int lane = threadIdx.x & 31;
-    const int d0 = g.d0, d1 = g.d1, d2 = g.d2, o0 = 2 * d0, o1 = 2 * d1, o2 = 2 * d2;
-    const T4 zero = {{{0.f, 0.f}, {0.f, 0.f}}};
+    const int d0 = g.d0, d1 = g.d1, d2 = g.d2, o1 = 2 * d1, o2 = 2 * d2;
     for (unsigned int w = (blockIdx.x * 256u + threadIdx.x) >> 5; w < g.items; w += nwarps) {
         unsigned int r, xb, r2, yb, bc, zr;
         fast_divmod(w, g.dnxb, r, xb);
@@ -427,23 +429,17 @@ up2_bwd_march_kernel(const float *__restrict__ gout, float *__restrict__ gx, flo
         fast_divmod(r2, g.dnz, bc, zr);
         const int x0 = ((int)xb * 32 + lane) * 2, y0 = (int)yb * UB_RY;
         const bool xok = x0 < d2;                       // d2 is even: x0 + 1 < d2 as well
+        const bool xfirst = x0 == 0, xlast = x0 + 2 == d2;
         const int z0 = (int)zr * g.zrun, z1 = min(d0, z0 + g.zrun);
-        float wx[2][4], wy[UB_RY][4];
-        adj4(x0, d2, wx[0]);
-        adj4(x0 + 1, d2, wx[1]);
-#pragma unroll
-        for (int rr = 0; rr < UB_RY; ++rr) {
-            adj4(y0 + rr, d1, wy[rr]);
-            if (y0 + rr >= d1) wy[rr][0] = wy[rr][1] = wy[rr][2] = wy[rr][3] = 0.0f;
-        }
-        const float *gb = gout + (i64)bc * o0 * o1 * o2;
+        const float *gb = gout + (i64)bc * 2 * d0 * o1 * o2;
         const i64 plane = (i64)o1 * o2;
-        // T(2z-1), T(2z) carried; T(2z+1), T(2z+2) computed per plane (both planes' loads in flight together)
+        // T(2z-1), T(2z) carried; T(2z+1), T(2z+2) computed per plane (both planes' loads in flight together).
+        // Beyond the two z faces T replicates the face plane (see up2_plane_adjoint).
         PlaneRaw ra, rb;
         if (z0 > 0) up2_plane_load(ra, gb + (i64)(2 * z0 - 1) * plane, o1, o2, y0, x0, xok, lane);
         up2_plane_load(rb, gb + (i64)(2 * z0) * plane, o1, o2, y0, x0, xok, lane);
-        T4 ta = (z0 > 0) ? up2_plane_adjoint(ra, lane, wx, wy) : zero;
-        T4 tb = up2_plane_adjoint(rb, lane, wx, wy);
+        T4 tb = up2_plane_adjoint(rb, lane, xfirst, xlast);
+        T4 ta = (z0 > 0) ? up2_plane_adjoint(ra, lane, xfirst, xlast) : tb;
         for (int z = z0; z < z1; ++z) {
 #if PULPO_UP2B_PF
             if (xok && z + 1 < z1) {   // the next iteration's two gradient planes -> L2 (one request per row and lane quad)
@@ -459,16 +455,14 @@ up2_bwd_march_kernel(const float *__restrict__ gout, float *__restrict__ gx, flo
 #endif
             up2_plane_load(ra, gb + (i64)(2 * z + 1) * plane, o1, o2, y0, x0, xok, lane);
             if (z + 1 < d0) up2_plane_load(rb, gb + (i64)(2 * z + 2) * plane, o1, o2, y0, x0, xok, lane);
-            const T4 tc = up2_plane_adjoint(ra, lane, wx, wy);
-            const T4 td = (z + 1 < d0) ? up2_plane_adjoint(rb, lane, wx, wy) : zero;
-            float wz[4];
-            adj4(z, d0, wz);
+            const T4 tc = up2_plane_adjoint(ra, lane, xfirst, xlast);
+            const T4 td = (z + 1 < d0) ? up2_plane_adjoint(rb, lane, xfirst, xlast) : tc;
 #pragma unroll
             for (int rr = 0; rr < UB_RY; ++rr) {
                 if (!xok || y0 + rr >= d1) continue;
                 float2 res;
-                res.x = scale * (wz[0] * ta.v[rr][0] + wz[1] * tb.v[rr][0] + wz[2] * tc.v[rr][0] + wz[3] * td.v[rr][0]);
-                res.y = scale * (wz[0] * ta.v[rr][1] + wz[1] * tb.v[rr][1] + wz[2] * tc.v[rr][1] + wz[3] * td.v[rr][1]);
+                res.x = scale * (0.25f * (ta.v[rr][0] + td.v[rr][0]) + 0.75f * (tb.v[rr][0] + tc.v[rr][0]));
+                res.y = scale * (0.25f * (ta.v[rr][1] + td.v[rr][1]) + 0.75f * (tb.v[rr][1] + tc.v[rr][1]));
                 float2 *o = reinterpret_cast<float2 *>(gx + (((i64)bc * d0 + z) * d1 + y0 + rr) * d2 + x0);
                 if (ACC) {
                     const float2 old = *o;
