@@ -202,7 +202,9 @@ ncc_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
 
         if constexpr (FWD) {
         // forward: pass 1 and pass 2 of a plane back to back across the plane barrier (its two 45-register z rings leave
-        // no room to overlap the passes of consecutive planes: the pipelined order below spills, 96 -> 110 us)
+        // no room to overlap the passes of consecutive planes: the pipelined order below spills, 81 -> 94 us; keeping the
+        // z windows as sums of three planes -- 4 instead of 8 additions, 8 instead of 9 registers per output -- was
+        // measured too: no gain in the backward, more spills in the forward)
         for (int p0 = 0; p0 < nplanes; p0 += W) {
 #pragma unroll
             for (int s = 0; s < W; ++s) {
@@ -224,31 +226,38 @@ ncc_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                 // ---------------- pass 1: y sums of the staged plane (products formed in registers).  Scalar loads
                 // let (I, J) land in one register pair, so everything downstream is packed FADD2 / FMUL2.
                 if (has_item) {
+                    // the forward lives at the register limit (two 45-register z rings per thread): the three y sums
+                    // are formed one after the other from the staged (I, J) pairs -- sum, store, then the next product
+                    // in the same registers -- and pass 2 below handles one quantity at a time as well.  Forming all
+                    // products / loading all staged columns at once spilled ~70 registers: 98 -> 81 us without.
                     const float *r0 = raw + st * NIN * L::RAW_FLOATS + (NT_RY * yrg) * NT_BOXW + XOFF + yc;
-                    float2 a[NVY], b[NVY];
-                    float c[NVY];
+                    const int idx0 = (NT_RY * yrg) * NT_YC + XOFF + yc;
+                    float2 a[NVY];
 #pragma unroll
-                    for (int j = 0; j < NVY; ++j) {
-                        a[j] = make_float2(r0[j * NT_BOXW], r0[L::RAW_FLOATS + j * NT_BOXW]);
-                        if (FWD) {
-                            b[j] = __fmul2_rn(a[j], a[j]);
-                            c[j] = __fmul_rn(a[j].x, a[j].y);
-                        } else {
-                            b[j] = make_float2(0.f, 0.f);
-                            c[j] = r0[2 * L::RAW_FLOATS + j * NT_BOXW];
-                        }
+                    for (int j = 0; j < NVY; ++j) a[j] = make_float2(r0[j * NT_BOXW], r0[L::RAW_FLOATS + j * NT_BOXW]);
+                    {
+                        float2 oA[4];
+                        xsum4<W>(a, oA);
+#pragma unroll
+                        for (int o = 0; o < NT_RY; ++o) YA[idx0 + o * NT_YC] = oA[o];
                     }
-                    float2 oA[4], oB[4];
-                    float oC[4];
-                    xsum4<W>(a, oA);
-                    if (FWD) xsum4<W>(b, oB);
-                    xsum4<W>(c, oC);
+                    asm volatile("" ::: "memory");
+                    {
+                        float c[NVY], oC[4];
 #pragma unroll
-                    for (int o = 0; o < NT_RY; ++o) {
-                        const int idx = (NT_RY * yrg + o) * NT_YC + XOFF + yc;
-                        YA[idx] = oA[o];
-                        if (FWD) YB[idx] = oB[o];
-                        YC[idx] = oC[o];
+                        for (int j = 0; j < NVY; ++j) c[j] = __fmul_rn(a[j].x, a[j].y);
+                        xsum4<W>(c, oC);
+#pragma unroll
+                        for (int o = 0; o < NT_RY; ++o) YC[idx0 + o * NT_YC] = oC[o];
+                    }
+                    asm volatile("" ::: "memory");
+                    {
+                        float2 oB[4];
+#pragma unroll
+                        for (int j = 0; j < NVY; ++j) a[j] = __fmul2_rn(a[j], a[j]);
+                        xsum4<W>(a, oB);
+#pragma unroll
+                        for (int o = 0; o < NT_RY; ++o) YB[idx0 + o * NT_YC] = oB[o];
                     }
                 }
                 __syncthreads();
@@ -261,85 +270,101 @@ ncc_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                     tma_load_box(dst + L::RAW_FLOATS * 4, &tm1, bar, x0 - NT_PADL, y0 - R, zin, bc);
                     if (!FWD) tma_load_box(dst + 2 * L::RAW_FLOATS * 4, &tm2, bar, x0 - NT_PADL, y0 - R, zin, bc);
                 }
-                // ---------------- pass 2: x sums for two adjacent outputs (shared window core) into ring slot s
+                // ---------------- pass 2: x sums for two adjacent outputs (shared window core) into ring slot s, one
+                // quantity after the other (A, then C, then B: at most 10 staged columns in registers next to the rings),
+                // each followed at once by its z window sum (computed on the halo planes too: guarding it spills again)
+                const int cb = ty * NT_YC + 2 * xp + XOFF;   // first y-summed column of this thread's windows
+                float2 sA[2], sB[2];
+                float sC[2];
                 {
-                    float2 PA[NP], PB[NP];
-                    float PC[NP];
-                    const int cb = ty * NT_YC + 2 * xp + XOFF;   // first y-summed column of this thread's windows
-                    if ((XOFF & 1) == 0) {
+                    float2 PA[NP];
 #pragma unroll
-                        for (int t = 0; t < NP / 2; ++t) {
+                    for (int t = 0; t < NP / 2; ++t) {
+                        if ((XOFF & 1) == 0) {
                             const float4 qa = *reinterpret_cast<const float4 *>(YA + cb + 2 * t);
                             PA[2 * t] = make_float2(qa.x, qa.y); PA[2 * t + 1] = make_float2(qa.z, qa.w);
-                            if (FWD) {
-                                const float4 qb = *reinterpret_cast<const float4 *>(YB + cb + 2 * t);
-                                PB[2 * t] = make_float2(qb.x, qb.y); PB[2 * t + 1] = make_float2(qb.z, qb.w);
-                            }
-                            const float2 qc = *reinterpret_cast<const float2 *>(YC + cb + 2 * t);
-                            PC[2 * t] = qc.x; PC[2 * t + 1] = qc.y;
-                        }
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < NP; ++t) {
-                            PA[t] = YA[cb + t];
-                            if (FWD) PB[t] = YB[cb + t];
-                            PC[t] = YC[cb + t];
+                        } else {
+                            PA[2 * t] = YA[cb + 2 * t]; PA[2 * t + 1] = YA[cb + 2 * t + 1];
                         }
                     }
                     float2 coreA = PA[1];
-                    float coreC = PC[1];
 #pragma unroll
-                    for (int t = 2; t < W; ++t) {
-                        coreA = add2(coreA, PA[t]);
-                        coreC = add2(coreC, PC[t]);
-                    }
+                    for (int t = 2; t < W; ++t) coreA = add2(coreA, PA[t]);
                     rA[s][0] = add2(PA[0], coreA);
                     rA[s][1] = add2(coreA, PA[W]);
-                    rC[s][0] = add2(PC[0], coreC);
-                    rC[s][1] = add2(coreC, PC[W]);
-                    if (FWD) {
-                        float2 coreB = PB[1];
 #pragma unroll
-                        for (int t = 2; t < W; ++t) coreB = add2(coreB, PB[t]);
-                        rB[FWD ? s : 0][0] = add2(PB[0], coreB);
-                        rB[FWD ? s : 0][1] = add2(coreB, PB[W]);
+                    for (int o = 0; o < 2; ++o) {
+                        sA[o] = rA[0][o];
+#pragma unroll
+                        for (int u = 1; u < W; ++u) sA[o] = add2(sA[o], rA[u][o]);
                     }
                 }
-                // ---------------- z window + epilogue
+                asm volatile("" ::: "memory");
+                {
+                    float PC[NP];
+#pragma unroll
+                    for (int t = 0; t < NP / 2; ++t) {
+                        if ((XOFF & 1) == 0) {
+                            const float2 qc = *reinterpret_cast<const float2 *>(YC + cb + 2 * t);
+                            PC[2 * t] = qc.x; PC[2 * t + 1] = qc.y;
+                        } else {
+                            PC[2 * t] = YC[cb + 2 * t]; PC[2 * t + 1] = YC[cb + 2 * t + 1];
+                        }
+                    }
+                    float coreC = PC[1];
+#pragma unroll
+                    for (int t = 2; t < W; ++t) coreC = add2(coreC, PC[t]);
+                    rC[s][0] = add2(PC[0], coreC);
+                    rC[s][1] = add2(coreC, PC[W]);
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) {
+                        sC[o] = rC[0][o];
+#pragma unroll
+                        for (int u = 1; u < W; ++u) sC[o] = add2(sC[o], rC[u][o]);
+                    }
+                }
+                asm volatile("" ::: "memory");
+                {
+                    float2 PB[NP];
+#pragma unroll
+                    for (int t = 0; t < NP / 2; ++t) {
+                        if ((XOFF & 1) == 0) {
+                            const float4 qb = *reinterpret_cast<const float4 *>(YB + cb + 2 * t);
+                            PB[2 * t] = make_float2(qb.x, qb.y); PB[2 * t + 1] = make_float2(qb.z, qb.w);
+                        } else {
+                            PB[2 * t] = YB[cb + 2 * t]; PB[2 * t + 1] = YB[cb + 2 * t + 1];
+                        }
+                    }
+                    float2 coreB = PB[1];
+#pragma unroll
+                    for (int t = 2; t < W; ++t) coreB = add2(coreB, PB[t]);
+                    rB[s][0] = add2(PB[0], coreB);
+                    rB[s][1] = add2(coreB, PB[W]);
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) {
+                        sB[o] = rB[0][o];
+#pragma unroll
+                        for (int u = 1; u < W; ++u) sB[o] = add2(sB[o], rB[u][o]);
+                    }
+                }
+                // ---------------- epilogue
                 if (pl >= 2 * R && live) {
                     const i64 off = obase + (i64)zout * sz;
                     float ra[2], rb[2], rc[2];
 #pragma unroll
                     for (int o = 0; o < 2; ++o) {
-                        float2 sA = rA[0][o], sB = FWD ? rB[0][o] : make_float2(0.f, 0.f);
-                        float sC = rC[0][o];
-#pragma unroll
-                        for (int u = 1; u < W; ++u) {
-                            sA = add2(sA, rA[u][o]);
-                            if (FWD) sB = add2(sB, rB[u % (FWD ? W : 1)][o]);
-                            sC = add2(sC, rC[u][o]);
-                        }
-                        if (FWD) {
-                            if (p.o0) {
-                                const NccPoint r = ncc_point<true>(sA.x, sA.y, sB.x, sB.y, sC, p.Wf, p.rcpW);
-                                cc_acc += r.cc;
-                                ra[o] = r.a; rb[o] = r.b; rc[o] = r.c;
-                            } else {
-                                cc_acc += ncc_point<false>(sA.x, sA.y, sB.x, sB.y, sC, p.Wf, p.rcpW).cc;
-                            }
+                        if (p.o0) {
+                            const NccPoint r = ncc_point<true>(sA[o].x, sA[o].y, sB[o].x, sB[o].y, sC[o], p.Wf, p.rcpW);
+                            cc_acc += r.cc;
+                            ra[o] = r.a; rb[o] = r.b; rc[o] = r.c;
                         } else {
-                            const float iv = o ? Iv.y : Iv.x, jv = o ? Jv.y : Jv.x;
-                            ra[o] = gk * (iv * sA.x + sA.y + 2.0f * jv * sC);
+                            cc_acc += ncc_point<false>(sA[o].x, sA[o].y, sB[o].x, sB[o].y, sC[o], p.Wf, p.rcpW).cc;
                         }
                     }
-                    if (FWD) {
-                        if (p.o0) {
-                            *reinterpret_cast<float2 *>(p.o0 + off) = make_float2(ra[0], ra[1]);
-                            *reinterpret_cast<float2 *>(p.o1 + off) = make_float2(rb[0], rb[1]);
-                            *reinterpret_cast<float2 *>(p.o2 + off) = make_float2(rc[0], rc[1]);
-                        }
-                    } else {
+                    if (p.o0) {
                         *reinterpret_cast<float2 *>(p.o0 + off) = make_float2(ra[0], ra[1]);
+                        *reinterpret_cast<float2 *>(p.o1 + off) = make_float2(rb[0], rb[1]);
+                        *reinterpret_cast<float2 *>(p.o2 + off) = make_float2(rc[0], rc[1]);
                     }
                 }
             }
