@@ -355,7 +355,7 @@ def run_ours(args):
     nvox = size[0] * size[1] * size[2]
     B = args.batch
     plan_kw = dict(fuse_reg=bool(args.fuse_reg), fuse_combine=bool(args.fuse_combine), pool_pyramid=bool(args.pool_pyramid),
-                   aux_early=bool(args.aux_early), dpos=bool(args.dpos), aux_after=args.aux_after)
+                   aux_early=bool(args.aux_early), dpos=bool(args.dpos), aux_after=args.aux_after, reg_coarse=bool(args.reg_coarse))
     x_h, y_h, d_h, m_h, s_h = syn.make_hot_path_inputs(size, total, latent, seed=rank, batch=B,
                                                        field_sigma_vox=args.field_sigma_vox, max_abs=args.field_max_abs)
     host = [x_h, y_h] + [d_h[l] for l in range(latent)] + [m_h[l] for l in range(latent)] + [s_h[l] for l in range(latent)]
@@ -914,6 +914,7 @@ def main():
     ap.add_argument("--fuse-combine", type=int, default=0, help="plan engine: pyramid combination inside the integration launches (1) or separate launches (0)")
     ap.add_argument("--pool-pyramid", type=int, default=1, help="plan engine: moving-image pyramid in one launch (1) or one launch per level (0)")
     ap.add_argument("--aux-early", type=int, default=0, help="plan engine: pyramid + KL start with the step (1) or after the integration (0)")
+    ap.add_argument("--reg-coarse", type=int, default=0, help="plan engine: regulariser of the x2-resized level in closed form on the coarse field (aux stream), backward = resize adjoint of gmoved * dpos formed on the fly (1) or a full-resolution regulariser + product pass (0)")
     ap.add_argument("--aux-after", default="up2", choices=["integ", "up2", "warp"],
                     help="plan engine: the aux stream (moving-image pyramid, KL) starts after the integration, after level 0's output resize or after level 0's warp")
     ap.add_argument("--field-sigma-vox", type=float, default=None,

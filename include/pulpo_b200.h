@@ -170,6 +170,14 @@ int pulpo_resize_up_fwd(const float *x, const float *addend, float *out, int fac
 int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, float scale, int accumulate,
                         int B, int C, int d0, int d1, int d2, pulpo_stream_t stream);
 
+/* The x2 output resize's adjoint (src/components/pulpo.py:314, autograd) with its input gradient formed on the fly
+ * from the warp's stored dpos (pulpo_warp3d_fwd_dpos):  gx (+)= scale * up2^T( gout * dpos ),  gout [B,1,2d0,2d1,2d2]
+ * (upstream gradient of the moved image), dpos [B,3,2d0,2d1,2d2], gx [B,3,d0,d1,d2] -- the full-resolution field
+ * gradient never exists in HBM.  Needs d2 even, d0 >= 2, 16-byte aligned pointers (PULPO_ERR_UNSUPPORTED otherwise:
+ * use pulpo_warp3d_bwd_dpos + pulpo_resize_up_bwd). */
+int pulpo_resize_up2_bwd_dpos(const float *gout, const float *dpos, float *gx, float scale, int accumulate,
+                              int B, int d0, int d1, int d2, pulpo_stream_t stream);
+
 /* ---- a10: F.interpolate(y, size=..., trilinear, align_corners=False)  src/losses.py:313 --- */
 int pulpo_interp_size_fwd(const float *x, float *out, int B, int C, int i0, int i1, int i2,
                           int o0, int o1, int o2, pulpo_stream_t stream);
@@ -251,6 +259,17 @@ int pulpo_l2reg_bwd(const float *gloss, const float *f, float lamb, float *gf, i
 int pulpo_l2reg_fwd_bwd(const float *f, float lamb, float *out, const float *gout, const float *dpos,
                         float *gf, int accumulate, void *ws, size_t ws_bytes, int B, int C, int D0, int D1,
                         int D2, pulpo_stream_t stream);
+
+/* L2_reg of the x2 up-sampled field, evaluated on the coarse grid: out = L2_reg(ResizeTransform(1/2)(v), lamb) with
+ * ResizeTransform(1/2)(v) = trilinear_up_2(2 v) (src/network_blocks.py:138-150; the hot path regularises exactly this
+ * field at level 0, src/components/pulpo.py:314 + src/models.py:162), gv (+)= d out / d v.  v, gv: [B,C,d0,d1,d2].
+ * Closed form (see csrc/losses.cu): the fine forward differences are fixed combinations of the coarse ones, so neither
+ * the fine field nor its gradient is touched; three 1-D passes over coarse arrays.  scratch: caller-owned,
+ * pulpo_l2reg_up2_scratch_bytes() bytes (no initialisation needed); ws: pulpo_reduce_ws_bytes() bytes, zeroed once. */
+size_t pulpo_l2reg_up2_scratch_bytes(int B, int C, int d0, int d1, int d2);
+int pulpo_l2reg_up2_fwd_bwd(const float *v, float lamb, float *out, float *gv, int accumulate, void *scratch,
+                            size_t scratch_bytes, void *ws, size_t ws_bytes, int B, int C, int d0, int d1, int d2,
+                            pulpo_stream_t stream);
 
 /* ---- f-2: jacobian_det(deformation_field, normalize) / JDetStd   src/losses.py:147-204 (3-D branch) ----
  * det: [B,D0,D1,D2] (the reference returns jacobian[:,0,0]-shaped maps).  Replication-padded central

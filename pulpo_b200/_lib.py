@@ -62,6 +62,7 @@ SIGNATURES = {
     "pulpo_combine_vecint_multi_bwd": (_i, [ctypes.POINTER(VecIntLevel), _i, _i, _i, _i, _vp]),
     "pulpo_resize_up_fwd": (_i, [_vp, _vp, _vp, _i, _f, _i, _i, _i, _i, _i, _vp]),
     "pulpo_resize_up_bwd": (_i, [_vp, _vp, _i, _f, _i, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_resize_up2_bwd_dpos": (_i, [_vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp]),
     "pulpo_interp_size_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_avgpool2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "pulpo_avgpool2_pyramid_fwd": (_i, [_vp, ctypes.POINTER(ctypes.c_void_p), _i, _i, _i, _i, _i, _i, _vp]),
@@ -78,6 +79,8 @@ SIGNATURES = {
     "pulpo_l2reg_fwd": (_i, [_vp, _f, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "pulpo_l2reg_bwd": (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pulpo_l2reg_fwd_bwd": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _i, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "pulpo_l2reg_up2_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "pulpo_l2reg_up2_fwd_bwd": (_i, [_vp, _f, _vp, _vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "pulpo_jacdet_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "pulpo_jacdet_bwd_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "pulpo_jacdet_bwd": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),

@@ -375,17 +375,28 @@ struct PlaneRaw {
 // All loads of a plane are issued back to back (six independent 128-bit loads + the edge lanes'
 // scalars); the shuffles and the arithmetic come later (a load placed after a shuffle waits for it:
 // that version ran at 0.8 TB/s with one load in flight per warp).
-__device__ __forceinline__ void up2_plane_load(PlaneRaw &p, const float *__restrict__ plane, int o1, int o2, int y0, int x0,
-                                               bool xok, int lane)
+// PROD: the gradient plane is formed on the fly as gm * plane -- the warp's gather-half backward gdf = gmoved * dpos
+// (warp3d.cu, pulpo_warp3d_fwd_dpos), so the full-resolution field gradient never exists in HBM; `mul` is the same
+// plane of the one-channel upstream gradient.
+template <bool PROD>
+__device__ __forceinline__ void up2_plane_load(PlaneRaw &p, const float *__restrict__ vol, const float *__restrict__ mvol,
+                                               i64 plane_off, int o1, int o2, int y0, int x0, bool xok, int lane)
 {
+    const float *plane = vol + plane_off, *mul = PROD ? mvol + plane_off : nullptr;
     const bool need_l = (lane == 0) && xok && x0 > 0, need_r = (lane == 31) && xok && (2 * x0 + 4 < o2);
 #pragma unroll
     for (int b = 0; b < UB_RY + 4; ++b) {
         int oy = 2 * y0 - 1 + b;
-        oy = oy < 0 ? 0 : (oy > o1 - 1 ? o1 - 1 : oy);   // out-of-range rows carry weight 0
-        const float *row = plane + (i64)oy * o2;
-        p.c[b] = xok ? ld_stream4(row + 2 * x0) : make_float4(0.f, 0.f, 0.f, 0.f);
-        p.e[b] = (need_l || need_r) ? __ldg(row + 2 * x0 + (need_l ? -1 : 4)) : 0.0f;
+        oy = oy < 0 ? 0 : (oy > o1 - 1 ? o1 - 1 : oy);   // clamped rows replicate the edge rows (see up2_plane_adjoint)
+        const i64 ro = (i64)oy * o2 + 2 * x0;
+        p.c[b] = xok ? ld_stream4(plane + ro) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int eo = need_l ? -1 : 4;
+        p.e[b] = (need_l || need_r) ? __ldg(plane + ro + eo) : 0.0f;
+        if (PROD) {
+            const float4 m = xok ? ld_stream4(mul + ro) : make_float4(0.f, 0.f, 0.f, 0.f);
+            p.c[b].x *= m.x; p.c[b].y *= m.y; p.c[b].z *= m.z; p.c[b].w *= m.w;
+            if (need_l || need_r) p.e[b] *= __ldg(mul + ro + eo);
+        }
     }
 }
 
@@ -415,9 +426,10 @@ __device__ __forceinline__ T4 up2_plane_adjoint(const PlaneRaw &p, int lane, boo
     return t;
 }
 
-template <bool ACC>
+template <bool ACC, bool PROD>
 __global__ void __launch_bounds__(256, 2)
-up2_bwd_march_kernel(const float *__restrict__ gout, float *__restrict__ gx, float scale, const Up2MGeom g)
+up2_bwd_march_kernel(const float *__restrict__ gout, const float *__restrict__ gmul, float *__restrict__ gx, float scale,
+                     const Up2MGeom g)
 {
     const unsigned int nwarps = gridDim.x * 8u;
     const int lane = threadIdx.x & 31;
@@ -432,14 +444,25 @@ up2_bwd_march_kernel(const float *__restrict__ gout, float *__restrict__ gx, flo
         const bool xfirst = x0 == 0, xlast = x0 + 2 == d2;
         const int z0 = (int)zr * g.zrun, z1 = min(d0, z0 + g.zrun);
         const float *gb = gout + (i64)bc * 2 * d0 * o1 * o2;
+        const float *gm = PROD ? gmul + (i64)(bc / 3u) * 2 * d0 * o1 * o2 : nullptr;   // fields have 3 channels
         const i64 plane = (i64)o1 * o2;
         // T(2z-1), T(2z) carried; T(2z+1), T(2z+2) computed per plane (both planes' loads in flight together).
         // Beyond the two z faces T replicates the face plane (see up2_plane_adjoint).
         PlaneRaw ra, rb;
-        if (z0 > 0) up2_plane_load(ra, gb + (i64)(2 * z0 - 1) * plane, o1, o2, y0, x0, xok, lane);
-        up2_plane_load(rb, gb + (i64)(2 * z0) * plane, o1, o2, y0, x0, xok, lane);
-        T4 tb = up2_plane_adjoint(rb, lane, xfirst, xlast);
-        T4 ta = (z0 > 0) ? up2_plane_adjoint(ra, lane, xfirst, xlast) : tb;
+        T4 ta, tb;
+        if (PROD) {
+            up2_plane_load<PROD>(rb, gb, gm, (i64)(2 * z0) * plane, o1, o2, y0, x0, xok, lane);
+            tb = up2_plane_adjoint(rb, lane, xfirst, xlast);
+            asm volatile("" ::: "memory");
+            if (z0 > 0) up2_plane_load<PROD>(ra, gb, gm, (i64)(2 * z0 - 1) * plane, o1, o2, y0, x0, xok, lane);
+            ta = (z0 > 0) ? up2_plane_adjoint(ra, lane, xfirst, xlast) : tb;
+            asm volatile("" ::: "memory");
+        } else {
+            if (z0 > 0) up2_plane_load<PROD>(ra, gb, gm, (i64)(2 * z0 - 1) * plane, o1, o2, y0, x0, xok, lane);
+            up2_plane_load<PROD>(rb, gb, gm, (i64)(2 * z0) * plane, o1, o2, y0, x0, xok, lane);
+            tb = up2_plane_adjoint(rb, lane, xfirst, xlast);
+            ta = (z0 > 0) ? up2_plane_adjoint(ra, lane, xfirst, xlast) : tb;
+        }
         for (int z = z0; z < z1; ++z) {
 #if PULPO_UP2B_PF
             if (xok && z + 1 < z1) {   // the next iteration's two gradient planes -> L2 (one request per row and lane quad)
@@ -453,10 +476,19 @@ up2_bwd_march_kernel(const float *__restrict__ gout, float *__restrict__ gx, flo
                 }
             }
 #endif
-            up2_plane_load(ra, gb + (i64)(2 * z + 1) * plane, o1, o2, y0, x0, xok, lane);
-            if (z + 1 < d0) up2_plane_load(rb, gb + (i64)(2 * z + 2) * plane, o1, o2, y0, x0, xok, lane);
-            const T4 tc = up2_plane_adjoint(ra, lane, xfirst, xlast);
-            const T4 td = (z + 1 < d0) ? up2_plane_adjoint(rb, lane, xfirst, xlast) : tc;
+            up2_plane_load<PROD>(ra, gb, gm, (i64)(2 * z + 1) * plane, o1, o2, y0, x0, xok, lane);
+            T4 tc, td;
+            if (PROD) {
+                // two sources per row: one plane at a time, or the 24 128-bit loads of both planes spill
+                tc = up2_plane_adjoint(ra, lane, xfirst, xlast);
+                asm volatile("" ::: "memory");
+                if (z + 1 < d0) up2_plane_load<PROD>(rb, gb, gm, (i64)(2 * z + 2) * plane, o1, o2, y0, x0, xok, lane);
+                td = (z + 1 < d0) ? up2_plane_adjoint(rb, lane, xfirst, xlast) : tc;
+            } else {
+                if (z + 1 < d0) up2_plane_load<PROD>(rb, gb, gm, (i64)(2 * z + 2) * plane, o1, o2, y0, x0, xok, lane);
+                tc = up2_plane_adjoint(ra, lane, xfirst, xlast);
+                td = (z + 1 < d0) ? up2_plane_adjoint(rb, lane, xfirst, xlast) : tc;
+            }
 #pragma unroll
             for (int rr = 0; rr < UB_RY; ++rr) {
                 if (!xok || y0 + rr >= d1) continue;
@@ -615,6 +647,46 @@ extern "C" int pulpo_resize_up_fwd(const float *x, const float *addend, float *o
     return launch_status();
 }
 
+// preconditions of the z-marching x2 adjoint
+static bool up2_march_ok(const void *gout, const void *gx, int factor, int BC, int d0, int d1, int d2)
+{
+    return factor == 2 && (d2 % 2 == 0) && aligned16(gout) && aligned16(gx) && d0 >= 2 &&
+           (i64)BC * d0 * d1 * d2 * 8 < (1ll << 31);
+}
+
+// gmul != nullptr: the gradient is gout * gmul, formed on the fly (see up2_plane_load)
+static int launch_up2_bwd_march(const float *gout, const float *gmul, float *gx, float scale, int accumulate, int BC, int d0,
+                                int d1, int d2, cudaStream_t st)
+{
+    Up2MGeom g;
+    g.BC = BC; g.d0 = d0; g.d1 = d1; g.d2 = d2;
+    g.nxb = (d2 / 2 + 31) / 32;
+    g.nyb = (d1 + UB_RY - 1) / UB_RY;
+    int dev = 0, sms = kSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const i64 columns = (i64)g.BC * g.nyb * g.nxb;
+    i64 grid = (columns * d0 + 7) / 8;                 // CTAs if every warp took one plane
+    if (grid > (i64)sms * 2) grid = (i64)sms * 2;
+    if (grid < 1) grid = 1;
+    i64 per_col = (2 * grid * 8 + columns - 1) / columns;   // ~2 runs per resident warp
+    if (per_col < 1) per_col = 1;
+    if (per_col > d0) per_col = d0;
+    g.zrun = (int)((d0 + per_col - 1) / per_col);
+    g.nzrun = (d0 + g.zrun - 1) / g.zrun;
+    g.items = (unsigned int)(columns * g.nzrun);
+    g.dnxb = make_fastdiv(g.nxb); g.dnyb = make_fastdiv(g.nyb); g.dnz = make_fastdiv(g.nzrun);
+    const unsigned int gr = (unsigned int)grid;
+    if (gmul) {
+        if (accumulate) up2_bwd_march_kernel<true, true><<<gr, 256, 0, st>>>(gout, gmul, gx, scale, g);
+        else up2_bwd_march_kernel<false, true><<<gr, 256, 0, st>>>(gout, gmul, gx, scale, g);
+    } else {
+        if (accumulate) up2_bwd_march_kernel<true, false><<<gr, 256, 0, st>>>(gout, nullptr, gx, scale, g);
+        else up2_bwd_march_kernel<false, false><<<gr, 256, 0, st>>>(gout, nullptr, gx, scale, g);
+    }
+    return launch_status();
+}
+
 extern "C" int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, float scale, int accumulate, int B,
                                    int C, int d0, int d1, int d2, pulpo_stream_t stream)
 {
@@ -622,32 +694,8 @@ extern "C" int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, flo
     PULPO_REQUIRE(gout && gx, PULPO_ERR_NULL_POINTER);
     PULPO_REQUIRE(B > 0 && C > 0 && d0 > 0 && d1 > 0 && d2 > 0, PULPO_ERR_INVALID_SHAPE);
     PULPO_REQUIRE(factor >= 2 && factor <= 64, PULPO_ERR_UNSUPPORTED);
-    if (factor == 2 && (d2 % 2 == 0) && aligned16(gout) && aligned16(gx) && d0 >= 2 &&
-        (i64)B * C * d0 * d1 * d2 * 8 < (1ll << 31)) {
-        Up2MGeom g;
-        g.BC = B * C; g.d0 = d0; g.d1 = d1; g.d2 = d2;
-        g.nxb = (d2 / 2 + 31) / 32;
-        g.nyb = (d1 + UB_RY - 1) / UB_RY;
-        int dev = 0, sms = kSMs;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const i64 columns = (i64)g.BC * g.nyb * g.nxb;
-        i64 grid = (columns * d0 + 7) / 8;                 // CTAs if every warp took one plane
-        if (grid > (i64)sms * 2) grid = (i64)sms * 2;
-        if (grid < 1) grid = 1;
-        i64 per_col = (2 * grid * 8 + columns - 1) / columns;   // ~2 runs per resident warp
-        if (per_col < 1) per_col = 1;
-        if (per_col > d0) per_col = d0;
-        g.zrun = (int)((d0 + per_col - 1) / per_col);
-        g.nzrun = (d0 + g.zrun - 1) / g.zrun;
-        g.items = (unsigned int)(columns * g.nzrun);
-        g.dnxb = make_fastdiv(g.nxb); g.dnyb = make_fastdiv(g.nyb); g.dnz = make_fastdiv(g.nzrun);
-        if (accumulate)
-            up2_bwd_march_kernel<true><<<(unsigned int)grid, 256, 0, (cudaStream_t)stream>>>(gout, gx, scale, g);
-        else
-            up2_bwd_march_kernel<false><<<(unsigned int)grid, 256, 0, (cudaStream_t)stream>>>(gout, gx, scale, g);
-        return launch_status();
-    }
+    if (up2_march_ok(gout, gx, factor, B * C, d0, d1, d2))
+        return launch_up2_bwd_march(gout, nullptr, gx, scale, accumulate, B * C, d0, d1, d2, (cudaStream_t)stream);
     if (factor == 2 && (d2 % 4 == 0) && aligned16(gout) && aligned16(gx) && (i64)B * C * d0 * d1 * d2 < (1ll << 31)) {
         Up2BGeom g;
         g.BC = B * C; g.d0 = d0; g.d1 = d1; g.d2 = d2; g.XQ = d2 / 4;
@@ -663,6 +711,16 @@ extern "C" int pulpo_resize_up_bwd(const float *gout, float *gx, int factor, flo
     upsample_bwd_kernel<<<grid_for(total, 128, 16), 128, 0, (cudaStream_t)stream>>>(gout, gx, factor, scale, B * C,
                                                                                   d0, d1, d2, accumulate);
     return launch_status();
+}
+
+extern "C" int pulpo_resize_up2_bwd_dpos(const float *gout, const float *dpos, float *gx, float scale, int accumulate,
+                                         int B, int d0, int d1, int d2, pulpo_stream_t stream)
+{
+    PULPO_NVTX("pulpo_resize_up2_bwd_dpos");
+    PULPO_REQUIRE(gout && dpos && gx, PULPO_ERR_NULL_POINTER);
+    PULPO_REQUIRE(B > 0 && d0 > 0 && d1 > 0 && d2 > 0, PULPO_ERR_INVALID_SHAPE);
+    PULPO_REQUIRE(up2_march_ok(dpos, gx, 2, B * 3, d0, d1, d2) && aligned16(gout), PULPO_ERR_UNSUPPORTED);
+    return launch_up2_bwd_march(dpos, gout, gx, scale, accumulate, B * 3, d0, d1, d2, (cudaStream_t)stream);
 }
 
 extern "C" int pulpo_interp_size_fwd(const float *x, float *out, int B, int C, int i0, int i1, int i2, int o0,

@@ -44,7 +44,7 @@ class HotPathPlan:
     def __init__(self, input_size, total_levels, latent_levels, batch=1, beta=0.1, gamma=0.05, lamb=0.025,
                  with_reg=True, nsteps=7, coord_mode=CPU_EXACT, device=None, multi_stream=True, fuse_reg=True,
                  vecint_mode=CPU_EXACT, fuse_combine=False, pool_pyramid=True, aux_early=False, df_resolution="level_res",
-                 dpos=True, aux_after="up2"):
+                 dpos=True, aux_after="up2", reg_coarse=False):
         self.L = L = latent_levels
         self.B = B = batch
         self.lk = lk = total_levels - latent_levels
@@ -109,6 +109,18 @@ class HotPathPlan:
         self.abc = {l: buf(3, B, 1, *self.outsz[l]) for l in range(L)}
         self.gmoved = {l: buf(B, 1, *self.outsz[l]) for l in range(L)}
         self.dposb = {l: buf(B, 3, *self.outsz[l]) for l in range(L)} if self.dpos else {}
+        # reg_coarse (opt-in): on levels with a x2 output resize the regulariser of the final field is evaluated in closed
+        # form on the integrated (coarse) field -- value and gradient, three 1-D passes over 10 MB arrays on a side stream
+        # as soon as the integration is done (pulpo_l2reg_up2_fwd_bwd) -- and the level's backward is ONE launch: the
+        # resize adjoint of gmoved * dpos, formed on the fly and accumulated on top (pulpo_resize_up2_bwd_dpos), so
+        # neither the full-resolution field gradient nor a full-resolution regulariser pass exists.  Measured at config 2:
+        # the level-0 chain gets 12 us shorter, but the side-stream kernels cannot overlap the register-saturated
+        # level-0 kernels (they wait for CTA slots, 62 us of work stretch to 170 us and delay the coarse levels):
+        # 0.731 vs 0.683 ms per step.  Default: the regulariser's value + gradient pass over the final field carries the
+        # product (pulpo_l2reg_fwd_bwd), then the resize adjoint.
+        self.reg_coarse = {l: bool(reg_coarse) and self.dpos and self.with_reg and self.ofac[l] == 2 and self.insz[l][2] % 2 == 0
+                           and self.insz[l][0] >= 2 for l in range(L)}
+        self.reg_scr = {l: buf(lib.pulpo_l2reg_up2_scratch_bytes(B, 3, *self.insz[l]) // 4) for l in range(L) if self.reg_coarse[l]}
         self.gfinal = {l: buf(B, 3, *self.outsz[l]) for l in range(L)}
         self.ginteg = {l: (buf(B, 3, *self.insz[l]) if self.outsz[l] != self.insz[l] else self.gfinal[l]) for l in range(L)}
         self.gdf = {l: buf(B, 3, *self.insz[l]) for l in range(L)}
@@ -137,7 +149,8 @@ class HotPathPlan:
         # kept waiting for CTA slots by the small kernels of the coarser levels / the aux stream (PULPO_PLAN_PRIO=0: off)
         import os
         prio = os.environ.get("PULPO_PLAN_PRIO", "1") != "0"
-        self.streams = [torch.cuda.Stream(device=dev, priority=(-1 if (prio and l == 0) else 0)) for l in range(L + 1)] \
+        # streams: one per level, the aux stream (moving-image pyramid, KL), the coarse-grid regulariser's stream
+        self.streams = [torch.cuda.Stream(device=dev, priority=(-1 if (prio and l == 0) else 0)) for l in range(L + 2)] \
             if multi_stream else None
         self.launches = 0
 
@@ -154,6 +167,7 @@ class HotPathPlan:
         ms = self.multi_stream
         lv = [self.streams[l] if ms else cur for l in range(L)]
         aux = self.streams[L] if ms else cur
+        regs = self.streams[L + 1] if ms else cur
         n = [0]
 
         def call(fn, *a):
@@ -258,6 +272,14 @@ class HotPathPlan:
             if dout != din:
                 call(lib.pulpo_resize_up_fwd, _p(self.integ[l]), None, _p(self.final[l]), self.ofac[l], float(self.ofac[l]),
                      B, 3, *din, hs)
+            ev_reg = None
+            if self.reg_coarse[l]:
+                if ms:
+                    regs.wait_event(ev_int)
+                call(lib.pulpo_l2reg_up2_fwd_bwd, _p(self.integ[l]), self.lamb_eff[l], self._loss_ptr(2, l), _p(self.ginteg[l]), 0,
+                     _p(self.reg_scr[l]), self.reg_scr[l].numel() * 4, _p(self.ws_l2[l]), self.ws_l2[l].numel(), B, 3, *din, H(regs))
+                ev_reg = torch.cuda.Event()
+                ev_reg.record(regs)
             if late_aux and l == 0 and self.aux_after == "up2":
                 ev_kl = aux_after_level0(s)
             # warp the (pooled) moving image
@@ -284,7 +306,11 @@ class HotPathPlan:
                  wsn.numel(), self.win[l], self.gamma_eff[l], B, 1, *dout, hs)
             call(lib.pulpo_ncc_bwd, _p(self.abc[l]), _p(self.moved[l]), _p(yt), None, _p(self.gmoved[l]),
                  self.win[l], self.gamma_eff[l], B, 1, *dout, hs)
-            if self.dpos and self.with_reg:
+            if self.reg_coarse[l]:
+                if ms:
+                    s.wait_event(ev_reg)
+                call(lib.pulpo_resize_up2_bwd_dpos, _p(self.gmoved[l]), _p(self.dposb[l]), _p(self.ginteg[l]), 2.0, 1, B, *din, hs)
+            elif self.dpos and self.with_reg:
                 # L2_reg value + gradient and the warp's backward (gmoved * dpos) in one pass over the final field
                 call(lib.pulpo_l2reg_fwd_bwd, _p(self.final[l]), self.lamb_eff[l], self._loss_ptr(2, l), _p(self.gmoved[l]),
                      _p(self.dposb[l]), _p(self.gfinal[l]), 0, _p(self.ws_l2[l]), self.ws_l2[l].numel(), B, 3, *dout, hs)
@@ -301,7 +327,7 @@ class HotPathPlan:
                      _p(self.ws_l2[l]), self.ws_l2[l].numel(), B, 3, *dout, hs)
                 call(lib.pulpo_l2reg_bwd, None, _p(self.final[l]), self.lamb_eff[l], _p(self.gfinal[l]), 1, B, 3,
                      *dout, hs)
-            if dout != din:
+            if dout != din and not self.reg_coarse[l]:
                 call(lib.pulpo_resize_up_bwd, _p(self.gfinal[l]), _p(self.ginteg[l]), self.ofac[l], float(self.ofac[l]), 0,
                      B, 3, *din, hs)
             ev_done[l] = torch.cuda.Event()

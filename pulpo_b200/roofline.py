@@ -56,6 +56,9 @@ def algo_bytes(name, args):
     if name == "pulpo_resize_up_bwd":       # gout, gx, factor, scale, accumulate, B, C, d0, d1, d2
         f, B, C, n = a[2], a[5], a[6], a[7] * a[8] * a[9]
         return B * C * 4 * (n * (2 if a[4] else 1) + n * f ** 3)
+    if name == "pulpo_resize_up2_bwd_dpos":  # gout, dpos, gx, scale, accumulate, B, d0, d1, d2: warp bwd (32 B / voxel) + x2 adjoint
+        n = a[5] * a[6] * a[7] * a[8]
+        return n * 8 * 32 + n * 12 * (2 if a[4] else 1)
     if name == "pulpo_interp_size_fwd":     # x, out, B, C, i0, i1, i2, o0, o1, o2
         return a[2] * a[3] * 4 * (a[4] * a[5] * a[6] + a[7] * a[8] * a[9])
     if name == "pulpo_avgpool2_fwd":        # x, out, B, C, D0, D1, D2

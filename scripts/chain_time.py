@@ -37,7 +37,9 @@ def main():
     ws = torch.zeros(L.pulpo_reduce_ws_bytes(), dtype=torch.uint8, device="cuda")
     wsn = torch.zeros(L.pulpo_ncc_ws_bytes(1, 1, *full), dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
+    rscr = torch.empty(L.pulpo_l2reg_up2_scratch_bytes(1, 3, *half) // 4, device="cuda")
     ops = [
+        ("l2reg_up2 (coarse)", lambda: L.pulpo_l2reg_up2_fwd_bwd(vp(integ), 0.025, vp(reg), vp(ginteg), 0, vp(rscr), rscr.numel() * 4, vp(ws), ws.numel(), 1, 3, *half, st)),
         ("resize_up_fwd x2", lambda: L.pulpo_resize_up_fwd(vp(integ), None, vp(final), 2, 2.0, 1, 3, *half, st)),
         ("warp3d_l2reg_fwd", lambda: L.pulpo_warp3d_l2reg_fwd(vp(x), vp(final), vp(moved), 0.025, vp(reg), vp(ws), ws.numel(), 1, 1, *full, 0, st)),
         ("warp3d_fwd", lambda: L.pulpo_warp3d_fwd(vp(x), vp(final), vp(moved), None, 1, 1, *full, 0, st)),
@@ -49,6 +51,7 @@ def main():
         ("l2reg_fwd_bwd", lambda: L.pulpo_l2reg_fwd_bwd(vp(final), 0.025, vp(reg), None, None, vp(gfinal), 0, vp(ws), ws.numel(), 1, 3, *full, st)),
         ("warp3d_bwd_dpos", lambda: L.pulpo_warp3d_bwd_dpos(vp(gmoved), vp(dpos), vp(gfinal), 0, 1, *full, st)),
         ("resize_up_bwd x2", lambda: L.pulpo_resize_up_bwd(vp(gfinal), vp(ginteg), 2, 2.0, 0, 1, 3, *half, st)),
+        ("resize_up2_bwd_dpos", lambda: L.pulpo_resize_up2_bwd_dpos(vp(gmoved), vp(dpos), vp(ginteg), 2.0, 1, 1, *half, st)),
     ]
     for name, fn in ops:
         if only and not any(o in name for o in only):

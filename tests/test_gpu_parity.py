@@ -629,7 +629,7 @@ def _run_plan(g_or_inputs, total, latent, size, B, multi_stream=True, graph=Fals
     (False, False, True, {}), (True, False, False, {}), (True, True, True, {}),
     (True, True, True, {"fuse_combine": True, "pool_pyramid": False, "aux_early": True}),
     (False, False, True, {"fuse_combine": True}), (True, True, True, {"dpos": False}), (False, False, True, {"dpos": False}),
-    (True, True, True, {"aux_after": "up2"}), (True, True, True, {"aux_after": "warp"}), (False, False, True, {"aux_after": "warp"})])
+    (True, True, True, {"aux_after": "up2"}), (True, True, True, {"reg_coarse": True}), (False, False, True, {"reg_coarse": True}), (True, True, True, {"aux_after": "warp"}), (False, False, True, {"aux_after": "warp"})])
 def test_plan_golden(PF, multi_stream, graph, fuse_reg, kw):
     g = load_golden("hot_path_3lvl")
     total, latent = int(g["total_levels"]), int(g["latent_levels"])
@@ -695,6 +695,40 @@ def test_warp_dpos_forward_and_streaming_backward_match_gather_backward(PF):
         g3 = torch.ones_like(f)
         _lib.check(L.pulpo_l2reg_fwd_bwd(vp(f), 0.025, vp(reg), vp(gout), vp(dpos), vp(g3), 1, vp(ws), ws.numel(), B, 3, D0, D1, D2, st))
         assert_grad_close(g3.cpu().numpy(), (freg.grad + gout * dpos + 1).cpu().numpy(), "fused l2reg grad, accumulate")
+
+
+def test_l2reg_of_upsampled_field_closed_form_on_coarse_grid(PF):
+    """pulpo_l2reg_up2_fwd_bwd: L2_reg(ResizeTransform(1/2)(v)) and its gradient w.r.t. v, evaluated on the coarse grid,
+    against the composition of the separate kernels (x2 resize -> L2_reg -> autograd), and the fused resize adjoint
+    pulpo_resize_up2_bwd_dpos against product + adjoint.  Ragged / minimal / vectorisable shapes, batches."""
+    import ctypes
+    from pulpo_b200 import _lib, synthetic as syn
+    L = _lib.lib()
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for shape, B, amp in [((6, 8, 10), 2, 3.0), ((2, 2, 2), 1, 1.0), ((3, 5, 4), 1, 40.0), ((20, 24, 28), 1, 9.0), ((40, 48, 56), 1, 21.0), ((1, 3, 2), 2, 2.0)]:
+        v = syn.make_field(shape, 7, batch=B, max_abs=amp).cuda()
+        vr = v.clone().requires_grad_(True)
+        ref = PF.l2_reg(PF.resize_up(vr, 2, 2.0), 0.025)
+        ref.backward()
+        ws = torch.zeros(L.pulpo_reduce_ws_bytes(), dtype=torch.uint8, device="cuda")
+        scr = torch.full((L.pulpo_l2reg_up2_scratch_bytes(B, 3, *shape) // 4,), float("nan"), device="cuda")
+        out = torch.zeros((), device="cuda")
+        for acc in (0, 0, 1):
+            g = torch.full_like(v, 2.0)
+            _lib.check(L.pulpo_l2reg_up2_fwd_bwd(vp(v), 0.025, vp(out), vp(g), acc, vp(scr), scr.numel() * 4, vp(ws), ws.numel(),
+                                                 B, 3, *shape, st))
+            assert_loss_close(out.item(), ref.item(), "coarse-grid l2reg value %s" % (shape,))
+            assert_grad_close(g.cpu().numpy(), (vr.grad + (2.0 if acc else 0.0)).cpu().numpy(), "coarse-grid l2reg grad %s" % (shape,))
+        if shape[2] % 2 == 0 and shape[0] >= 2:
+            full = tuple(2 * s for s in shape)
+            gm, dp = torch.randn(B, 1, *full, device="cuda"), torch.randn(B, 3, *full, device="cuda")
+            want = torch.empty_like(v)
+            prod = (gm * dp).contiguous()
+            _lib.check(L.pulpo_resize_up_bwd(vp(prod), vp(want), 2, 2.0, 0, B, 3, *shape, st))
+            got = torch.full_like(v, 1.5)
+            _lib.check(L.pulpo_resize_up2_bwd_dpos(vp(gm), vp(dp), vp(got), 2.0, 1, B, *shape, st))
+            assert_grad_close(got.cpu().numpy(), (want + 1.5).cpu().numpy(), "fused resize adjoint %s" % (shape,))
 
 
 def test_plan_without_regulariser_dpos_equals_gather_backward(PF):
