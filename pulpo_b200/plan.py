@@ -57,8 +57,8 @@ class HotPathPlan:
         # backward (second position chain, second round of corner gathers), regulariser inside the warp kernels.
         self.dpos = bool(dpos) and (self.fuse_reg or not with_reg)
         # pyramid combination (and its adjoint) inside the integration launches: fewer launches (25 instead of 31) but
-        # measured slower (0.936 vs 0.916 ms at config 2): the in-kernel phases run on the cooperative grid's 113 k / 75 k
-        # threads and are latency-bound, while the separate small launches overlap with the aux stream's work
+        # measured slower (0.70 vs 0.68 ms at config 2, re-measured with the 1.4 us barriers): the in-kernel phases run on
+        # the cooperative grid's 113 k / 75 k threads and are latency-bound
         self.fuse_combine = bool(fuse_combine)
         self.dev = dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.lib = _lib.lib()

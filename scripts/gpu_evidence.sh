@@ -18,7 +18,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     $cmd > $out/ncu_$tag.log 2>&1
 echo "ncu launches rc=$?"
 # the first step runs eagerly: its launches are one of each kernel of the step, coarse levels first
-ncu --set full --clock-control none --import-source on -k regex:'vecint_|ncc_tma_kernel|warp3d_|up2_' -c 24 -f \
+ncu --set full --clock-control none --import-source on -k regex:'vecint_|ncc_tma_kernel|warp3d_|up2_|l2reg_fwd_bwd' -c 28 -f \
     -o $out/full_${tag} $cmd > $out/ncu_full_$tag.log 2>&1
 echo "ncu full rc=$?"; tail -2 $out/ncu_full_$tag.log
 python - <<PY
