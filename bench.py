@@ -566,6 +566,13 @@ def run_ours(args):
     # warp kernels do not pay again); otherwise the sum of the per-call algorithmic bytes of one step
     algo_bpv = SURVEY_BYTES_PER_VOXEL.get(args.workload, step_algo_bytes / float(B * nvox))
 
+    selfcheck = None
+    if world > 1 and not args.no_selfcheck:
+        try:
+            selfcheck = multi_gpu_selfcheck(dev, rank, world)
+        except Exception as e:  # pragma: no cover
+            selfcheck = {"ok": False, "error": repr(e)}
+
     if rank == 0:
         cb = None
         if world == 1 and not args.no_cpu_baseline:
@@ -600,6 +607,8 @@ def run_ours(args):
         }
         if cb is not None:
             line["cpu_baseline"] = cb
+        if selfcheck is not None:
+            line["selfcheck"] = selfcheck
         if world == 1 and not args.no_cpu_baseline:
             try:
                 ms_t = torch_cuda_baseline(dev, (x_h, y_h, d_h, m_h, s_h), total)
@@ -612,6 +621,58 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
 
+
+
+# ------------------------------------------------------------------------------------------ multi-GPU self-check
+def multi_gpu_selfcheck(dev, rank, world):
+    """N > 1 only, outside every timed region: the MC-sample sharding of config 3 at 32^3 with the real kernels over
+    NCCL -- Philox sampler + forward plan + streaming statistics per sample, samples dealt round-robin to the ranks
+    (ragged: 2 W + 1 of them), flat all_to_all / reduce_scatter / gather reduction to rank 0 -- against the same samples
+    run on rank 0 alone (the noise of sample i does not depend on the rank that draws it).  This is the content of
+    tests/test_gpu_multirank.py, which a 1-GPU test box has to skip.  Every rank executes the same collectives in the
+    same order; the comparison itself is rank-local."""
+    import torch
+    import torch.distributed as dist
+    from pulpo_b200 import mc, synthetic as syn
+    from pulpo_b200.plan import HotPathPlan
+
+    size, total, latent, n_samples = [32, 32, 32], 4, 3, 2 * world + 1
+    solo = [dist.new_group([r]) for r in range(world)][rank]      # collective: every rank creates every group
+    x, y, dfs, mus, sgs = syn.make_hot_path_inputs(size, total, latent, seed=3)
+    x, y = x.to(dev), y.to(dev)
+    mu = {l: dfs[l].to(dev) for l in dfs}
+    sg = {l: (0.3 * sgs[l]).to(dev) for l in dfs}
+
+    def job(r, w, group):
+        plan = HotPathPlan(size, total, latent, batch=1, device=dev, with_reg=False)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        sampler = mc.PhiloxSampler(mu, sg, seed=5, first_id=r, id_stride=w, count_dev=cnt)
+        plan.run_forward(x, sampler.z)
+        bufs = {"moved0": plan.moved[0][0], "final0": plan.final[0][0], "final1": plan.final[1][0]}
+        stats = mc.StreamingStats(bufs, targets={"moved0": y[0]})
+        stats.count_dev = cnt
+        stats.reset()
+        for _ in mc.shard_samples(n_samples, r, w):
+            sampler.draw()
+            plan.run_forward(x, sampler.z)
+            stats.update()
+            stats.count += 1
+        return stats.reduce_to_maps([len(mc.shard_samples(n_samples, q, w)) for q in range(w)], group=group, dst=0)
+
+    got = job(rank, world, None)
+    torch.cuda.synchronize()
+    out = {"what": "config-3 sharding at 32^3: %d Philox samples over %d ranks, NCCL all_to_all + reduce_scatter + gather "
+                   "to rank 0, vs the same samples on rank 0 alone" % (n_samples, world), "ranks": world}
+    if rank == 0:
+        one = job(0, 1, solo)
+        torch.cuda.synchronize()
+        worst = 0.0
+        for k in one:
+            a, b = got[k].double(), one[k].double()
+            worst = max(worst, float(((a - b).abs() / (1e-6 + 1e-4 * b.abs())).max()))
+        out.update(ok=bool(worst <= 1.0), maps=sorted(one.keys()), worst_err_over_tol=worst, tol="rtol 1e-4, atol 1e-6")
+    dist.barrier()
+    return out
 
 
 # ------------------------------------------------------------------------------------------ shared rank plumbing
@@ -931,6 +992,7 @@ def main():
     ap.add_argument("--samples", type=int, default=128, help="mc128: MC deformation samples per pair (dealt to the ranks)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfcheck", action="store_true", help="N > 1: skip the multi-GPU MC-sharding self-check (untimed)")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":
