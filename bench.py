@@ -671,8 +671,7 @@ def multi_gpu_selfcheck(dev, rank, world):
             a, b = got[k].double(), one[k].double()
             worst = max(worst, float(((a - b).abs() / (1e-6 + 1e-4 * b.abs())).max()))
         out.update(ok=bool(worst <= 1.0), maps=sorted(one.keys()), worst_err_over_tol=worst, tol="rtol 1e-4, atol 1e-6")
-    dist.barrier()
-    return out
+    return out    # no collective after the rank-local comparison: a failure on rank 0 cannot leave the others waiting
 
 
 # ------------------------------------------------------------------------------------------ shared rank plumbing
