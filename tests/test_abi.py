@@ -76,3 +76,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/pulpo_b200.h compiles as pedantic C99 (no C++, no torch types) and a
+    plain C program links against the shared library and calls it (no compute call without a GPU)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from pulpo_b200 import build as b
+    src = tmp_path / "use_abi.c"
+    src.write_text('#include "pulpo_b200.h"\n#include <string.h>\n'
+                   'int main(void) { return (pulpo_version() >= 100 && strcmp(pulpo_strerror(0), "ok") == 0 &&\n'
+                   '                         pulpo_warp3d_fwd(0, 0, 0, 0, 1, 1, 4, 4, 4, 0, 0) == PULPO_ERR_NULL_POINTER) ? 0 : 1; }\n')
+    inc, libdir = os.path.join(ROOT, "include"), os.path.dirname(b.LIB)
+    exe = tmp_path / "use_abi"
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                           "-L", libdir, "-lpulpo_b200", "-Wl,-rpath," + libdir])
+    assert subprocess.run([str(exe)]).returncode == 0
